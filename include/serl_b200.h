@@ -1,0 +1,180 @@
+/* libserl_b200 - C ABI of the B200-native DrQ/SAC learner hot path.
+ *
+ * The reference (rail-berkeley/serl) has no FFI: its boundary is the Python API of `serl_launcher`
+ * (SURVEY.md §8b).  This header is the C-ABI underneath this repo's Python mirror of that API
+ * (serl_b200/): plain pointers and sizes, an explicit CUDA stream (cudaStream_t passed as void*),
+ * no torch types, no allocation inside the library (callers own all buffers / workspaces).
+ * Every function returns 0 on success or a negative SERL_ERR_* code; serl_last_error() gives the
+ * message for the calling thread.  All pointers are DEVICE pointers unless a name says `host`.
+ *
+ * Citations are relative to /root/reference/serl_launcher/serl_launcher.
+ */
+#ifndef SERL_B200_H_
+#define SERL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SERL_MAX_CAMS 4
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* serl_last_error(void);
+int serl_version(void);                       /* ABI version, bumped on signature changes */
+int serl_device_sm_count(int device);         /* host query used to size persistent grids */
+
+/* ---- replay ring in HBM ---------------------------------------------------------------------
+ * Storage layout of data/replay_buffer.py:41-66 + data/memory_efficient_replay_buffer.py:13-51:
+ * ONE camera frame per slot (frame dedup), per-slot scalars, a validity byte per slot. */
+typedef struct serl_replay_view {
+  const uint8_t* frames[SERL_MAX_CAMS];  /* (capacity, H, W, C) uint8 per camera                   */
+  const float* state;                    /* (capacity, T*S) observations.state                      */
+  const float* next_state;               /* (capacity, T*S) next_observations.state                 */
+  const float* actions;                  /* (capacity, A)                                           */
+  const float* rewards;                  /* (capacity,)                                             */
+  const float* masks;                    /* (capacity,)                                             */
+  const uint8_t* dones;                  /* (capacity,)                                             */
+  const uint8_t* valid;                  /* (capacity,) _is_correct_index                           */
+  int32_t num_cams, height, width, channels, num_stack /*T*/, state_dim /*S*/, action_dim /*A*/;
+  int32_t capacity, size;                /* size = len(buffer): draws are uniform over [0, size)    */
+} serl_replay_view;
+
+typedef struct serl_sample_request {
+  uint64_t seed, step;           /* Philox key / counter words of the index draw (repo spec)         */
+  const uint64_t* step_dev;      /* optional device counter overriding `step` (CUDA-graph replay)     */
+  const int32_t* size_dev;       /* optional device fill level overriding rv->size                    */
+  uint32_t lane_offset;          /* Philox lane of output row 0                                      */
+  int32_t batch;                 /* rows drawn by this call                                          */
+  const int32_t* explicit_idx;   /* optional (batch): gather these slots instead of drawing          */
+  const uint32_t* key_obs;       /* device uint32[2]: JAX key; frame g uses split(key, crop_total)[g] */
+  const uint32_t* key_next;
+  const int32_t* explicit_off_obs;   /* optional (crop_total, 2) [cy, cx] overriding the keys        */
+  const int32_t* explicit_off_next;
+  int32_t crop_total;            /* frames in the whole (possibly concatenated) batch = B_total * T   */
+  int32_t out_row_offset;        /* first output row written by this call (RLPD: demo half offset)    */
+  int32_t padding;               /* DrQ pad (4): offsets in [0, 2*padding]                            */
+} serl_sample_request;
+
+typedef struct serl_batch_out {
+  uint8_t* obs_pix[SERL_MAX_CAMS];   /* (B_total, T, H, W, C) shifted observation frames             */
+  uint8_t* next_pix[SERL_MAX_CAMS];  /* (B_total, T, H, W, C) shifted next-observation frames         */
+  float* obs_state; float* next_state;   /* (B_total, T*S)                                           */
+  float* actions; float* rewards; float* masks; uint8_t* dones;
+  int32_t* idx;                      /* optional (B_total) drawn slots                                */
+  int32_t* off_obs; int32_t* off_next;   /* optional (B_total*T, 2) applied offsets                   */
+  int32_t* status;                   /* device int32, OR-ed with 1 if a draw found no valid slot      */
+} serl_batch_out;
+
+/* Replaces MemoryEfficientReplayBuffer.sample (memory_efficient_replay_buffer.py:91-164) +
+ * ReplayBuffer.get_iterator's device_put (replay_buffer.py:77-90) + _unpack (utils/train_utils.py:44-66)
+ * + batched_random_crop (vision/data_augmentations.py:7-36, agents/continuous/drq.py:244-253). */
+int serl_replay_sample_crop(const serl_replay_view* rv, const serl_sample_request* rq,
+                            const serl_batch_out* out, void* stream);
+
+typedef struct serl_scatter_request {
+  int32_t n;                         /* slot writes, applied independently (no ordering inside a call) */
+  const int32_t* dst_slot;           /* (n)                                                            */
+  const int32_t* src_slot;           /* (n)  >= 0: copy from that ring slot; < 0: from staging row k    */
+  const uint8_t* frames[SERL_MAX_CAMS];  /* staging (n, H, W, C)                                       */
+  const float* state; const float* next_state; const float* actions;
+  const float* rewards; const float* masks; const uint8_t* dones;
+  const uint8_t* valid;              /* (n) validity byte to store                                     */
+} serl_scatter_request;
+
+/* Device side of MemoryEfficientReplayBuffer.insert (memory_efficient_replay_buffer.py:53-89,
+ * replay_buffer.py:71-75): applies slot writes staged by the host ring logic. */
+int serl_replay_scatter(const serl_replay_view* rv, const serl_scatter_request* rq, void* stream);
+int serl_counter_add(uint64_t* counter, uint64_t inc, void* stream);   /* device-resident step counters */
+int serl_replay_set_valid(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n, void* stream);
+
+/* ---- JAX-compatible key schedule and random fills ---------------------------------------------
+ * Key slots written by serl_rng_schedule (uint32[2] each), following SACAgent.update's split order
+ * (agents/continuous/sac.py:137,152,197,224,288; common/common.py:198-200; drq.py:307-308). */
+enum {
+  SERL_KEY_CROP_OBS = 0, SERL_KEY_CROP_NEXT = 1, SERL_KEY_CRITIC_NEXT = 2, SERL_KEY_CRITIC_SUBSAMPLE = 3,
+  SERL_KEY_ACTOR_DROPOUT = 4, SERL_KEY_ACTOR_SAMPLE = 5, SERL_KEY_TEMP_NEXT = 6, SERL_NUM_KEYS = 8
+};
+int serl_rng_schedule(uint32_t* rng_state, uint32_t* keys, int do_aug, int do_update, void* stream);
+int serl_normal_fill(const uint32_t* key, float* out, int n, void* stream);            /* jax.random.normal   */
+int serl_dropout_mask_fill(const uint32_t* key, uint32_t fold, float keep, uint8_t* mask, int n, void* stream);
+int serl_subsample_idx(const uint32_t* key, int ensemble, int32_t* out /*2*/, void* stream); /* sac.py:153-158 */
+
+/* Host mirrors of the integer RNG specs (same code compiled for the host; usable without a GPU). */
+int serl_host_rng_schedule(uint32_t* rng_state_host, uint32_t* keys_host, int do_aug, int do_update);
+int serl_host_crop_offsets(const uint32_t key_host[2], int n_frames, int padding, int32_t* out_host);
+int serl_host_draw_indices(uint64_t seed, uint64_t step, uint32_t lane_offset, int batch, int size,
+                           const uint8_t* valid_host, int32_t* out_host);
+int serl_host_threefry_split(const uint32_t key_host[2], int n, uint32_t* out_host);
+int serl_host_random_bits(const uint32_t key_host[2], int size, uint32_t* out_host);
+
+/* ---- frozen ResNet-10 trunk, fp32 build (vision/resnet_v1.py:217-286,129-156) ------------------ */
+/* NHWC conv, HWIO weights, explicit low/high zero padding.  x_is_u8: x is uint8 and the ImageNet
+ * normalisation (x/255 - mean)/std of resnet_v1.py:222-224 is fused into the operand load. */
+int serl_conv2d_nhwc_f32(const void* x, int x_is_u8, const float* w, float* y, int N, int Hi, int Wi, int Ci,
+                         int Co, int kh, int kw, int stride, int pad_lo, int pad_hi, void* stream);
+/* GroupNorm (flax statistics), optional residual add and ReLU; y may alias x. */
+int serl_groupnorm_nhwc_f32(const float* x, float* y, const float* scale, const float* bias, const float* residual,
+                            int N, int HW, int C, int groups, float eps, int relu, void* stream);
+int serl_maxpool3x3s2_nhwc_f32(const float* x, float* y, int N, int Hi, int Wi, int C, void* stream);
+
+/* ---- dense algebra for the trainable heads (fp32) ---------------------------------------------- */
+typedef struct serl_gemm_desc {
+  const float* A; const float* B; float* C; const float* bias;
+  float* workspace; size_t workspace_bytes;     /* split-K / batch-reduce partials */
+  int32_t M, N, K, Z;
+  int64_t sAz, sAm, sAk, sBz, sBk, sBn, sCz, sBiasZ;
+  int32_t ldc;
+  int32_t accumulate;                           /* C += result                                     */
+  int32_t reduce_z;                             /* single C = sum over z                           */
+} serl_gemm_desc;
+int serl_gemm_f32(const serl_gemm_desc* d, void* stream);
+
+/* SpatialLearnedEmbeddings (vision/resnet_v1.py:81-116) + Dropout (resnet_v1.py:352) */
+int serl_sle_fwd(const float* feat, const float* kernel, const uint8_t* keep_mask, float keep, float* out,
+                 int N, int P, int C, int F, int ld_out, void* stream);
+int serl_sle_bwd_kernel_grad(const float* feat, const float* dout, float* dkernel, float* workspace, size_t workspace_bytes,
+                             int N, int P, int C, int F, int ld_dout, void* stream);
+/* LayerNorm(eps, fast variance) + tanh, rows grouped for vmapped (ensemble) parameters (networks/mlp.py:26-31) */
+int serl_layernorm_tanh_fwd(const float* z, int ld_z, const float* scale, const float* bias, int rows_per_group, int group_stride,
+                            float* out, int ld_out, float* xhat, float* rstd, int R, int D, float eps, void* stream);
+int serl_layernorm_tanh_bwd(const float* dt, int ld_dt, const float* t, int ld_t, const float* xhat, const float* rstd,
+                            const float* scale, int rows_per_group, int group_stride, float* dz, float* dy,
+                            float* dscale, float* dbias, int R, int D, void* stream);
+int serl_colsum_f32(const float* x, float* out, int groups, int rows, int D, long long ld, int accumulate, void* stream);
+int serl_copy2d_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int R, int D, void* stream);
+int serl_fill_f32(float* x, float v, int n, void* stream);
+
+/* ---- SAC losses (agents/continuous/sac.py:118-234, networks/actor_critic_nets.py:230-272) -------- */
+int serl_tanh_gaussian_fwd(const float* mu, const float* log_std, const float* eps, float std_min, float std_max,
+                           float* act, int ld_act, float* logp, float* u_out, float* std_out, int B, int A,
+                           int deterministic, void* stream);
+int serl_critic_loss(const float* q, const float* q_next, const int32_t* sub, int n_sub, const float* rewards,
+                     const float* masks, const float* logp_next, const float* lagrange, int backup_entropy, float gamma,
+                     float grad_scale, float* target_q, float* dq, float* info /*3*/, int E, int B, void* stream);
+int serl_actor_loss(const float* q, const float* logp, const float* lagrange, const float* da, int ld_da, const float* act,
+                    int ld_act, const float* std, const float* log_std, const float* eps, float std_min, float std_max,
+                    float grad_scale, float* dmu, float* dlogstd, float* info /*3*/, int E, int B, int A, void* stream);
+int serl_temperature_loss(const float* logp, const float* lagrange, float target_entropy, float grad_scale,
+                          float* dlagrange, float* info /*1*/, int B, void* stream);
+
+/* ---- optimizer (common/common.py:124-168, common/optimizers.py:6-56) --------------------------- */
+typedef struct serl_adam_desc {
+  float* params; float* target; float* m; float* v; const float* grad;
+  int32_t n;
+  int32_t seg_end[3];        /* flat layout: group 0 = critic tx, 1 = actor tx, 2 = temperature tx */
+  int32_t live[3];           /* network updated this call (else its gradient is zero)             */
+  int32_t* counts;           /* device int32[3]: optax counts, incremented by the call            */
+  float lr[3]; int32_t warmup[3];
+  float b1, b2, eps, tau;
+  int32_t polyak;            /* soft target update after the step                                 */
+  float* lr_out;             /* optional device float[3]                                          */
+} serl_adam_desc;
+int serl_adam_polyak(const serl_adam_desc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SERL_B200_H_ */

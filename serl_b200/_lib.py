@@ -1,0 +1,128 @@
+"""ctypes binding of libserl_b200.so (the C-ABI declared in include/serl_b200.h).
+
+There is NO fallback: if the library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libserl_b200.so")
+MAX_CAMS = 4
+ABI_VERSION = 1
+
+(KEY_CROP_OBS, KEY_CROP_NEXT, KEY_CRITIC_NEXT, KEY_CRITIC_SUBSAMPLE, KEY_ACTOR_DROPOUT, KEY_ACTOR_SAMPLE,
+ KEY_TEMP_NEXT) = range(7)
+NUM_KEYS = 8
+
+vp, i32, i64, u32, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float
+
+
+class ReplayView(C.Structure):
+    _fields_ = [("frames", vp * MAX_CAMS), ("state", vp), ("next_state", vp), ("actions", vp), ("rewards", vp),
+                ("masks", vp), ("dones", vp), ("valid", vp),
+                ("num_cams", i32), ("height", i32), ("width", i32), ("channels", i32), ("num_stack", i32),
+                ("state_dim", i32), ("action_dim", i32), ("capacity", i32), ("size", i32)]
+
+
+class SampleRequest(C.Structure):
+    _fields_ = [("seed", u64), ("step", u64), ("step_dev", vp), ("size_dev", vp), ("lane_offset", u32), ("batch", i32), ("explicit_idx", vp),
+                ("key_obs", vp), ("key_next", vp), ("explicit_off_obs", vp), ("explicit_off_next", vp),
+                ("crop_total", i32), ("out_row_offset", i32), ("padding", i32)]
+
+
+class BatchOut(C.Structure):
+    _fields_ = [("obs_pix", vp * MAX_CAMS), ("next_pix", vp * MAX_CAMS), ("obs_state", vp), ("next_state", vp),
+                ("actions", vp), ("rewards", vp), ("masks", vp), ("dones", vp), ("idx", vp), ("off_obs", vp),
+                ("off_next", vp), ("status", vp)]
+
+
+class ScatterRequest(C.Structure):
+    _fields_ = [("n", i32), ("dst_slot", vp), ("src_slot", vp), ("frames", vp * MAX_CAMS), ("state", vp),
+                ("next_state", vp), ("actions", vp), ("rewards", vp), ("masks", vp), ("dones", vp), ("valid", vp)]
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [("A", vp), ("B", vp), ("C", vp), ("bias", vp), ("workspace", vp), ("workspace_bytes", C.c_size_t),
+                ("M", i32), ("N", i32), ("K", i32), ("Z", i32),
+                ("sAz", i64), ("sAm", i64), ("sAk", i64), ("sBz", i64), ("sBk", i64), ("sBn", i64), ("sCz", i64),
+                ("sBiasZ", i64), ("ldc", i32), ("accumulate", i32), ("reduce_z", i32)]
+
+
+class AdamDesc(C.Structure):
+    _fields_ = [("params", vp), ("target", vp), ("m", vp), ("v", vp), ("grad", vp), ("n", i32), ("seg_end", i32 * 3),
+                ("live", i32 * 3), ("counts", vp), ("lr", f32 * 3), ("warmup", i32 * 3), ("b1", f32), ("b2", f32),
+                ("eps", f32), ("tau", f32), ("polyak", i32), ("lr_out", vp)]
+
+
+_PROTOS = {
+    "serl_replay_sample_crop": [C.POINTER(ReplayView), C.POINTER(SampleRequest), C.POINTER(BatchOut), vp],
+    "serl_replay_scatter": [C.POINTER(ReplayView), C.POINTER(ScatterRequest), vp],
+    "serl_replay_set_valid": [vp, vp, vp, C.c_int, vp],
+    "serl_counter_add": [vp, u64, vp],
+    "serl_rng_schedule": [vp, vp, C.c_int, C.c_int, vp],
+    "serl_normal_fill": [vp, vp, C.c_int, vp],
+    "serl_dropout_mask_fill": [vp, u32, f32, vp, C.c_int, vp],
+    "serl_subsample_idx": [vp, C.c_int, vp, vp],
+    "serl_host_rng_schedule": [vp, vp, C.c_int, C.c_int],
+    "serl_host_crop_offsets": [vp, C.c_int, C.c_int, vp],
+    "serl_host_draw_indices": [u64, u64, u32, C.c_int, C.c_int, vp, vp],
+    "serl_host_threefry_split": [vp, C.c_int, vp],
+    "serl_host_random_bits": [vp, C.c_int, vp],
+    "serl_conv2d_nhwc_f32": [vp, C.c_int, vp, vp] + [C.c_int] * 10 + [vp],
+    "serl_groupnorm_nhwc_f32": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, C.c_int, vp],
+    "serl_maxpool3x3s2_nhwc_f32": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "serl_gemm_f32": [C.POINTER(GemmDesc), vp],
+    "serl_sle_fwd": [vp, vp, vp, f32, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "serl_sle_bwd_kernel_grad": [vp, vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "serl_layernorm_tanh_fwd": [vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int, f32, vp],
+    "serl_layernorm_tanh_bwd": [vp, C.c_int, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, C.c_int, C.c_int, vp],
+    "serl_colsum_f32": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int, vp],
+    "serl_copy2d_f32": [vp, C.c_longlong, vp, C.c_longlong, C.c_int, C.c_int, vp],
+    "serl_fill_f32": [vp, f32, C.c_int, vp],
+    "serl_tanh_gaussian_fwd": [vp, vp, vp, f32, f32, vp, C.c_int, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp],
+    "serl_critic_loss": [vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, f32, f32, vp, vp, vp, C.c_int, C.c_int, vp],
+    "serl_actor_loss": [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, f32, f32, f32, vp, vp, vp, C.c_int, C.c_int,
+                        C.c_int, vp],
+    "serl_temperature_loss": [vp, vp, f32, f32, vp, vp, C.c_int, vp],
+    "serl_adam_polyak": [C.POINTER(AdamDesc), vp],
+}
+EXPORTS = sorted(list(_PROTOS) + ["serl_last_error", "serl_version", "serl_device_sm_count"])
+
+_lib = None
+
+
+class SerlError(RuntimeError):
+    pass
+
+
+def load():
+    """Loads the shared library; raises (no CPU fallback) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SerlError(f"{LIB_PATH} not found - run `python -m serl_b200.build` (or __graft_entry__.build()). "
+                        "serl_b200 has no fallback path.")
+    lib = C.CDLL(LIB_PATH)
+    lib.serl_last_error.restype = C.c_char_p
+    lib.serl_last_error.argtypes = []
+    lib.serl_version.restype = C.c_int
+    lib.serl_device_sm_count.argtypes = [C.c_int]
+    for name, args in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    if lib.serl_version() != ABI_VERSION:
+        raise SerlError(f"libserl_b200 ABI {lib.serl_version()} != binding {ABI_VERSION}; rebuild")
+    _lib = lib
+    return lib
+
+
+def call(name: str, *args):
+    lib = load()
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise SerlError(f"{name} failed ({rc}): {lib.serl_last_error().decode()}")
+    return rc

@@ -1,0 +1,39 @@
+// Library-level entry points: error reporting, version, device queries.
+#include <cstdarg>
+#include <cstdio>
+
+#include "common.cuh"
+#include "serl_b200.h"
+
+namespace serl {
+
+static thread_local char g_err[512] = "";
+
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_last_error("%s: %s", what, cudaGetErrorString(e));
+    return SERL_ERR_CUDA;
+  }
+  return SERL_OK;
+}
+
+}  // namespace serl
+
+extern "C" const char* serl_last_error(void) { return serl::g_err; }
+extern "C" int serl_version(void) { return 1; }
+extern "C" int serl_device_sm_count(int device) {
+  int n = 0;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+    serl::set_last_error("serl_device_sm_count: no CUDA device %d", device);
+    return SERL_ERR_CUDA;
+  }
+  return n;
+}

@@ -1,0 +1,379 @@
+// Replay minibatch sampler for the HBM-resident frame-dedup ring.
+//
+// ONE kernel per (buffer, step): draws uniform indices (Philox4x32-10 + Lemire, bounded redraw on
+// invalid slots), gathers (s, a, r, s', mask, done) and the T+1 adjacent camera frames, and applies
+// the DrQ random shift (edge-replicating crop) on the way out.  Frames are staged global->shared with
+// a TMA bulk copy (cp.async.bulk, 16-byte aligned row ranges) and written back with 128-bit stores.
+//
+// Replaces (reference, relative to serl_launcher/serl_launcher):
+//   data/memory_efficient_replay_buffer.py:91-164  sample()      (host python loop + numpy gather)
+//   data/replay_buffer.py:77-90                    get_iterator  (host->device copy of the batch)
+//   utils/train_utils.py:44-66                     _unpack
+//   vision/data_augmentations.py:7-36 + agents/continuous/drq.py:244-253  batched_random_crop
+// Semantics are restated in oracle/replay.py (draw_indices, gather_packed, random_shift) and
+// oracle/jax_prng.py (crop_offsets).
+#include "common.cuh"
+#include "serl_b200.h"
+
+namespace serl {
+
+constexpr int kBandRows = 32;
+constexpr int kSamplerThreads = 128;
+constexpr int kMaxDrawAttempts = 64;
+
+struct SamplerArgs {
+  serl_replay_view rv;
+  // draw
+  uint64_t seed, step;
+  const uint64_t* step_dev;      // optional device counter overriding `step` (CUDA-graph replays)
+  const int32_t* size_dev;       // optional device fill level overriding rv.size
+  uint32_t lane_offset;          // philox lane of row 0 (independent of out_row_offset)
+  const int32_t* explicit_idx;   // optional (B): skip the draw
+  // crop
+  const uint32_t* key_obs;       // device, 2 words: JAX key whose split(key, crop_total)[g] seeds frame g
+  const uint32_t* key_next;
+  const int32_t* explicit_off_obs;   // optional (crop_total, 2) [cy, cx]
+  const int32_t* explicit_off_next;
+  int crop_total;                // total frames in the (possibly concatenated) batch = B_total * T
+  int out_row_offset;            // first output row of this launch inside the B_total-row outputs
+  int padding;
+  // outputs (B_total rows each)
+  uint8_t* obs_pix[SERL_MAX_CAMS];    // (B_total, T, H, W, C)
+  uint8_t* next_pix[SERL_MAX_CAMS];
+  float* obs_state; float* next_state; float* actions; float* rewards; float* masks;
+  uint8_t* dones; int32_t* idx_out; int32_t* off_obs_out; int32_t* off_next_out;   // off_*: (B_total*T, 2)
+  int32_t* status;               // device int, OR-ed with 1 when a draw fails
+  int batch;                     // rows produced by this launch
+};
+
+__device__ inline int draw_index(const SamplerArgs& a, uint32_t lane) {
+  const uint32_t size = (uint32_t)(a.size_dev ? *a.size_dev : a.rv.size);
+  const uint64_t step = a.step_dev ? *a.step_dev : a.step;
+  if (size == 0) return -1;
+  const uint32_t thresh = (uint32_t)((0x100000000ull - size) % size);
+  for (int att = 0; att < kMaxDrawAttempts; ++att) {
+    u32x4 r = philox4x32_10(u32x4{lane, (uint32_t)att, (uint32_t)step, (uint32_t)(step >> 32)},
+                            (uint32_t)a.seed, (uint32_t)(a.seed >> 32));
+    uint64_t m = (uint64_t)r.x * size;
+    if ((uint32_t)m < thresh) continue;
+    uint32_t idx = (uint32_t)(m >> 32);
+    if (a.rv.valid[idx]) return (int)idx;
+  }
+  return -1;
+}
+
+__device__ inline void crop_offset_for(const uint32_t* key, const int32_t* expl, int crop_total, int g,
+                                       int span, int* cy, int* cx) {
+  if (expl) { *cy = expl[2 * g]; *cx = expl[2 * g + 1]; return; }
+  u32x2 k = jax_split_at(u32x2{key[0], key[1]}, (uint32_t)crop_total, (uint32_t)g);
+  jax_randint2(k, (uint32_t)span, cy, cx);
+}
+
+__device__ inline void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ inline void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ inline void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t addr = (uint32_t)__cvta_generic_to_shared(bar), done = 0;
+  while (!done) {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(addr), "r"(phase) : "memory");
+  }
+}
+__device__ inline void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes),
+                 "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+// grid: x = band, y = (cam, which, t) flattened, z = row i.   kFast: row_bytes % 16 == 0.
+template <bool kFast>
+__global__ void __launch_bounds__(kSamplerThreads) sample_gather_crop_kernel(const SamplerArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ int s_idx, s_cy, s_cx;
+
+  const serl_replay_view& rv = a.rv;
+  const int T = rv.num_stack, H = rv.height, W = rv.width, C = rv.channels;
+  const int row_bytes = W * C;
+  const int band = blockIdx.x;
+  int yz = blockIdx.y;
+  const int t = yz % T; yz /= T;
+  const int which = yz & 1; yz >>= 1;
+  const int cam = yz;
+  const int i = blockIdx.z;
+  const int out_row = a.out_row_offset + i;
+  const int g = out_row * T + t;                         // frame index inside the batch
+  const int y0 = band * kBandRows;
+  const int rows = min(kBandRows, H - y0);
+  const bool leader = (cam == 0 && which == 0 && t == 0 && band == 0);
+
+  if (threadIdx.x == 0) {
+    int idx = a.explicit_idx ? a.explicit_idx[i] : draw_index(a, a.lane_offset + (uint32_t)i);
+    int cy, cx;
+    crop_offset_for(which ? a.key_next : a.key_obs, which ? a.explicit_off_next : a.explicit_off_obs,
+                    a.crop_total, g, 2 * a.padding + 1, &cy, &cx);
+    s_idx = idx; s_cy = cy; s_cx = cx;
+    if (idx < 0) atomicOr(a.status, 1);
+    if (cam == 0 && band == 0) {                          // record offsets once per (which, t)
+      int32_t* o = which ? a.off_next_out : a.off_obs_out;
+      if (o) { o[2 * g] = cy; o[2 * g + 1] = cx; }
+    }
+    if (kFast) { mbar_init(&bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  }
+  __syncthreads();
+  const int idx = s_idx, cy = s_cy, cx = s_cx;
+  if (idx < 0) return;
+
+  // ---- small fields: one CTA per row ---------------------------------------------------------
+  if (leader) {
+    const int ns = T * rv.state_dim;
+    for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+      a.obs_state[(size_t)out_row * ns + k] = rv.state[(size_t)idx * ns + k];
+      a.next_state[(size_t)out_row * ns + k] = rv.next_state[(size_t)idx * ns + k];
+    }
+    for (int k = threadIdx.x; k < rv.action_dim; k += blockDim.x)
+      a.actions[(size_t)out_row * rv.action_dim + k] = rv.actions[(size_t)idx * rv.action_dim + k];
+    if (threadIdx.x == 0) {
+      a.rewards[out_row] = rv.rewards[idx];
+      a.masks[out_row] = rv.masks[idx];
+      a.dones[out_row] = rv.dones[idx];
+      if (a.idx_out) a.idx_out[out_row] = idx;
+    }
+  }
+
+  // ---- frame band: slot idx - T + t + which, rows clamp(y + cy - pad) ---------------------------
+  const size_t frame_bytes = (size_t)H * row_bytes;
+  const int slot = idx - T + t + which;
+  const uint8_t* src = rv.frames[cam] + (size_t)slot * frame_bytes;
+  uint8_t* dst = (which ? a.next_pix[cam] : a.obs_pix[cam]) + ((size_t)g * H + y0) * row_bytes;
+  const int dy = cy - a.padding;
+  const int sh = (cx - a.padding) * C;                   // byte shift inside a row
+  const int r_lo = min(max(y0 + dy, 0), H - 1);
+  const int r_hi = min(max(y0 + rows - 1 + dy, 0), H - 1);
+
+  if (kFast) {
+    const uint32_t nbytes = (uint32_t)(r_hi - r_lo + 1) * row_bytes;
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, nbytes);
+      bulk_g2s(smem, src + (size_t)r_lo * row_bytes, nbytes, &bar);
+    }
+    mbar_wait(&bar, 0);
+    const int cpr = row_bytes >> 4;                      // 16-byte chunks per row
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(smem);
+    for (int q = threadIdx.x; q < rows * cpr; q += blockDim.x) {
+      const int yl = q / cpr, j = q - yl * cpr;
+      const int r = min(max(y0 + yl + dy, 0), H - 1) - r_lo;
+      const int b0 = j * 16;
+      const int a0 = b0 + sh;                            // first source byte if no clamping
+      uint4 v;
+      if (a0 >= 0 && a0 + 16 <= row_bytes) {
+        const int base = r * row_bytes + a0;
+        const int wi = base >> 2, bs = (base & 3) * 8;
+        uint32_t w0 = s32[wi], w1 = s32[wi + 1], w2 = s32[wi + 2], w3 = s32[wi + 3], w4 = s32[wi + 4];
+        v.x = __funnelshift_r(w0, w1, bs); v.y = __funnelshift_r(w1, w2, bs);
+        v.z = __funnelshift_r(w2, w3, bs); v.w = __funnelshift_r(w3, w4, bs);
+      } else {
+        uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+          const int ob = b0 + b;
+          const int x = ob / C, ch = ob - x * C;
+          const int xs = min(max(x + cx - a.padding, 0), W - 1);
+          o[b >> 2] |= (uint32_t)smem[r * row_bytes + xs * C + ch] << ((b & 3) * 8);
+        }
+        v = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)yl * row_bytes + b0),
+                   "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+  } else {
+    for (int q = threadIdx.x; q < rows * row_bytes; q += blockDim.x) {
+      const int yl = q / row_bytes, ob = q - yl * row_bytes;
+      const int r = min(max(y0 + yl + dy, 0), H - 1);
+      const int x = ob / C, ch = ob - x * C;
+      const int xs = min(max(x + cx - a.padding, 0), W - 1);
+      dst[(size_t)yl * row_bytes + ob] = src[(size_t)r * row_bytes + xs * C + ch];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Replay ring writes (insert path).  The ring bookkeeping (cursor, episode-start fillers, validity)
+// is host logic mirroring data/memory_efficient_replay_buffer.py:53-89; these kernels apply a batch
+// of slot writes staged in device memory.
+// ---------------------------------------------------------------------------------------------
+struct ScatterArgs {
+  serl_replay_view rv;           // frames etc. are written (const_cast on the device side)
+  int n;                         // slot writes
+  const int32_t* dst_slot;       // (n)
+  const int32_t* src_slot;       // (n) >= 0: copy from ring slot; < 0: from staging row k
+  const uint8_t* st_frames[SERL_MAX_CAMS];   // (n, frame_bytes)
+  const float* st_state; const float* st_next_state; const float* st_actions;
+  const float* st_rewards; const float* st_masks; const uint8_t* st_dones; const uint8_t* st_valid;
+};
+
+// grid: x = chunk of the frame, y = cam, z = write k.  Ordered writes: launch once per dependency level.
+__global__ void __launch_bounds__(256) replay_scatter_kernel(const ScatterArgs a) {
+  const serl_replay_view& rv = a.rv;
+  const int k = blockIdx.z, cam = blockIdx.y;
+  const int dst = a.dst_slot[k], ss = a.src_slot[k];
+  const size_t fb = (size_t)rv.height * rv.width * rv.channels;
+  const uint8_t* s = ss >= 0 ? rv.frames[cam] + (size_t)ss * fb : a.st_frames[cam] + (size_t)k * fb;
+  uint8_t* d = const_cast<uint8_t*>(rv.frames[cam]) + (size_t)dst * fb;
+  if ((fb & 15) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(s);
+    uint4* d4 = reinterpret_cast<uint4*>(d);
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < (fb >> 4); q += (size_t)gridDim.x * blockDim.x)
+      d4[q] = s4[q];
+  } else {
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < fb; q += (size_t)gridDim.x * blockDim.x)
+      d[q] = s[q];
+  }
+  if (cam == 0 && blockIdx.x == 0) {
+    const int ns = rv.num_stack * rv.state_dim;
+    float* st = const_cast<float*>(rv.state); float* nst = const_cast<float*>(rv.next_state);
+    float* ac = const_cast<float*>(rv.actions);
+    for (int e = threadIdx.x; e < ns; e += blockDim.x) {
+      st[(size_t)dst * ns + e] = ss >= 0 ? rv.state[(size_t)ss * ns + e] : a.st_state[(size_t)k * ns + e];
+      nst[(size_t)dst * ns + e] = ss >= 0 ? rv.next_state[(size_t)ss * ns + e] : a.st_next_state[(size_t)k * ns + e];
+    }
+    for (int e = threadIdx.x; e < rv.action_dim; e += blockDim.x)
+      ac[(size_t)dst * rv.action_dim + e] = ss >= 0 ? rv.actions[(size_t)ss * rv.action_dim + e]
+                                                     : a.st_actions[(size_t)k * rv.action_dim + e];
+    if (threadIdx.x == 0) {
+      const_cast<float*>(rv.rewards)[dst] = ss >= 0 ? rv.rewards[ss] : a.st_rewards[k];
+      const_cast<float*>(rv.masks)[dst] = ss >= 0 ? rv.masks[ss] : a.st_masks[k];
+      const_cast<uint8_t*>(rv.dones)[dst] = ss >= 0 ? rv.dones[ss] : a.st_dones[k];
+      const_cast<uint8_t*>(rv.valid)[dst] = a.st_valid[k];
+    }
+  }
+}
+
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) { if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += inc; }
+
+__global__ void replay_set_valid_kernel(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) valid[slots[k]] = vals[k];
+}
+
+}  // namespace serl
+
+using namespace serl;
+
+static int check_view(const serl_replay_view* rv) {
+  if (!rv || rv->num_cams < 1 || rv->num_cams > SERL_MAX_CAMS || rv->num_stack < 1 || rv->size < 0 ||
+      rv->size > rv->capacity || rv->height < 1 || rv->width < 1 || rv->channels < 1) {
+    set_last_error("serl_replay: invalid replay view");
+    return SERL_ERR_INVALID;
+  }
+  return SERL_OK;
+}
+
+extern "C" int serl_replay_sample_crop(const serl_replay_view* rv, const serl_sample_request* rq,
+                                       const serl_batch_out* out, void* stream) {
+  if (int e = check_view(rv)) return e;
+  if (!rq || !out || rq->batch < 1 || rq->crop_total < (rq->out_row_offset + rq->batch) * rv->num_stack) {
+    set_last_error("serl_replay_sample_crop: invalid request (batch=%d crop_total=%d)", rq ? rq->batch : -1,
+                   rq ? rq->crop_total : -1);
+    return SERL_ERR_INVALID;
+  }
+  if (!rq->explicit_idx && rv->size <= rv->num_stack) {
+    set_last_error("serl_replay_sample_crop: buffer holds %d slots, need > num_stack", rv->size);
+    return SERL_ERR_INVALID;
+  }
+  if ((!rq->key_obs || !rq->key_next) && (!rq->explicit_off_obs || !rq->explicit_off_next)) {
+    set_last_error("serl_replay_sample_crop: need crop keys or explicit offsets");
+    return SERL_ERR_INVALID;
+  }
+  SamplerArgs a{};
+  a.rv = *rv;
+  a.seed = rq->seed; a.step = rq->step; a.step_dev = rq->step_dev; a.size_dev = rq->size_dev; a.lane_offset = rq->lane_offset; a.explicit_idx = rq->explicit_idx;
+  a.key_obs = rq->key_obs; a.key_next = rq->key_next;
+  a.explicit_off_obs = rq->explicit_off_obs; a.explicit_off_next = rq->explicit_off_next;
+  a.crop_total = rq->crop_total; a.out_row_offset = rq->out_row_offset; a.padding = rq->padding;
+  for (int c = 0; c < rv->num_cams; ++c) { a.obs_pix[c] = out->obs_pix[c]; a.next_pix[c] = out->next_pix[c]; }
+  a.obs_state = out->obs_state; a.next_state = out->next_state; a.actions = out->actions;
+  a.rewards = out->rewards; a.masks = out->masks; a.dones = out->dones; a.idx_out = out->idx;
+  a.off_obs_out = out->off_obs; a.off_next_out = out->off_next; a.status = out->status; a.batch = rq->batch;
+
+  const int row_bytes = rv->width * rv->channels;
+  const bool fast = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(rv->frames[0]) & 15) == 0);
+  dim3 grid(ceil_div(rv->height, kBandRows), rv->num_cams * 2 * rv->num_stack, rq->batch);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (fast) {
+    size_t smem = (size_t)kBandRows * row_bytes + 32;
+    sample_gather_crop_kernel<true><<<grid, kSamplerThreads, smem, st>>>(a);
+  } else {
+    sample_gather_crop_kernel<false><<<grid, kSamplerThreads, 0, st>>>(a);
+  }
+  return check_launch("sample_gather_crop_kernel");
+}
+
+extern "C" int serl_replay_scatter(const serl_replay_view* rv, const serl_scatter_request* rq, void* stream) {
+  if (int e = check_view(rv)) return e;
+  if (!rq || rq->n < 0) { set_last_error("serl_replay_scatter: invalid request"); return SERL_ERR_INVALID; }
+  if (rq->n == 0) return SERL_OK;
+  ScatterArgs a{};
+  a.rv = *rv; a.n = rq->n; a.dst_slot = rq->dst_slot; a.src_slot = rq->src_slot;
+  for (int c = 0; c < rv->num_cams; ++c) a.st_frames[c] = rq->frames[c];
+  a.st_state = rq->state; a.st_next_state = rq->next_state; a.st_actions = rq->actions;
+  a.st_rewards = rq->rewards; a.st_masks = rq->masks; a.st_dones = rq->dones; a.st_valid = rq->valid;
+  const size_t fb = (size_t)rv->height * rv->width * rv->channels;
+  int chunks = (int)((fb / 16 + 255) / 256); if (chunks < 1) chunks = 1; if (chunks > 16) chunks = 16;
+  dim3 grid(chunks, rv->num_cams, rq->n);
+  replay_scatter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  return check_launch("replay_scatter_kernel");
+}
+
+extern "C" int serl_replay_set_valid(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n, void* stream) {
+  if (n <= 0) return SERL_OK;
+  replay_set_valid_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(valid, slots, vals, n);
+  return check_launch("replay_set_valid_kernel");
+}
+
+extern "C" int serl_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
+  counter_add_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(counter, inc);
+  return check_launch("counter_add_kernel");
+}
+
+// Host-side mirrors of the integer RNG specs (no GPU needed): used by CPU tests to pin the device
+// functions (same __host__ __device__ code) against oracle/jax_prng.py and oracle/replay.py.
+extern "C" int serl_host_crop_offsets(const uint32_t key[2], int n_frames, int padding, int32_t* out) {
+  for (int g = 0; g < n_frames; ++g) {
+    u32x2 k = jax_split_at(u32x2{key[0], key[1]}, (uint32_t)n_frames, (uint32_t)g);
+    int cy, cx; jax_randint2(k, (uint32_t)(2 * padding + 1), &cy, &cx);
+    out[2 * g] = cy; out[2 * g + 1] = cx;
+  }
+  return SERL_OK;
+}
+
+extern "C" int serl_host_draw_indices(uint64_t seed, uint64_t step, uint32_t lane_offset, int batch, int size,
+                                      const uint8_t* valid, int32_t* out) {
+  if (size < 1) return SERL_ERR_INVALID;
+  const uint32_t thresh = (uint32_t)((0x100000000ull - (uint32_t)size) % (uint32_t)size);
+  for (int i = 0; i < batch; ++i) {
+    out[i] = -1;
+    for (int att = 0; att < kMaxDrawAttempts; ++att) {
+      u32x4 r = philox4x32_10(u32x4{lane_offset + (uint32_t)i, (uint32_t)att, (uint32_t)step, (uint32_t)(step >> 32)},
+                              (uint32_t)seed, (uint32_t)(seed >> 32));
+      uint64_t m = (uint64_t)r.x * (uint32_t)size;
+      if ((uint32_t)m < thresh) continue;
+      uint32_t idx = (uint32_t)(m >> 32);
+      if (valid[idx]) { out[i] = (int)idx; break; }
+    }
+  }
+  return SERL_OK;
+}
+
+extern "C" int serl_host_threefry_split(const uint32_t key[2], int n, uint32_t* out) {
+  for (int i = 0; i < n; ++i) { u32x2 k = jax_split_at(u32x2{key[0], key[1]}, (uint32_t)n, (uint32_t)i); out[2 * i] = k.x; out[2 * i + 1] = k.y; }
+  return SERL_OK;
+}
+
+extern "C" int serl_host_random_bits(const uint32_t key[2], int size, uint32_t* out) {
+  for (int j = 0; j < size; ++j) out[j] = jax_random_bits_at(u32x2{key[0], key[1]}, (uint32_t)size, (uint32_t)j);
+  return SERL_OK;
+}
