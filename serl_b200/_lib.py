@@ -126,3 +126,38 @@ def call(name: str, *args):
     if rc != 0:
         raise SerlError(f"{name} failed ({rc}): {lib.serl_last_error().decode()}")
     return rc
+
+
+# ---- torch plumbing indirections (device memory / streams / events); tests may patch these for dry runs -------
+def require_cuda(device):
+    if device.type != "cuda":
+        raise SerlError("serl_b200 runs on a CUDA device only (HBM-resident replay and sm_100a kernels; no CPU fallback)")
+
+
+def stream_ptr():
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Event:
+    def __init__(self):
+        import torch
+        self.e = torch.cuda.Event()
+
+    def record(self):
+        self.e.record()
+
+    def synchronize(self):
+        self.e.synchronize()
+
+    def make_current_stream_wait(self):
+        import torch
+        torch.cuda.current_stream().wait_event(self.e)
+
+
+def new_event():
+    return _Event()
+
+
+def pin(t):
+    return t.pin_memory()

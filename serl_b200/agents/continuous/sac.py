@@ -1,0 +1,333 @@
+"""SACAgent on hand-written sm_100a kernels.
+
+Mirrors the public surface of the reference's `SACAgent` (agents/continuous/sac.py:21-596):
+`create_states` / `create_pixels`-style construction, `update(batch, pmap_axis, networks_to_update)`,
+`update_high_utd(batch, utd_ratio)`, `sample_actions(observations, seed, argmax)`, `state`, `config`,
+`replace(state=...)`.  Calls return `(agent, info)` like the reference (the agent is updated in place:
+its parameters live in HBM).  `info` leaves are 0-d device tensors; `float(x)` synchronises.
+
+Semantics reproduced: ensemble subsample with replacement + min for the TD
+target, mean over the ensemble in the actor loss, shared value head for the pixel agent, same key for
+dropout and action sampling in `_compute_next_actions`, ALL three Adam txs tick on every `update`
+(zero-gradient momentum drift), polyak over the whole tree after critic updates, JAX key chain.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, FrozenSet, Optional, Sequence
+
+import numpy as np
+import torch
+
+from ... import _lib as L
+from ... import ops
+from ...common.common import TrainState
+from ...data.replay_buffer import BatchHandle
+from ...engine import AgentConfig, Engine
+from ...params import ParamStore, init_trainable, init_trunk, trainable_spec, trunk_spec
+
+ALL_NETS = frozenset({"actor", "critic", "temperature"})
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            return dist
+    except Exception:                                   # noqa: BLE001
+        pass
+    return None
+
+
+class SACAgent:
+    def __init__(self, cfg: AgentConfig, store: ParamStore, trunk, state: TrainState, config: dict, device):
+        self._cfg, self._store, self._trunk, self.state, self.config, self.device = cfg, store, trunk, state, config, device
+        self._engines: Dict[int, Engine] = {}
+        self._keys = torch.zeros(2 * L.NUM_KEYS, dtype=torch.uint32, device=device)
+        self._seed_key = torch.zeros(2, dtype=torch.uint32, device=device)
+        self.data_parallel = False          # set True to all-reduce(mean) gradients + infos (reference: pmap_axis)
+        self.explicit_randomness = None     # tests: dict with eps / dropout / subsample (and crop offsets)
+
+    # ---- construction (sac.py:322-400,486-542) ------------------------------------------------------
+    @classmethod
+    def _build(cls, seed: int, cfg: AgentConfig, temperature_init: float, device, in_channels: int = 3, config_extra=None):
+        L.load()
+        device = torch.device(device if device is not None else "cuda")
+        L.require_cuda(device)
+        rng = np.random.default_rng(seed)
+        spec = trainable_spec(cfg.cams, cfg.state_in, cfg.action_dim, cfg.ensemble, cfg.pixel)
+        store = ParamStore(spec, device)
+        values = init_trainable(rng, spec, temperature_init)
+        store.load(store.params, values)
+        store.target.copy_(store.params)                               # target_params=params (sac.py:369)
+        trunk = {}
+        if cfg.pixel:
+            for cam in cfg.cams:
+                w = init_trunk(rng, in_channels)
+                trunk[cam] = {k: torch.as_tensor(v).to(device).contiguous() for k, v in w.items()}
+        # rng, init_rng = split(PRNGKey(seed)); rng, create_rng = split(rng)  (sac.py:360,368): state.rng = create_rng
+        key = np.array([(seed >> 32) & 0xFFFFFFFF, seed & 0xFFFFFFFF], dtype=np.uint32)
+        key = _host_split(key, 2)[0]
+        create = _host_split(key, 2)[1]
+        rng_dev = torch.zeros(2, dtype=torch.uint32, device=device)
+        state = TrainState(store, trunk, rng_dev)
+        state.replace(rng=create)
+        config = dict(critic_ensemble_size=cfg.ensemble, critic_subsample_size=cfg.subsample, discount=cfg.discount,
+                      soft_target_update_rate=cfg.tau, target_entropy=cfg.target_entropy, backup_entropy=cfg.backup_entropy)
+        config.update(config_extra or {})
+        return cls(cfg, store, trunk, state, config, device)
+
+    @classmethod
+    def create_states(cls, seed: int, observations, actions, *, discount=0.95, critic_ensemble_size=2,
+                      critic_subsample_size=None, temperature_init=1.0, backup_entropy=False, soft_target_update_rate=0.005,
+                      target_entropy=None, policy_kwargs=None, actor_warmup=2000, critic_warmup=2000, learning_rate=3e-4,
+                      device=None, **_):
+        """State-observation agent (sac.py:486-542).  Optimizer defaults follow SACAgent.create (:333-343):
+        2000-step linear warm-up for actor and critic."""
+        pk = policy_kwargs or {}
+        S = int(np.asarray(observations).shape[-1])
+        A = int(np.asarray(actions).shape[-1])
+        cfg = AgentConfig(cams=(), state_in=S, action_dim=A, pixel=False, ensemble=critic_ensemble_size,
+                          subsample=critic_subsample_size, discount=discount, tau=soft_target_update_rate,
+                          target_entropy=(-A / 2 if target_entropy is None else target_entropy), backup_entropy=backup_entropy,
+                          lr=(learning_rate,) * 3, warmup=(critic_warmup, actor_warmup, 0),
+                          std_min=pk.get("std_min", 1e-5), std_max=pk.get("std_max", 10.0))
+        return cls._build(seed, cfg, temperature_init, device)
+
+    def replace(self, **kw):
+        if "state" in kw:
+            self.state = kw.pop("state")
+        if kw:
+            raise TypeError(f"replace: unknown fields {sorted(kw)}")
+        return self
+
+    # ---- engines ---------------------------------------------------------------------------------
+    def _engine(self, B: int) -> Engine:
+        if B not in self._engines:
+            self._engines[B] = Engine(self._cfg, self._store, self._trunk, B, self.device)
+        return self._engines[B]
+
+    @property
+    def kernel_launches(self) -> int:
+        return sum(e.launches for e in self._engines.values())
+
+    # ---- batch ingestion -------------------------------------------------------------------------------
+    def _load_batch(self, eng: Engine, batch, *, augment: bool, keys) -> None:
+        """Fills the engine's batch buffers.  Pixel agents: obs crops to pix rows [0,B), next crops to [B,2B)."""
+        cfg, B = self._cfg, eng.B
+        if not isinstance(batch, BatchHandle):
+            batch = self._handle_from_dict(batch)
+        if batch.batch_size != B:
+            raise ValueError(f"batch size {batch.batch_size} != engine batch {B}")
+        out = L.BatchOut()
+        if cfg.pixel:
+            hw = cfg.image_hw
+            for j, cam in enumerate(cfg.cams):
+                out.obs_pix[j] = eng.pix[cam].data_ptr()
+                out.next_pix[j] = eng.pix[cam].data_ptr() + B * hw * hw * 3
+            out.off_obs, out.off_next = eng.off[0].data_ptr(), eng.off[1].data_ptr()
+        out.obs_state, out.next_state, out.actions = eng.state_o.data_ptr(), eng.state_n.data_ptr(), eng.actions.data_ptr()
+        out.rewards, out.masks, out.dones = eng.rewards.data_ptr(), eng.masks.data_ptr(), eng.dones.data_ptr()
+        out.idx, out.status = eng.idx.data_ptr(), eng.status.data_ptr()
+        expl = None
+        if self.explicit_randomness is not None and "crop" in self.explicit_randomness:
+            expl = tuple(torch.as_tensor(np.asarray(o), dtype=torch.int32, device=self.device).contiguous()
+                         for o in self.explicit_randomness["crop"])
+        elif not augment or not cfg.pixel:
+            ident = torch.full((B, 2), 4, dtype=torch.int32, device=self.device)
+            expl = (ident, ident)
+        row = 0
+        for part in batch.parts:
+            ring = part["ring"]
+            if cfg.pixel and ring.T != 1:
+                raise NotImplementedError("the trunk kernels take one frame per observation (obs_horizon=1), like every SERL example")
+            ring.launch_sample(part, out, crop_total=B, out_row_offset=row, key_obs=ops.key_ptr(keys, L.KEY_CROP_OBS),
+                               key_next=ops.key_ptr(keys, L.KEY_CROP_NEXT), explicit_off=expl)
+            eng.launches += 1
+            row += part["batch"]
+
+    def _handle_from_dict(self, batch: dict) -> BatchHandle:
+        """Host / device dict in the reference layout -> a temporary HBM ring + explicit indices."""
+        from ...data.replay_buffer import DeviceRing
+        cfg = self._cfg
+        dev = self.device
+        t = lambda x, dt=torch.float32: torch.as_tensor(np.asarray(x) if not isinstance(x, torch.Tensor) else x).to(dev, dt)
+        B = int(t(batch["rewards"]).shape[0])
+        if cfg.pixel:
+            obs, nobs = batch["observations"], batch["next_observations"]
+            T = 1
+            ring = DeviceRing(B * 2, cfg.cams, (cfg.image_hw, cfg.image_hw, 3), T, cfg.state_in, cfg.action_dim, device=dev, seed=0)
+            for cam in cfg.cams:
+                pix = t(obs[cam], torch.uint8)
+                packed = pix if cam not in nobs else torch.cat([pix, t(nobs[cam], torch.uint8)[:, -1:]], dim=1)
+                if packed.shape[1] != 2:
+                    raise NotImplementedError("dict batches: obs_horizon must be 1")
+                ring.frames[cam].copy_(packed.reshape(B * 2, *packed.shape[2:]))
+            sl = slice(1, None, 2)
+            ring.state[sl] = t(obs["state"]).reshape(B, -1)
+            ring.next_state[sl] = t(nobs["state"]).reshape(B, -1)
+            idx = torch.arange(B, device=dev, dtype=torch.int32) * 2 + 1
+        else:
+            ring = DeviceRing(B, (), (1, 1, 1), 1, cfg.state_in, cfg.action_dim, device=dev, seed=0)
+            sl = slice(None)
+            ring.state[sl] = t(batch["observations"]).reshape(B, -1)
+            ring.next_state[sl] = t(batch["next_observations"]).reshape(B, -1)
+            idx = torch.arange(B, device=dev, dtype=torch.int32)
+        ring.actions[sl] = t(batch["actions"]).reshape(B, -1)
+        ring.rewards[sl] = t(batch["rewards"])
+        ring.masks[sl] = t(batch["masks"])
+        ring.dones[sl] = t(batch["dones"], torch.uint8) if "dones" in batch else 0
+        ring.valid.fill_(1)
+        ring._size = ring._capacity
+        ring.size_dev.fill_(ring._size)
+        return BatchHandle([dict(ring=ring, seed=0, step=0, batch=B, indx=idx)], True)
+
+    # ---- update (sac.py:243-299) ------------------------------------------------------------------------
+    def _features(self, eng: Engine):
+        if self._cfg.pixel:
+            for cam in self._cfg.cams:
+                eng.trunk_forward(cam, eng.pix[cam], eng.feats[cam])
+
+    def _allreduce(self, eng: Engine, lo: int, hi: int):
+        dist = _dist()
+        if dist is None:
+            return
+        g = self._store.grad[lo:hi]
+        dist.all_reduce(g, op=dist.ReduceOp.AVG)                 # jax.lax.pmean(grads_and_aux) (common.py:213-214)
+        dist.all_reduce(eng.info[:12], op=dist.ReduceOp.AVG)
+
+    def _update_on_engine(self, eng: Engine, nets: FrozenSet[str], pmap_axis=None, schedule_keys: bool = True):
+        assert nets.issubset(ALL_NETS), f"Invalid gradient steps: {nets}"
+        if schedule_keys:
+            ops.rng_schedule(self.state._rng, self._keys, False, True)
+            eng.launches += 1
+        expl = self.explicit_randomness
+        st = self._store
+        if "critic" in nets:
+            eng.critic_loss_and_grads(self._keys, explicit=expl)
+        if "actor" in nets or "temperature" in nets:
+            if not ("actor" in nets and "temperature" in nets):
+                raise NotImplementedError("actor and temperature are updated together (update_high_utd, sac.py:586-590)")
+            eng.actor_temp_loss_and_grads(self._keys, explicit=expl)
+        if pmap_axis is not None or self.data_parallel:
+            if "critic" in nets:
+                self._allreduce(eng, 0, st.seg_end[0])
+            if "actor" in nets:
+                self._allreduce(eng, st.seg_end[0], st.seg_end[2])
+        eng.optimizer_step([int("critic" in nets), int("actor" in nets), int("temperature" in nets)], polyak="critic" in nets)
+        self.state.step += 1
+        return self._info(eng, nets)
+
+    def _info(self, eng: Engine, nets) -> dict:
+        snap = eng.info.clone()
+        info = {"critic": {}, "actor": {}, "temperature": {}}
+        if "critic" in nets:
+            info["critic"] = {"critic_loss": snap[0], "predicted_qs": snap[1], "target_qs": snap[2]}
+        if "actor" in nets:
+            info["actor"] = {"actor_loss": snap[4], "temperature": snap[5], "entropy": snap[6]}
+        if "temperature" in nets:
+            info["temperature"] = {"temperature_loss": snap[8]}
+        info["critic_lr"], info["actor_lr"], info["temperature_lr"] = snap[12], snap[13], snap[14]   # sac.py:292-297
+        return info
+
+    def update(self, batch, *, pmap_axis: Optional[str] = None, networks_to_update: FrozenSet[str] = ALL_NETS):
+        """One gradient step on all (or a subset of) the networks (sac.py:243-299)."""
+        nets = frozenset(networks_to_update)
+        B = batch.batch_size if isinstance(batch, BatchHandle) else int(np.asarray(_leaf(batch, "rewards")).shape[0])
+        eng = self._engine(B)
+        ops.rng_schedule(self.state._rng, self._keys, False, True)
+        eng.launches += 1
+        self._load_batch(eng, batch, augment=False, keys=self._keys)
+        self._features(eng)
+        info = self._update_on_engine(eng, nets, pmap_axis, schedule_keys=False)
+        self._check(eng)
+        return self, info
+
+    def _check(self, eng: Engine):
+        pass   # draw failures are surfaced lazily by check_status() to avoid a sync per step
+
+    def check_status(self):
+        for eng in self._engines.values():
+            if int(eng.status.item()):
+                raise L.SerlError("replay draw failed: no valid slot within the redraw budget")
+
+    def update_high_utd(self, batch, *, utd_ratio: int, pmap_axis: Optional[str] = None, _augment: bool = False):
+        """sac.py:544-596: utd_ratio critic updates on consecutive minibatches, then one actor+temperature update
+        on the full batch."""
+        B = batch.batch_size if isinstance(batch, BatchHandle) else int(np.asarray(_leaf(batch, "rewards")).shape[0])
+        assert B % utd_ratio == 0, f"Batch size {B} must be divisible by UTD ratio {utd_ratio}"
+        full = self._engine(B)
+        if _augment:
+            ops.rng_schedule(self.state._rng, self._keys, True, False)          # drq.py:279
+            full.launches += 1
+        self._load_batch(full, batch, augment=_augment, keys=self._keys)
+        self._features(full)
+        mb = B // utd_ratio
+        crit_infos = []
+        for i in range(utd_ratio):
+            eng = full if utd_ratio == 1 else self._minibatch_engine(full, i, mb)
+            crit_infos.append(self._update_on_engine(eng, frozenset({"critic"}), pmap_axis))
+        at = self._update_on_engine(full, frozenset({"actor", "temperature"}), pmap_axis)
+        crit = {k: torch.stack([c["critic"][k] for c in crit_infos]).mean() for k in crit_infos[0]["critic"]}
+        info = {"critic": crit, "actor": at["actor"], "temperature": at["temperature"]}
+        for k in ("critic_lr", "actor_lr", "temperature_lr"):
+            info[k] = at[k]
+        return self, info
+
+    def _minibatch_engine(self, full: Engine, i: int, mb: int) -> Engine:
+        eng = self._engine(mb)
+        lo, hi, B = i * mb, (i + 1) * mb, full.B
+        for name in ("state_o", "state_n", "actions", "rewards", "masks"):
+            getattr(eng, name).copy_(getattr(full, name)[lo:hi])
+        if self._cfg.pixel:
+            for cam in self._cfg.cams:
+                eng.feats[cam][:mb].copy_(full.feats[cam][lo:hi])
+                eng.feats[cam][mb:].copy_(full.feats[cam][B + lo:B + hi])
+        return eng
+
+    # ---- sample_actions (sac.py:301-320) ---------------------------------------------------------------
+    def sample_actions(self, observations, *, seed=None, argmax: bool = False, return_device: bool = False, **kwargs):
+        cfg, dev = self._cfg, self.device
+        if argmax:
+            assert seed is None, "Cannot specify seed when sampling deterministically"
+        if cfg.pixel:
+            st = np.asarray(observations["state"])
+            unbatched = st.ndim == 2                                        # (T,S)
+            B = 1 if unbatched else st.shape[0]
+            eng = self._engine(B)
+            for cam in cfg.cams:
+                img = torch.as_tensor(np.asarray(observations[cam])).to(dev)
+                eng.pix[cam][:B].copy_(img.reshape(B, cfg.image_hw, cfg.image_hw, 3))
+                eng.trunk_forward(cam, eng.pix[cam][:B], eng.feats[cam])
+            eng.state_o.copy_(torch.as_tensor(st, dtype=torch.float32).reshape(B, -1))
+        else:
+            st = np.asarray(observations)
+            unbatched = st.ndim == 1
+            B = 1 if unbatched else st.shape[0]
+            eng = self._engine(B)
+            eng.state_o.copy_(torch.as_tensor(st, dtype=torch.float32).reshape(B, -1))
+        eng.encode(self._store.params, slice(0, B), eng.state_o, eng.Xp, eng.F, None, save=False)   # train=False: no dropout
+        eng.policy_forward(self._store.params, eng.Xp, save=False)
+        A = cfg.action_dim
+        if not argmax:
+            key = np.ascontiguousarray(np.asarray(seed), dtype=np.uint32).reshape(2)
+            self._seed_key.copy_(torch.from_numpy(key.view(np.int32)).view(torch.uint32))
+            ops.normal_fill(self._seed_key.data_ptr(), eng.eps, B * A)
+        ops.tanh_gaussian_fwd(eng.mu, eng.ls, eng.eps, cfg.std_min, cfg.std_max, eng.act_scratch.data_ptr(), A, None, None, None,
+                              B, A, deterministic=argmax)
+        out = eng.act_scratch.clone()
+        out = out[0] if unbatched else out
+        return out if return_device else out.cpu().numpy()
+
+
+def _host_split(key: np.ndarray, n: int) -> np.ndarray:
+    """jax.random.split on the host through the library's host mirror of the device PRNG."""
+    key = np.ascontiguousarray(key, dtype=np.uint32)
+    out = np.zeros((n, 2), dtype=np.uint32)
+    L.call("serl_host_threefry_split", key.ctypes.data, n, out.ctypes.data)
+    return out
+
+
+def _leaf(batch, key):
+    v = batch[key]
+    return v.cpu() if isinstance(v, torch.Tensor) else v

@@ -112,12 +112,13 @@ __global__ void __launch_bounds__(kSamplerThreads) sample_gather_crop_kernel(con
 
   if (threadIdx.x == 0) {
     int idx = a.explicit_idx ? a.explicit_idx[i] : draw_index(a, a.lane_offset + (uint32_t)i);
-    int cy, cx;
-    crop_offset_for(which ? a.key_next : a.key_obs, which ? a.explicit_off_next : a.explicit_off_obs,
-                    a.crop_total, g, 2 * a.padding + 1, &cy, &cx);
+    int cy = a.padding, cx = a.padding;
+    if (rv.num_cams > 0)
+      crop_offset_for(which ? a.key_next : a.key_obs, which ? a.explicit_off_next : a.explicit_off_obs,
+                      a.crop_total, g, 2 * a.padding + 1, &cy, &cx);
     s_idx = idx; s_cy = cy; s_cx = cx;
     if (idx < 0) atomicOr(a.status, 1);
-    if (cam == 0 && band == 0) {                          // record offsets once per (which, t)
+    if (cam == 0 && band == 0 && rv.num_cams > 0) {       // record offsets once per (which, t)
       int32_t* o = which ? a.off_next_out : a.off_obs_out;
       if (o) { o[2 * g] = cy; o[2 * g + 1] = cx; }
     }
@@ -143,6 +144,8 @@ __global__ void __launch_bounds__(kSamplerThreads) sample_gather_crop_kernel(con
       if (a.idx_out) a.idx_out[out_row] = idx;
     }
   }
+
+  if (rv.num_cams == 0) return;                          // state-only ring (data/replay_buffer.py:40-75)
 
   // ---- frame band: slot idx - T + t + which, rows clamp(y + cy - pad) ---------------------------
   const size_t frame_bytes = (size_t)H * row_bytes;
@@ -264,7 +267,7 @@ __global__ void replay_set_valid_kernel(uint8_t* valid, const int32_t* slots, co
 using namespace serl;
 
 static int check_view(const serl_replay_view* rv) {
-  if (!rv || rv->num_cams < 1 || rv->num_cams > SERL_MAX_CAMS || rv->num_stack < 1 || rv->size < 0 ||
+  if (!rv || rv->num_cams < 0 || rv->num_cams > SERL_MAX_CAMS || rv->num_stack < 1 || rv->size < 0 ||
       rv->size > rv->capacity || rv->height < 1 || rv->width < 1 || rv->channels < 1) {
     set_last_error("serl_replay: invalid replay view");
     return SERL_ERR_INVALID;
@@ -284,7 +287,7 @@ extern "C" int serl_replay_sample_crop(const serl_replay_view* rv, const serl_sa
     set_last_error("serl_replay_sample_crop: buffer holds %d slots, need > num_stack", rv->size);
     return SERL_ERR_INVALID;
   }
-  if ((!rq->key_obs || !rq->key_next) && (!rq->explicit_off_obs || !rq->explicit_off_next)) {
+  if (rv->num_cams > 0 && (!rq->key_obs || !rq->key_next) && (!rq->explicit_off_obs || !rq->explicit_off_next)) {
     set_last_error("serl_replay_sample_crop: need crop keys or explicit offsets");
     return SERL_ERR_INVALID;
   }
@@ -300,8 +303,9 @@ extern "C" int serl_replay_sample_crop(const serl_replay_view* rv, const serl_sa
   a.off_obs_out = out->off_obs; a.off_next_out = out->off_next; a.status = out->status; a.batch = rq->batch;
 
   const int row_bytes = rv->width * rv->channels;
-  const bool fast = (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(rv->frames[0]) & 15) == 0);
+  const bool fast = rv->num_cams > 0 && (row_bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(rv->frames[0]) & 15) == 0);
   dim3 grid(ceil_div(rv->height, kBandRows), rv->num_cams * 2 * rv->num_stack, rq->batch);
+  if (rv->num_cams == 0) grid = dim3(1, 1, rq->batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (fast) {
     size_t smem = (size_t)kBandRows * row_bytes + 32;

@@ -1,0 +1,187 @@
+"""Thin torch-tensor wrappers over the C-ABI ops (pointer + stream extraction only; no math here).
+
+torch is plumbing: it owns device memory and the current stream.  Every function launches
+hand-written kernels from libserl_b200.so and raises if the library or a launch fails.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _s():
+    return L.stream_ptr()
+
+
+def _chk(t: torch.Tensor, dtype, name):
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+# ---- trunk (fp32) ----------------------------------------------------------------------------------
+def conv2d_nhwc(x, w, y, stride, pad_lo, pad_hi):
+    """x (N,Hi,Wi,Ci) u8|f32, w (kh,kw,Ci,Co) f32 -> y (N,Ho,Wo,Co) f32."""
+    N, Hi, Wi, Ci = x.shape
+    kh, kw, ci2, Co = w.shape
+    assert ci2 == Ci and x.is_contiguous() and w.is_contiguous() and y.is_contiguous()
+    L.call("serl_conv2d_nhwc_f32", _p(x), int(x.dtype == torch.uint8), _p(w), _p(y), N, Hi, Wi, Ci, Co, kh, kw, stride,
+           pad_lo, pad_hi, _s())
+    return y
+
+
+def groupnorm_nhwc(x, y, scale, bias, residual, groups, eps, relu):
+    N, H, W, Cc = x.shape
+    L.call("serl_groupnorm_nhwc_f32", _p(x), _p(y), _p(scale), _p(bias), _p(residual), N, H * W, Cc, groups, float(eps),
+           int(relu), _s())
+    return y
+
+
+def maxpool3x3s2_nhwc(x, y):
+    N, H, W, Cc = x.shape
+    L.call("serl_maxpool3x3s2_nhwc_f32", _p(x), _p(y), N, H, W, Cc, _s())
+    return y
+
+
+# ---- GEMM -------------------------------------------------------------------------------------------
+class Workspace:
+    """Caller-owned scratch for split-K / batch-reduce partials."""
+
+    def __init__(self, nbytes: int, device):
+        self.buf = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
+        self.nbytes = self.buf.numel() * 4
+
+
+def gemm(ws: Workspace, A_ptr, B_ptr, C_ptr, M, N, K, *, sAm, sAk, sBk, sBn, ldc, Z=1, sAz=0, sBz=0, sCz=0,
+         bias_ptr=None, sBiasZ=0, accumulate=False, reduce_z=False):
+    d = L.GemmDesc()
+    d.A, d.B, d.C, d.bias = A_ptr, B_ptr, C_ptr, bias_ptr
+    d.workspace, d.workspace_bytes = ws.buf.data_ptr(), ws.nbytes
+    d.M, d.N, d.K, d.Z = M, N, K, Z
+    d.sAz, d.sAm, d.sAk, d.sBz, d.sBk, d.sBn, d.sCz, d.sBiasZ = sAz, sAm, sAk, sBz, sBk, sBn, sCz, sBiasZ
+    d.ldc, d.accumulate, d.reduce_z = ldc, int(accumulate), int(reduce_z)
+    L.call("serl_gemm_f32", C.byref(d), _s())
+
+
+def at(t: torch.Tensor, elem_offset: int = 0) -> int:
+    """Device address of element `elem_offset` of a tensor's storage view."""
+    return t.data_ptr() + elem_offset * t.element_size()
+
+
+def dense_fwd(ws, x, ldx, w, b, out, ldo, M, K, N, *, Z=1, x_z=0, w_z=None, b_z=None, out_z=0):
+    """out[z] (M,N) = x[z] (M,K) @ w[z] (K,N) + b[z];  x/out given as (address, ld)."""
+    gemm(ws, x, w, out, M, N, K, sAm=ldx, sAk=1, sBk=N, sBn=1, ldc=ldo, Z=Z, sAz=x_z, sBz=(K * N if w_z is None else w_z),
+         sCz=out_z, bias_ptr=b, sBiasZ=(N if b_z is None else b_z))
+
+
+def dense_bwd_weight(ws, x, ldx, dz, lddz, dw, M, K, N, *, Z=1, x_z=0, dz_z=0, dw_z=None):
+    """dw[z] (K,N) = x[z]^T (K,M) @ dz[z] (M,N)."""
+    gemm(ws, x, dz, dw, K, N, M, sAm=1, sAk=ldx, sBk=lddz, sBn=1, ldc=N, Z=Z, sAz=x_z, sBz=dz_z,
+         sCz=(K * N if dw_z is None else dw_z))
+
+
+def dense_bwd_input(ws, dz, lddz, w, dx, lddx, M, K, N, *, Z=1, dz_z=0, w_z=None, dx_z=0, reduce_z=False, accumulate=False):
+    """dx[z] (M,K) = dz[z] (M,N) @ w[z]^T (N,K)   (w stored (K,N) row-major)."""
+    gemm(ws, dz, w, dx, M, K, N, sAm=lddz, sAk=1, sBk=1, sBn=N, ldc=lddx, Z=Z, sAz=dz_z, sBz=(K * N if w_z is None else w_z),
+         sCz=dx_z, reduce_z=reduce_z, accumulate=accumulate)
+
+
+# ---- heads -------------------------------------------------------------------------------------------
+def sle_fwd(feat, kernel, keep_mask, keep, out, ld_out):
+    N, Pp, Cc = feat.shape[0], feat.shape[1] * feat.shape[2], feat.shape[3]
+    L.call("serl_sle_fwd", _p(feat), _p(kernel), _p(keep_mask), float(keep), out, N, Pp, Cc, kernel.shape[-1], ld_out, _s())
+
+
+def sle_bwd_kernel_grad(ws, feat, dout, ld_dout, dkernel):
+    N, Pp, Cc = feat.shape[0], feat.shape[1] * feat.shape[2], feat.shape[3]
+    L.call("serl_sle_bwd_kernel_grad", _p(feat), dout, dkernel, ws.buf.data_ptr(), ws.nbytes, N, Pp, Cc, 8, ld_dout, _s())
+
+
+def ln_tanh_fwd(z, ld_z, scale, bias, rows_per_group, group_stride, out, ld_out, xhat, rstd, R, D, eps=1e-6):
+    L.call("serl_layernorm_tanh_fwd", z, ld_z, scale, bias, rows_per_group, group_stride, out, ld_out, xhat, rstd, R, D,
+           float(eps), _s())
+
+
+def ln_tanh_bwd(dt, ld_dt, t, ld_t, xhat, rstd, scale, rows_per_group, group_stride, dz, dy, dscale, dbias, R, D):
+    L.call("serl_layernorm_tanh_bwd", dt, ld_dt, t, ld_t, xhat, rstd, scale, rows_per_group, group_stride, dz, dy, dscale,
+           dbias, R, D, _s())
+
+
+def colsum(x, out, groups, rows, D, ld, accumulate=False):
+    L.call("serl_colsum_f32", x, out, groups, rows, D, ld, int(accumulate), _s())
+
+
+def copy2d(src, ld_src, dst, ld_dst, R, D):
+    L.call("serl_copy2d_f32", src, ld_src, dst, ld_dst, R, D, _s())
+
+
+def fill(x, v, n):
+    L.call("serl_fill_f32", x, float(v), n, _s())
+
+
+# ---- rng ---------------------------------------------------------------------------------------------
+def rng_schedule(rng_state, keys, do_aug, do_update):
+    L.call("serl_rng_schedule", _p(_chk(rng_state, torch.uint32, "rng")), _p(keys), int(do_aug), int(do_update), _s())
+
+
+def key_ptr(keys: torch.Tensor, slot: int) -> int:
+    return keys.data_ptr() + 8 * slot
+
+
+def normal_fill(key_addr, out, n):
+    L.call("serl_normal_fill", key_addr, _p(out), n, _s())
+
+
+def dropout_mask_fill(key_addr, fold, keep, mask, n):
+    L.call("serl_dropout_mask_fill", key_addr, fold, float(keep), _p(mask), n, _s())
+
+
+def subsample_idx(key_addr, ensemble, out):
+    L.call("serl_subsample_idx", key_addr, ensemble, _p(out), _s())
+
+
+def counter_add(counter, inc=1):
+    L.call("serl_counter_add", _p(counter), inc, _s())
+
+
+# ---- losses / optimizer ------------------------------------------------------------------------------
+def tanh_gaussian_fwd(mu, log_std, eps, std_min, std_max, act, ld_act, logp, u, std, B, A, deterministic=False):
+    L.call("serl_tanh_gaussian_fwd", _p(mu), _p(log_std), _p(eps), float(std_min), float(std_max), act, ld_act, _p(logp),
+           _p(u), _p(std), B, A, int(deterministic), _s())
+
+
+def critic_loss(q, q_next, sub, n_sub, rewards, masks, logp_next, lagrange, backup_entropy, gamma, grad_scale, target_q,
+                dq, info, E, B):
+    L.call("serl_critic_loss", _p(q), _p(q_next), _p(sub), n_sub, _p(rewards), _p(masks), _p(logp_next), lagrange,
+           int(backup_entropy), float(gamma), float(grad_scale), _p(target_q), _p(dq), info, E, B, _s())
+
+
+def actor_loss(q, logp, lagrange, da, ld_da, act, ld_act, std, log_std, eps, std_min, std_max, grad_scale, dmu, dlogstd,
+               info, E, B, A):
+    L.call("serl_actor_loss", _p(q), _p(logp), lagrange, da, ld_da, act, ld_act, _p(std), _p(log_std), _p(eps),
+           float(std_min), float(std_max), float(grad_scale), _p(dmu), _p(dlogstd), info, E, B, A, _s())
+
+
+def temperature_loss(logp, lagrange, target_entropy, grad_scale, dlagrange, info, B):
+    L.call("serl_temperature_loss", _p(logp), lagrange, float(target_entropy), float(grad_scale), dlagrange, info, B, _s())
+
+
+def adam_polyak(params, target, m, v, grad, seg_end: Sequence[int], live: Sequence[int], counts, lr, warmup, tau, polyak,
+                lr_out=None, b1=0.9, b2=0.999, eps=1e-8):
+    d = L.AdamDesc()
+    d.params, d.target, d.m, d.v, d.grad = _p(params), _p(target), _p(m), _p(v), _p(grad)
+    d.n = params.numel()
+    for g in range(3):
+        d.seg_end[g], d.live[g], d.lr[g], d.warmup[g] = int(seg_end[g]), int(live[g]), float(lr[g]), int(warmup[g])
+    d.counts = _p(counts)
+    d.b1, d.b2, d.eps, d.tau, d.polyak = b1, b2, eps, float(tau), int(polyak)
+    d.lr_out = _p(lr_out)
+    L.call("serl_adam_polyak", C.byref(d), _s())

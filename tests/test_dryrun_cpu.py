@@ -1,0 +1,121 @@
+"""CPU: walks the whole Python orchestration (replay ring bookkeeping, batch handles, agent update paths, launch
+counting) with the kernel launches replaced by a recorder.  No arithmetic is checked here (that is the GPU
+suite's job); this pins the host logic: which C-ABI entry points a step calls, in which order, and that the
+host ring bookkeeping equals the reference semantics (via the oracle ring)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import fake_env, random_transitions
+
+
+@pytest.fixture()
+def dry(monkeypatch):
+    from serl_b200 import _lib as L
+    calls = []
+    real_call = L.call
+
+    def fake_call(name, *args):
+        if name.startswith("serl_host_"):
+            return real_call(name, *args)
+        calls.append(name)
+        return 0
+
+    class Ev:
+        def record(self): pass
+        def synchronize(self): pass
+        def make_current_stream_wait(self): pass
+
+    monkeypatch.setattr(L, "call", fake_call)
+    monkeypatch.setattr(L, "require_cuda", lambda d: None)
+    monkeypatch.setattr(L, "stream_ptr", lambda: 0)
+    monkeypatch.setattr(L, "new_event", lambda: Ev())
+    monkeypatch.setattr(L, "pin", lambda t: t)
+    return calls
+
+
+def _ring(cams, cap, hw=16, T=1):
+    from serl_b200.utils.launcher import make_replay_buffer
+    return make_replay_buffer(fake_env(cams, hw, T), capacity=cap, type="memory_efficient_replay_buffer", image_keys=list(cams),
+                              device="cpu", seed=5)
+
+
+@pytest.mark.parametrize("T,cap,n", [(1, 37, 150), (2, 23, 120)])
+def test_host_ring_bookkeeping_equals_reference_semantics(dry, T, cap, n):
+    from oracle.replay import OracleFrameRing
+    cams = ("a", "b")
+    rb = _ring(cams, cap, 8, T)
+    ora = OracleFrameRing(cap, cams, (8, 8, 3), T, 7, 4)
+    for tr in random_transitions(np.random.default_rng(T), n, cams, 8, T, mean_ep=6):
+        rb.insert(tr)
+        ora.insert(tr)
+        assert len(rb) == ora.size and rb._insert_index == ora.cursor and rb._first == ora.episode_start
+        np.testing.assert_array_equal(rb._valid_host, ora.valid)
+    rb.flush()
+    assert "serl_replay_scatter" in dry and "serl_replay_set_valid" in dry
+
+
+def test_drq_learner_iteration_call_sequence(dry):
+    from serl_b200.utils.launcher import make_drq_agent
+    from serl_b200.utils.train_utils import concat_batches
+    cams = ("front", "wrist")
+    rb, demo = _ring(cams, 64, 128), _ring(cams, 32, 128)
+    trs = random_transitions(np.random.default_rng(0), 40, cams, 128)
+    for tr in trs:
+        rb.insert(tr)
+    for tr in trs[:20]:
+        demo.insert(tr)
+    agent = make_drq_agent(42, trs[0]["observations"], trs[0]["actions"], image_keys=cams, encoder_type="resnet-pretrained", device="cpu")
+    it = rb.get_iterator(sample_args={"batch_size": 4, "pack_obs_and_next_obs": True})
+    dit = demo.get_iterator(sample_args={"batch_size": 4, "pack_obs_and_next_obs": True})
+    del dry[:]
+    batch = concat_batches(next(it), next(dit), axis=0)             # RLPD 50/50
+    assert batch.batch_size == 8
+    agent, info = agent.update_critics(batch)
+    assert set(info) == {"critic", "critic_lr", "actor_lr", "temperature_lr"}
+    assert set(info["critic"]) == {"critic_loss", "predicted_qs", "target_qs"}
+    seq = [c for c in dry if c not in ("serl_replay_scatter", "serl_replay_set_valid")]     # pending inserts are flushed by sample()
+    assert seq[0] == "serl_rng_schedule" and seq.count("serl_replay_sample_crop") == 2       # online + demo halves
+    assert seq.count("serl_conv2d_nhwc_f32") == 2 * 12                                       # 12 convs per camera, ONE trunk pass
+    assert seq.count("serl_adam_polyak") == 1 and seq[-1] == "serl_adam_polyak"
+    assert agent.kernel_launches > 100
+    del dry[:]
+    agent, info = agent.update_high_utd(next(it).concat(next(dit)), utd_ratio=1)
+    assert set(info["actor"]) == {"actor_loss", "temperature", "entropy"} and "temperature_loss" in info["temperature"]
+    seq = list(dry)
+    assert seq.count("serl_adam_polyak") == 2 and seq.count("serl_rng_schedule") == 3        # aug, critic update, actor/temp update
+    assert seq.count("serl_conv2d_nhwc_f32") == 2 * 12                                       # features reused by actor/temperature
+    assert seq.count("serl_actor_loss") == 1 and seq.count("serl_temperature_loss") == 1 and seq.count("serl_critic_loss") == 1
+    assert agent.state.step == 3
+    # wire format: Flax-layout tree incl. the frozen trunk
+    tree = agent.state.params
+    enc = tree["modules_actor"]["encoder"]
+    assert enc["encoder_front"]["pretrained_encoder"]["conv_init"]["kernel"].shape == (7, 7, 3, 64)
+    assert enc["encoder_wrist"]["SpatialLearnedEmbeddings_0"]["kernel"].shape == (4, 4, 512, 8)
+    assert tree["modules_critic"]["network"]["Dense_0"]["kernel"].shape == (10, 256 * 2 + 64 + 4, 256)
+    assert tree["modules_critic"]["Dense_0"]["kernel"].shape == (256, 1)
+    assert tree["modules_temperature"]["lagrange"].shape == ()
+    agent.state.replace(params=tree)
+
+
+def test_state_sac_high_utd_and_sample_actions(dry):
+    from serl_b200.utils.launcher import make_sac_agent
+    rng = np.random.default_rng(0)
+    agent = make_sac_agent(0, rng.standard_normal(10).astype(np.float32), np.zeros(4, np.float32), device="cpu")
+    B = 32
+    batch = dict(observations=rng.standard_normal((B, 10)).astype(np.float32), next_observations=rng.standard_normal((B, 10)).astype(np.float32),
+                 actions=np.zeros((B, 4), np.float32), rewards=np.zeros(B, np.float32), masks=np.ones(B, np.float32), dones=np.zeros(B, bool))
+    del dry[:]
+    agent, info = agent.update_high_utd(batch, utd_ratio=4)
+    assert dry.count("serl_adam_polyak") == 5 and dry.count("serl_critic_loss") == 4 and "serl_conv2d_nhwc_f32" not in dry
+    assert agent.state.step == 5
+    a = agent.sample_actions(rng.standard_normal(10).astype(np.float32), argmax=True)
+    assert a.shape == (4,)
+    a = agent.sample_actions(rng.standard_normal((3, 10)).astype(np.float32), seed=np.array([0, 7], np.uint32))
+    assert a.shape == (3, 4)
+    tree = agent.state.params
+    assert tree["modules_critic"]["Dense_0"]["kernel"].shape == (10, 256, 1)
+    os_ = agent.state.opt_states
+    assert set(os_) == {"actor", "critic", "temperature"} and os_["actor"]["count"] == 0    # counts live on the (dry) device

@@ -1,0 +1,232 @@
+"""GPU: every hand-written fp32 kernel vs a float64 CPU restatement of the same op (through the C-ABI)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-5      # fp32 kernels vs fp64 truth (north_star: 1e-5 on the end-to-end quantities; per-op slack for long K)
+
+
+def cu(x, dt=torch.float32):
+    return torch.as_tensor(np.asarray(x)).to("cuda", dt).contiguous()
+
+
+@pytest.mark.parametrize("N,Hi,Ci,Co,k,stride,lo,hi,u8", [
+    (3, 128, 3, 64, 7, 2, 3, 3, True), (2, 32, 64, 64, 3, 1, 1, 1, False), (5, 32, 64, 128, 3, 2, 0, 1, False),
+    (2, 32, 64, 128, 1, 2, 0, 0, False), (3, 8, 256, 512, 3, 2, 0, 1, False), (7, 4, 512, 512, 3, 1, 1, 1, False)])
+def test_conv(N, Hi, Ci, Co, k, stride, lo, hi, u8):
+    from oracle.drq import IMAGENET_MEAN, IMAGENET_STD, conv_nhwc
+    from serl_b200 import ops
+    rng = np.random.default_rng(0)
+    w = (rng.standard_normal((k, k, Ci, Co)) * np.sqrt(2.0 / (k * k * Ci))).astype(np.float32)
+    if u8:
+        x = rng.integers(0, 256, (N, Hi, Hi, Ci), dtype=np.uint8)
+        xr = (torch.as_tensor(x).double() / 255.0 - torch.tensor(IMAGENET_MEAN).double()) / torch.tensor(IMAGENET_STD).double()
+    else:
+        x = rng.standard_normal((N, Hi, Hi, Ci)).astype(np.float32)
+        xr = torch.as_tensor(x).double()
+    ref = conv_nhwc(xr, torch.as_tensor(w).double(), stride, lo, hi).numpy()
+    Ho = ref.shape[1]
+    y = torch.empty(N, Ho, Ho, Co, device="cuda")
+    ops.conv2d_nhwc(cu(x, torch.uint8 if u8 else torch.float32), cu(w), y, stride, lo, hi)
+    assert rel_err(y.cpu().numpy(), ref) < TOL
+
+
+@pytest.mark.parametrize("N,H,C,res,relu", [(3, 64, 64, False, True), (2, 16, 128, True, True), (5, 4, 512, True, False)])
+def test_groupnorm(N, H, C, res, relu):
+    from oracle.drq import group_norm_nhwc
+    from serl_b200 import ops
+    rng = np.random.default_rng(1)
+    x = (rng.standard_normal((N, H, H, C)) * 3 + 1.5).astype(np.float32)
+    sc, bi = rng.standard_normal(C).astype(np.float32), rng.standard_normal(C).astype(np.float32)
+    r = rng.standard_normal((N, H, H, C)).astype(np.float32)
+    ref = group_norm_nhwc(torch.as_tensor(x).double(), torch.as_tensor(sc).double(), torch.as_tensor(bi).double())
+    if res:
+        ref = ref + torch.as_tensor(r).double()
+    if relu:
+        ref = ref.relu()
+    xd = cu(x)
+    ops.groupnorm_nhwc(xd, xd, cu(sc), cu(bi), cu(r) if res else None, 4, 1e-5, relu)      # in place
+    assert rel_err(xd.cpu().numpy(), ref.numpy()) < TOL
+
+
+def test_maxpool():
+    from oracle.drq import max_pool_3x3_s2_same
+    from serl_b200 import ops
+    x = np.random.default_rng(2).standard_normal((3, 64, 64, 64)).astype(np.float32)
+    y = torch.empty(3, 32, 32, 64, device="cuda")
+    ops.maxpool3x3s2_nhwc(cu(x), y)
+    np.testing.assert_array_equal(y.cpu().numpy(), max_pool_3x3_s2_same(torch.as_tensor(x)).numpy())
+
+
+@pytest.mark.parametrize("M,K,N,Z", [(37, 4096, 256, 1), (256, 580, 256, 10), (256, 256, 1, 1), (19, 7, 64, 1), (64, 256, 4, 1)])
+def test_dense_fwd_bwd(M, K, N, Z):
+    from serl_b200 import ops
+    rng = np.random.default_rng(3)
+    ws = ops.Workspace(64 << 20, "cuda")
+    x = rng.standard_normal((Z, M, K)).astype(np.float32)
+    w = (rng.standard_normal((Z, K, N)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal((Z, N)).astype(np.float32)
+    dz = rng.standard_normal((Z, M, N)).astype(np.float32)
+    xd, wd, bd, dzd = cu(x), cu(w), cu(b), cu(dz)
+    out = torch.empty(Z, M, N, device="cuda")
+    ops.dense_fwd(ws, xd.data_ptr(), K, wd.data_ptr(), bd.data_ptr(), out.data_ptr(), N, M, K, N, Z=Z, x_z=M * K, out_z=M * N)
+    ref = np.einsum("zmk,zkn->zmn", x.astype(np.float64), w.astype(np.float64)) + b[:, None, :]
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+    dw = torch.empty(Z, K, N, device="cuda")
+    ops.dense_bwd_weight(ws, xd.data_ptr(), K, dzd.data_ptr(), N, dw.data_ptr(), M, K, N, Z=Z, x_z=M * K, dz_z=M * N)
+    assert rel_err(dw.cpu().numpy(), np.einsum("zmk,zmn->zkn", x.astype(np.float64), dz.astype(np.float64))) < TOL
+    dx = torch.empty(Z, M, K, device="cuda")
+    ops.dense_bwd_input(ws, dzd.data_ptr(), N, wd.data_ptr(), dx.data_ptr(), K, M, K, N, Z=Z, dz_z=M * N, dx_z=M * K)
+    refdx = np.einsum("zmn,zkn->zmk", dz.astype(np.float64), w.astype(np.float64))
+    assert rel_err(dx.cpu().numpy(), refdx) < TOL
+    dxs = torch.empty(M, K, device="cuda")                                   # broadcast input: sum over the ensemble
+    ops.dense_bwd_input(ws, dzd.data_ptr(), N, wd.data_ptr(), dxs.data_ptr(), K, M, K, N, Z=Z, dz_z=M * N, reduce_z=True)
+    assert rel_err(dxs.cpu().numpy(), refdx.sum(0)) < TOL
+
+
+def test_sle_fwd_bwd_and_dropout():
+    from serl_b200 import ops
+    rng = np.random.default_rng(4)
+    B = 70
+    feat = np.abs(rng.standard_normal((B, 4, 4, 512))).astype(np.float32)
+    kern = (rng.standard_normal((4, 4, 512, 8)) / 90).astype(np.float32)
+    mask = rng.random((B, 4096)) < 0.9
+    dout = rng.standard_normal((B, 4096)).astype(np.float32)
+    ref = np.einsum("bhwc,hwcf->bcf", feat.astype(np.float64), kern.astype(np.float64)).reshape(B, -1)
+    out = torch.empty(B, 4096, device="cuda")
+    fd, kd = cu(feat), cu(kern)
+    ops.sle_fwd(fd, kd, None, 0.9, out.data_ptr(), 4096)
+    assert rel_err(out.cpu().numpy(), ref) < TOL
+    ops.sle_fwd(fd, kd, cu(mask, torch.uint8), 0.9, out.data_ptr(), 4096)
+    assert rel_err(out.cpu().numpy(), np.where(mask, ref / 0.9, 0.0)) < TOL
+    ws = ops.Workspace(64 << 20, "cuda")
+    dk = torch.empty(4, 4, 512, 8, device="cuda")
+    ops.sle_bwd_kernel_grad(ws, fd, cu(dout).data_ptr(), 4096, dk.data_ptr())
+    refdk = np.einsum("bhwc,bcf->hwcf", feat.astype(np.float64), dout.reshape(B, 512, 8).astype(np.float64))
+    assert rel_err(dk.cpu().numpy(), refdk) < TOL
+
+
+@pytest.mark.parametrize("E,B,D", [(1, 33, 256), (10, 24, 256), (1, 50, 64)])
+def test_layernorm_tanh_fwd_bwd(E, B, D):
+    from oracle.drq import layer_norm
+    from serl_b200 import ops
+    rng = np.random.default_rng(5)
+    R = E * B
+    z = (rng.standard_normal((E, B, D)) * 2 + 0.3).astype(np.float32)
+    sc, bi = (1 + 0.2 * rng.standard_normal((E, D))).astype(np.float32), (0.1 * rng.standard_normal((E, D))).astype(np.float32)
+    dt = rng.standard_normal((E, B, D)).astype(np.float32)
+    zt = torch.as_tensor(z).double().requires_grad_(True)
+    sct, bit = torch.as_tensor(sc).double().requires_grad_(True), torch.as_tensor(bi).double().requires_grad_(True)
+    t_ref = torch.tanh(layer_norm(zt, sct[:, None, :], bit[:, None, :]))
+    t_ref.backward(torch.as_tensor(dt).double())
+    zd, scd, bid = cu(z), cu(sc), cu(bi)
+    t, xhat, rstd = torch.empty(R, D, device="cuda"), torch.empty(R, D, device="cuda"), torch.empty(R, device="cuda")
+    ops.ln_tanh_fwd(zd.data_ptr(), D, scd.data_ptr(), bid.data_ptr(), B, D if E > 1 else 0, t.data_ptr(), D, xhat.data_ptr(), rstd.data_ptr(), R, D)
+    assert rel_err(t.cpu().numpy().reshape(E, B, D), t_ref.detach().numpy()) < TOL
+    dz, dy = torch.empty(R, D, device="cuda"), torch.empty(R, D, device="cuda")
+    dsc, dbi = torch.empty(E, D, device="cuda"), torch.empty(E, D, device="cuda")
+    ops.ln_tanh_bwd(cu(dt).data_ptr(), D, t.data_ptr(), D, xhat.data_ptr(), rstd.data_ptr(), scd.data_ptr(), B, D if E > 1 else 0,
+                    dz.data_ptr(), dy.data_ptr(), dsc.data_ptr(), dbi.data_ptr(), R, D)
+    assert rel_err(dz.cpu().numpy().reshape(E, B, D), zt.grad.numpy()) < 5e-5
+    assert rel_err(dsc.cpu().numpy(), sct.grad.numpy()) < 5e-5
+    assert rel_err(dbi.cpu().numpy(), bit.grad.numpy()) < 5e-5
+
+
+def test_rng_kernels_match_jax_restatement():
+    from oracle import jax_prng as P
+    from serl_b200 import _lib as L
+    from serl_b200 import ops
+    key = P.prng_key(99)
+    rng_dev = torch.from_numpy(key.view(np.int32).copy()).view(torch.uint32).cuda()
+    keys = torch.zeros(2 * L.NUM_KEYS, dtype=torch.uint32, device="cuda")
+    ops.rng_schedule(rng_dev, keys, True, True)
+    hk, hr = np.zeros(16, np.uint32), key.copy()
+    L.call("serl_host_rng_schedule", hr.ctypes.data, hk.ctypes.data, 1, 1)
+    np.testing.assert_array_equal(keys.cpu().numpy(), hk)
+    np.testing.assert_array_equal(rng_dev.cpu().numpy(), hr)
+    k_na = hk[2 * L.KEY_CRITIC_NEXT: 2 * L.KEY_CRITIC_NEXT + 2]
+    for n in (1024, 7, 1):
+        eps = torch.empty(n, device="cuda")
+        ops.normal_fill(ops.key_ptr(keys, L.KEY_CRITIC_NEXT), eps, n)
+        np.testing.assert_allclose(eps.cpu().numpy(), P.normal(k_na, (n,)), rtol=0, atol=3e-6)
+    mask = torch.empty(16 * 4096, dtype=torch.uint8, device="cuda")
+    for j in range(2):
+        ops.dropout_mask_fill(ops.key_ptr(keys, L.KEY_CRITIC_NEXT), j, 0.9, mask, mask.numel())
+        np.testing.assert_array_equal(mask.cpu().numpy().astype(bool), P.bernoulli(P.fold_in(k_na, j), 0.9, (mask.numel(),)))
+    sub = torch.zeros(2, dtype=torch.int32, device="cuda")
+    ops.subsample_idx(ops.key_ptr(keys, L.KEY_CRITIC_SUBSAMPLE), 10, sub)
+    k_sub = hk[2 * L.KEY_CRITIC_SUBSAMPLE: 2 * L.KEY_CRITIC_SUBSAMPLE + 2]
+    np.testing.assert_array_equal(sub.cpu().numpy(), P.randint(k_sub, (2,), 0, 10))
+
+
+def test_tanh_gaussian_and_losses():
+    from oracle.drq import tanh_normal_sample_logp
+    from serl_b200 import ops
+    rng = np.random.default_rng(6)
+    B, A, E = 64, 4, 10
+    mu = rng.standard_normal((B, A)).astype(np.float32)
+    ls = (rng.standard_normal((B, A)) * 1.5).astype(np.float32)
+    ls[0, 0], ls[1, 1] = 3.0, -14.0                                       # hit both std clips
+    eps = rng.standard_normal((B, A)).astype(np.float32)
+    std = torch.clamp(torch.exp(torch.as_tensor(ls).double()), 1e-5, 5.0)
+    a_ref, lp_ref = tanh_normal_sample_logp(torch.as_tensor(mu).double(), std, torch.as_tensor(eps).double())
+    act, logp = torch.empty(B, A, device="cuda"), torch.empty(B, device="cuda")
+    u, sd = torch.empty(B, A, device="cuda"), torch.empty(B, A, device="cuda")
+    ops.tanh_gaussian_fwd(cu(mu), cu(ls), cu(eps), 1e-5, 5.0, act.data_ptr(), A, logp, u, sd, B, A)
+    assert rel_err(act.cpu().numpy(), a_ref.numpy()) < TOL and rel_err(logp.cpu().numpy(), lp_ref.numpy()) < TOL
+    # critic loss
+    q, qn = rng.standard_normal((E, B)).astype(np.float32), rng.standard_normal((E, B)).astype(np.float32)
+    r, m = rng.random(B).astype(np.float32), (rng.random(B) > 0.1).astype(np.float32)
+    sub = np.array([3, 3], np.int32)
+    y = r + 0.96 * m * np.minimum(qn[3], qn[3])
+    tq, dq, info = torch.empty(B, device="cuda"), torch.empty(E, B, device="cuda"), torch.zeros(4, device="cuda")
+    lam = cu(np.array([-4.6], np.float32))
+    ops.critic_loss(cu(q), cu(qn), cu(sub, torch.int32), 2, cu(r), cu(m), logp, lam.data_ptr(), False, 0.96, 1.0, tq, dq, info.data_ptr(), E, B)
+    assert rel_err(tq.cpu().numpy(), y) < TOL
+    assert rel_err(dq.cpu().numpy(), 2 * (q - y[None]) / (E * B)) < TOL
+    np.testing.assert_allclose(info.cpu().numpy()[:3], [((q - y[None]) ** 2).mean(), q.mean(), y.mean()], rtol=2e-5)
+    # temperature loss
+    dl, ti = torch.zeros(1, device="cuda"), torch.zeros(1, device="cuda")
+    ops.temperature_loss(logp, lam.data_ptr(), -2.0, 1.0, dl.data_ptr(), ti.data_ptr(), B)
+    lt = torch.tensor(-4.6, dtype=torch.float64, requires_grad=True)
+    ent = -lp_ref.mean()
+    loss = F.softplus(lt) * (ent - (-2.0))
+    loss.backward()
+    np.testing.assert_allclose(ti.item(), loss.item(), rtol=2e-5)
+    np.testing.assert_allclose(dl.item(), lt.grad.item(), rtol=2e-5)
+
+
+def test_adam_polyak_three_txs():
+    from oracle.drq import adam_tx_update, lr_schedule
+    from serl_b200 import ops
+    rng = np.random.default_rng(7)
+    n, seg = 1000, [400, 900, 1000]
+    p0, g = rng.standard_normal(n).astype(np.float32), rng.standard_normal(n).astype(np.float32)
+    P_, T_, M_, V_ = cu(p0), cu(p0), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    counts = torch.zeros(3, dtype=torch.int32, device="cuda")
+    lr_out = torch.zeros(3, device="cuda")
+    pr = torch.as_tensor(p0).double()
+    tr = pr.clone()
+    opts = [{"count": 0, "mu": {"x": torch.zeros(n).double()}, "nu": {"x": torch.zeros(n).double()}} for _ in range(3)]
+    warm = (0, 5, 0)
+    for step in range(7):
+        live = [(1, 0, 0), (0, 1, 1), (1, 0, 0)][step % 3]
+        gs = g * (step + 1)
+        ops.adam_polyak(P_, T_, M_, V_, cu(gs), seg, live, counts, (3e-4, 3e-4, 3e-4), warm, 0.005, bool(live[0]), lr_out)
+        total = torch.zeros(n).double()
+        for gid in range(3):                       # literal reference semantics: every tx over the whole vector
+            lo, hi = (0 if gid == 0 else seg[gid - 1]), seg[gid]
+            gg = torch.zeros(n).double()
+            if live[gid]:
+                gg[lo:hi] = torch.as_tensor(gs).double()[lo:hi]
+            lr = lr_schedule(opts[gid]["count"], 3e-4, warm[gid])
+            total += adam_tx_update({"x": gg}, opts[gid], lr)["x"]
+        pr = pr + total
+        if live[0]:
+            tr = pr * 0.005 + tr * 0.995
+    assert rel_err(P_.cpu().numpy(), pr.numpy()) < TOL and rel_err(T_.cpu().numpy(), tr.numpy()) < TOL
+    assert counts.cpu().tolist() == [7, 7, 7]
