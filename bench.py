@@ -42,7 +42,7 @@ FRAME_BYTES = 128 * 128 * 3
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default=os.environ.get("SERL_PRECISION", "fp32"), choices=["fp32", "bf16"])
@@ -123,19 +123,20 @@ def workload_config(args):
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.p, self.index = None, index
 
     def start(self):
         try:
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.index)],
                                       stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:                       # noqa: BLE001
             self.p = None
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        import datetime
         if self.p is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.p.terminate()
@@ -147,13 +148,16 @@ class ClockSampler:
         sm, mx, reasons = [], None, set()
         for ln in out.strip().splitlines():
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx = float(f[1])
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if t_begin is not None and not (t_begin - 0.05 <= ts <= t_end + 0.05):
+                    continue
+                sm.append(float(f[1])); mx = float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
@@ -225,20 +229,21 @@ def run_b200(args):
     def timed_load(e, batch, **kw):
         a, b = ev(), ev(); a.record(); orig_load(e, batch, **kw); b.record(); samp_ev.append((a, b))
 
+    clocks = ClockSampler(local)
+    clocks.start()
     for _ in range(args.warmup):
         agent.update_critics(next(it))
     agent._features, agent._load_batch = timed_features, timed_load
     launches0 = agent.kernel_launches
-    clocks = ClockSampler(local)
     barrier()
-    clocks.start()
+    w0 = time.time()
     t0, t1 = ev(), ev()
     t0.record()
     for _ in range(args.steps):
         agent.update_critics(next(it))
     t1.record()
     barrier()
-    clk = clocks.stop()
+    clk = clocks.stop(w0, time.time())
     agent._features, agent._load_batch = orig_features, orig_load
     ms = t0.elapsed_time(t1)
     launches = agent.kernel_launches - launches0

@@ -462,8 +462,12 @@ def update_high_utd(state: OracleState, cfg: OracleConfig, batch_unpacked: dict,
                        for k in ("critic_loss", "predicted_qs", "target_qs")},
             "actor": at["actor"], "temperature": at["temperature"]}
     for n in ("actor", "critic", "temperature"):
-        info[f"{n}_lr"] = float(np.mean([c[f"{n}_lr"] for c in crit] + [])) if False else at[f"{n}_lr"]
+        info[f"{n}_lr"] = at[f"{n}_lr"]          # sac.py:592: {**critic_infos, **actor_temp_infos}
     info["_aug"] = batch
+    merged = {n: {k: sum(c["_grads"][n][k].abs() for c in crit) + at["_grads"][n][k].abs() for k in at["_grads"][n]}
+              for n in at["_grads"]}
+    info["_grads"] = at["_grads"]
+    info["_grads_abs_all_calls"] = merged
     return info
 
 

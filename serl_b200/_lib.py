@@ -50,6 +50,12 @@ class GemmDesc(C.Structure):
                 ("sBiasZ", i64), ("ldc", i32), ("accumulate", i32), ("reduce_z", i32)]
 
 
+class ConvTcDesc(C.Structure):
+    _fields_ = [("x", vp), ("w", vp), ("y", vp), ("stats", vp), ("in_a", vp), ("in_b", vp), ("error", vp),
+                ("N", i32), ("Hi", i32), ("Wi", i32), ("Ci", i32), ("Ho", i32), ("Wo", i32), ("Co", i32), ("kh", i32),
+                ("kw", i32), ("stride", i32), ("pad_lo", i32), ("stem", i32)]
+
+
 class AdamDesc(C.Structure):
     _fields_ = [("params", vp), ("target", vp), ("m", vp), ("v", vp), ("grad", vp), ("n", i32), ("seg_end", i32 * 3),
                 ("live", i32 * 3), ("counts", vp), ("lr", f32 * 3), ("warmup", i32 * 3), ("b1", f32), ("b2", f32),
@@ -73,6 +79,11 @@ _PROTOS = {
     "serl_conv2d_nhwc_f32": [vp, C.c_int, vp, vp] + [C.c_int] * 10 + [vp],
     "serl_groupnorm_nhwc_f32": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, C.c_int, vp],
     "serl_maxpool3x3s2_nhwc_f32": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "serl_trunk_stem_prep_bf16": [vp, vp, C.c_int, C.c_int, C.c_int, vp],
+    "serl_conv2d_tc_bf16": [C.POINTER(ConvTcDesc), vp],
+    "serl_gn_finalize": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp],
+    "serl_maxpool_affine_bf16": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "serl_block_combine_bf16": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp],
     "serl_gemm_f32": [C.POINTER(GemmDesc), vp],
     "serl_sle_fwd": [vp, vp, vp, f32, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_sle_bwd_kernel_grad": [vp, vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],

@@ -1,0 +1,429 @@
+// Frozen ResNet-10 trunk, bf16 build: implicit-GEMM convolutions on the 5th-gen tensor cores
+// (tcgen05.mma, fp32 accumulators in TMEM), warp-specialised:
+//
+//   warps 0-3  producers: gather the im2col A tile (128 output pixels x 64 K) and the weight B tile straight
+//              into 128B-swizzled shared memory; the previous layer's GroupNorm + ReLU is applied to the operand
+//              in registers on the way (so normalised activations never round-trip through HBM); then the same
+//              warps run the epilogue: TMEM -> registers, GroupNorm partial sums (fp32, from the accumulators),
+//              bf16 pack, NHWC store.
+//   warp 4     allocates TMEM and issues tcgen05.mma (one elected lane), commits stage-free / accumulator-ready
+//              mbarriers.
+//
+// Layer algebra replaced (reference, relative to serl_launcher/serl_launcher): vision/resnet_v1.py:217-286
+// (conv_init 7x7/2 -> GroupNorm(4) -> ReLU -> max_pool -> 4 ResNetBlocks), :129-156 (ResNetBlock).
+// The 7x7/2 stem on 3 channels is rewritten exactly as a 4x4/1 convolution over a 2x2 space-to-depth image with
+// 12 channels (zero-extended 8x8 kernel), which gives K = 4 kernel rows x (4 taps x 12 ch = 48, padded to 64).
+// bf16 operands, fp32 accumulation: the 1e-2 tolerance build (north_star); the fp32 build is trunk_fp32.cu.
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "serl_b200.h"
+
+namespace serl {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 64;
+constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;          // 16 KiB
+constexpr int TC_THREADS = 160;
+
+struct ConvTcArgs {
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* w;        // [Co][num_kb * 64], K-major
+  __nv_bfloat16* y;              // (M, Co) raw convolution output (pre-GroupNorm)
+  float* stats;                  // (N, groups, 2): sum, sum of squares of the fp32 accumulators
+  const float* in_a;             // optional (N, Ci): operand transform relu(a * x + b)
+  const float* in_b;
+  int N, Hi, Wi, Ci, Ho, Wo, Co, kh, kw, stride, pad;
+  int M, num_kb, cblocks, Cg;
+  int32_t* error;
+};
+
+__device__ inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ inline void tc_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ inline void tc_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Bounded wait: a protocol bug must not hang the GPU box.  Returns false (and flags) on timeout.
+__device__ inline bool tc_mbar_wait(uint64_t* bar, uint32_t parity, int32_t* error) {
+  const uint32_t addr = smem_u32(bar);
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (;;) {
+    uint32_t done;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return true;
+    if (clock64() - t0 > 4000000000ll) break;               // ~2 s: flag and bail out instead of hanging the box
+  }
+  atomicOr(error, 2);
+  return false;
+}
+
+__device__ inline uint64_t make_smem_desc(uint32_t saddr) {
+  // K-major, SWIZZLE_128B: start>>4 | LBO(=1)<<16 | SBO(=1024B>>4)<<32 | version(1)<<46 | layout_type(2)<<61
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ inline void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ inline void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ inline void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ inline uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ inline float2 unpack_bf16x2(uint32_t u) {
+  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+}
+__device__ inline uint32_t affine_relu_bf16x2(uint32_t u, float a0, float b0, float a1, float b1) {
+  float2 f = unpack_bf16x2(u);
+  return pack_bf16x2(fmaxf(fmaf(f.x, a0, b0), 0.f), fmaxf(fmaf(f.y, a1, b1), 0.f));
+}
+
+template <int BN, int STAGES, bool kStem, bool kAffine>
+__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int B_STAGE = BN * TC_BK * 2;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * TC_A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
+  uint64_t* empty = full + STAGES;
+  uint64_t* tmem_full = empty + STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { tc_mbar_init(&full[s], 4); tc_mbar_init(&empty[s], 1); }
+    tc_mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------- producers -------------------------------
+    const int tid = threadIdx.x;
+    const int chunk = tid & 7, rsub = tid >> 3;
+    const int HoWo = a.Ho * a.Wo;
+    int rn[8], rh[8], rw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int gm = m0 + rsub + 16 * i;
+      if (gm < a.M) {
+        const int n = gm / HoWo, rem = gm - n * HoWo, ho = rem / a.Wo, wo = rem - ho * a.Wo;
+        rn[i] = n; rh[i] = ho * a.stride - a.pad; rw[i] = wo * a.stride - a.pad;
+      } else { rn[i] = -1; rh[i] = 0; rw[i] = 0; }
+    }
+    bool ok = true;
+    for (int kb = 0; kb < a.num_kb && ok; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      ok = tc_mbar_wait(&empty[s], ph ^ 1u, a.error);
+      uint8_t* As = sA + s * TC_A_STAGE;
+      int r = 0, sx = 0, c0 = 0;
+      if (!kStem) { const int tap = kb / a.cblocks; c0 = (kb - tap * a.cblocks) * TC_BK; r = tap / a.kw; sx = tap - r * a.kw; }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rsub + 16 * i;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (rn[i] >= 0) {
+          if (kStem) {
+            // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 12 ch = 48 contiguous bf16 (96 B)
+            if (chunk < 6) {
+              const __nv_bfloat16* src = a.x + (((size_t)rn[i] * a.Hi + (rh[i] + kb)) * a.Wi + rw[i]) * 12 + chunk * 8;
+              const uint2 lo = *reinterpret_cast<const uint2*>(src), hi = *reinterpret_cast<const uint2*>(src + 4);
+              v = make_uint4(lo.x, lo.y, hi.x, hi.y);
+            }
+          } else {
+            const int hi_ = rh[i] + r, wi_ = rw[i] + sx;
+            if (hi_ >= 0 && hi_ < a.Hi && wi_ >= 0 && wi_ < a.Wi) {
+              const int c = c0 + chunk * 8;
+              v = *reinterpret_cast<const uint4*>(a.x + (((size_t)rn[i] * a.Hi + hi_) * a.Wi + wi_) * a.Ci + c);
+              if (kAffine) {
+                const float4 a0 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c);
+                const float4 a1 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c + 4);
+                const float4 b0 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c);
+                const float4 b1 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c + 4);
+                v.x = affine_relu_bf16x2(v.x, a0.x, b0.x, a0.y, b0.y);
+                v.y = affine_relu_bf16x2(v.y, a0.z, b0.z, a0.w, b0.w);
+                v.z = affine_relu_bf16x2(v.z, a1.x, b1.x, a1.y, b1.y);
+                v.w = affine_relu_bf16x2(v.w, a1.z, b1.z, a1.w, b1.w);
+              }
+            }
+          }
+        }
+        *reinterpret_cast<uint4*>(As + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4)) = v;
+      }
+      uint8_t* Bs = sB + s * B_STAGE;
+      const size_t Kp = (size_t)a.num_kb * TC_BK;
+#pragma unroll
+      for (int j = 0; j < BN / 16; ++j) {
+        const int idx = tid + 128 * j, brow = idx >> 3, bch = idx & 7;
+        const uint4 v = *reinterpret_cast<const uint4*>(a.w + (size_t)(n0 + brow) * Kp + (size_t)kb * TC_BK + bch * 8);
+        *reinterpret_cast<uint4*>(Bs + (brow >> 3) * 1024 + (brow & 7) * 128 + ((bch ^ (brow & 7)) << 4)) = v;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&full[s]);
+    }
+    // ------------------------------- epilogue --------------------------------
+    ok = ok && tc_mbar_wait(tmem_full, 0u, a.error);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = warp * 32 + lane, gm = m0 + row;
+    const bool valid = gm < a.M;
+    const int n_img = valid ? gm / HoWo : 0;
+    const int seg = HoWo < 32 ? HoWo : 32;                  // lanes sharing one image (power of two >= 16)
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      float s = 0.f, ss = 0.f;
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+        s += f0 + f1; ss += f0 * f0 + f1 * f1;
+        pk[j] = pack_bf16x2(f0, f1);
+      }
+      if (!valid || !ok) { s = 0.f; ss = 0.f; }
+      for (int o = seg >> 1; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+      if (valid && ok) {
+        if ((lane & (seg - 1)) == 0) {
+          float* st = a.stats + ((size_t)n_img * 4 + (n0 + c0) / a.Cg) * 2;
+          atomicAdd(st, s); atomicAdd(st + 1, ss);
+        }
+        uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)gm * a.Co + n0 + c0);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else {
+    // ------------------------------- MMA issuer ------------------------------
+    // instruction descriptor: D=F32 (bit 4), A=B=BF16 (bits 7, 10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    bool ok = true;
+    for (int kb = 0; kb < a.num_kb && ok; ++kb) {
+      const int s = kb % STAGES;
+      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+      ok = tc_mbar_wait(&full[s], ph, a.error);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      if (lane == 0 && ok) {
+        const uint64_t ad = make_smem_desc(smem_u32(sA + s * TC_A_STAGE));
+        const uint64_t bd = make_smem_desc(smem_u32(sB + s * B_STAGE));
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k)                 // UMMA_K = 16 bf16 = 32 B: advance the start address by 2 (x16 B)
+          tc_mma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+        tc_commit(&empty[s]);                                // stage reusable once these MMAs retire
+        if (kb == a.num_kb - 1) tc_commit(tmem_full);        // accumulator complete
+      }
+      __syncwarp();
+    }
+    if (!ok && lane == 0) tc_mbar_arrive(tmem_full);         // let the epilogue warps out after a flagged timeout
+  }
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+// ---- stem input: uint8 crops -> normalised bf16, 2x2 space-to-depth, zero padded: (N,67,67,12) ------------
+__global__ void stem_prep_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ xs, int N, int H, int W, int Hs, int Ws) {
+  const size_t total = (size_t)N * Hs * Ws;
+  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(e % Ws); size_t r = e / Ws; const int aa = (int)(r % Hs); const int n = (int)(r / Hs);
+    uint32_t out[6];
+#pragma unroll
+    for (int pq = 0; pq < 4; ++pq) {
+      const int p = pq >> 1, q = pq & 1;
+      const int hi = 2 * aa + p - 3, wi = 2 * b + q - 3;          // explicit padding (3,3) of conv_init (resnet_v1.py:247)
+      float f[3] = {0.f, 0.f, 0.f};
+      if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
+        const uint8_t* px = x + (((size_t)n * H + hi) * W + wi) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) f[c] = ((float)px[c] / 255.0f - mean[c]) / stdv[c];
+      }
+      // channel order (p, q, c): element index pq*3 + c
+      const int base = pq * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int ei = base + c;
+        const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f[c]));
+        if (ei & 1) out[ei >> 1] |= h << 16; else out[ei >> 1] = h;
+      }
+    }
+    uint2* dst = reinterpret_cast<uint2*>(xs + e * 12);
+    dst[0] = make_uint2(out[0], out[1]); dst[1] = make_uint2(out[2], out[3]); dst[2] = make_uint2(out[4], out[5]);
+  }
+}
+
+// ---- GroupNorm finalize: sums -> per-(image, channel) affine  y = a*x + b --------------------------------
+__global__ void gn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ oa, float* __restrict__ ob, int N, int C, int Cg, float count, float eps) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N * C) return;
+  const int n = e / C, c = e - n * C, g = c / Cg;
+  const float s = stats[((size_t)n * 4 + g) * 2], ss = stats[((size_t)n * 4 + g) * 2 + 1];
+  const float mean = s / count;
+  const float var = fmaxf(ss / count - mean * mean, 0.f);
+  const float a = rsqrtf(var + eps) * gamma[c];
+  oa[e] = a; ob[e] = beta[c] - mean * a;
+}
+
+// ---- max_pool 3x3/2 SAME over relu(a*x+b), bf16 in/out; thread per 8 channels ------------------------------
+__global__ void maxpool_affine_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ga, const float* __restrict__ gb,
+                                           __nv_bfloat16* __restrict__ y, int N, int Hi, int Wi, int C, int Ho, int Wo) {
+  const int c8n = C >> 3;
+  const size_t total = (size_t)N * Ho * Wo * c8n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(e % c8n); size_t r = e / c8n;
+    const int wo = (int)(r % Wo); r /= Wo; const int ho = (int)(r % Ho); const int n = (int)(r / Ho);
+    float av[8], bv[8], m[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { av[j] = ga[(size_t)n * C + c8 * 8 + j]; bv[j] = gb[(size_t)n * C + c8 * 8 + j]; m[j] = 0.f; }   // relu output >= 0
+    for (int dh = 0; dh < 3; ++dh) {
+      const int hi = ho * 2 + dh; if (hi >= Hi) continue;                 // SAME on even sizes: pad low 0 / high 1
+      for (int dw = 0; dw < 3; ++dw) {
+        const int wi = wo * 2 + dw; if (wi >= Wi) continue;
+        const uint4 v = *reinterpret_cast<const uint4*>(x + (((size_t)n * Hi + hi) * Wi + wi) * C + c8 * 8);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(u[j]);
+          m[2 * j] = fmaxf(m[2 * j], fmaf(f.x, av[2 * j], bv[2 * j]));
+          m[2 * j + 1] = fmaxf(m[2 * j + 1], fmaf(f.y, av[2 * j + 1], bv[2 * j + 1]));
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(y + (((size_t)n * Ho + ho) * Wo + wo) * C + c8 * 8) =
+        make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+  }
+}
+
+// ---- block output: relu( (a2*y2 + b2) + residual ), residual = res (identity) or ar*res + br (projection) ----
+__global__ void block_combine_bf16_kernel(const __nv_bfloat16* __restrict__ y2, const float* __restrict__ a2, const float* __restrict__ b2,
+                                          const __nv_bfloat16* __restrict__ res, const float* __restrict__ ar, const float* __restrict__ br,
+                                          __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, int N, int HW, int C) {
+  const int c8n = C >> 3;
+  const size_t total = (size_t)N * HW * c8n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(e % c8n); const size_t pix = e / c8n; const int n = (int)(pix / HW);
+    const size_t off = pix * C + c8 * 8, co = (size_t)n * C + c8 * 8;
+    const uint4 yv = *reinterpret_cast<const uint4*>(y2 + off), rv = *reinterpret_cast<const uint4*>(res + off);
+    const uint32_t yu[4] = {yv.x, yv.y, yv.z, yv.w}, ru[4] = {rv.x, rv.y, rv.z, rv.w};
+    float o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fy = unpack_bf16x2(yu[j]), fr = unpack_bf16x2(ru[j]);
+      float r0 = fr.x, r1 = fr.y;
+      if (ar) { r0 = fmaf(r0, ar[co + 2 * j], br[co + 2 * j]); r1 = fmaf(r1, ar[co + 2 * j + 1], br[co + 2 * j + 1]); }
+      o[2 * j] = fmaxf(fmaf(fy.x, a2[co + 2 * j], b2[co + 2 * j]) + r0, 0.f);
+      o[2 * j + 1] = fmaxf(fmaf(fy.y, a2[co + 2 * j + 1], b2[co + 2 * j + 1]) + r1, 0.f);
+    }
+    if (out_f32) {
+      *reinterpret_cast<float4*>(out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<float4*>(out_f32 + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    } else {
+      *reinterpret_cast<uint4*>(out_bf16 + off) =
+          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+  }
+}
+
+template <int BN, int STAGES, bool kStem, bool kAffine>
+static int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (TC_A_STAGE + BN * TC_BK * 2) + 1024 + 128;
+  auto kern = conv_tc_kernel<BN, STAGES, kStem, kAffine>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv_tc)");
+    configured = true;
+  }
+  dim3 grid(ceil_div(a.M, TC_BM), a.Co / BN);
+  kern<<<grid, TC_THREADS, smem, st>>>(a);
+  return check_launch("conv_tc_kernel");
+}
+
+}  // namespace serl
+
+using namespace serl;
+#define ST(s) static_cast<cudaStream_t>(s)
+
+extern "C" int serl_trunk_stem_prep_bf16(const uint8_t* x, void* xs, int N, int H, int W, void* stream) {
+  const int Hs = H / 2 + 3, Ws = W / 2 + 3;
+  size_t total = (size_t)N * Hs * Ws;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  stem_prep_kernel<<<blocks, 256, 0, ST(stream)>>>(x, static_cast<__nv_bfloat16*>(xs), N, H, W, Hs, Ws);
+  return check_launch("stem_prep_kernel");
+}
+
+extern "C" int serl_conv2d_tc_bf16(const serl_conv_tc_desc* d, void* stream) {
+  if (!d || !d->x || !d->w || !d->y || !d->stats || !d->error) { set_last_error("serl_conv2d_tc_bf16: invalid descriptor"); return SERL_ERR_INVALID; }
+  ConvTcArgs a{};
+  a.x = static_cast<const __nv_bfloat16*>(d->x); a.w = static_cast<const __nv_bfloat16*>(d->w); a.y = static_cast<__nv_bfloat16*>(d->y);
+  a.stats = d->stats; a.in_a = d->in_a; a.in_b = d->in_b; a.error = d->error;
+  a.N = d->N; a.Hi = d->Hi; a.Wi = d->Wi; a.Ci = d->Ci; a.Co = d->Co; a.kh = d->kh; a.kw = d->kw; a.stride = d->stride; a.pad = d->pad_lo;
+  a.Ho = d->Ho; a.Wo = d->Wo; a.M = d->N * d->Ho * d->Wo; a.Cg = d->Co / 4;
+  const int HoWo = d->Ho * d->Wo;
+  if (d->Co % 64 != 0 || (HoWo & (HoWo - 1)) != 0 || HoWo < 16) {
+    set_last_error("serl_conv2d_tc_bf16: unsupported shape (Co=%d Ho*Wo=%d)", d->Co, HoWo); return SERL_ERR_UNSUPPORTED;
+  }
+  if (d->stem) {
+    a.num_kb = 4; a.cblocks = 1;
+    if (d->Co != 64) { set_last_error("serl_conv2d_tc_bf16: stem expects Co=64"); return SERL_ERR_UNSUPPORTED; }
+    return launch_conv_tc<64, 4, true, false>(a, ST(stream));
+  }
+  if (d->Ci % 64 != 0) { set_last_error("serl_conv2d_tc_bf16: Ci %% 64 != 0"); return SERL_ERR_UNSUPPORTED; }
+  a.cblocks = d->Ci / 64; a.num_kb = d->kh * d->kw * a.cblocks;
+  const bool aff = d->in_a != nullptr;
+  if (d->Co == 64) return aff ? launch_conv_tc<64, 4, false, true>(a, ST(stream)) : launch_conv_tc<64, 4, false, false>(a, ST(stream));
+  return aff ? launch_conv_tc<128, 3, false, true>(a, ST(stream)) : launch_conv_tc<128, 3, false, false>(a, ST(stream));
+}
+
+extern "C" int serl_gn_finalize(const float* stats, const float* gamma, const float* beta, float* out_a, float* out_b, int N, int C,
+                                int HW, float eps, void* stream) {
+  const int Cg = C / 4;
+  gn_finalize_kernel<<<ceil_div(N * C, 256), 256, 0, ST(stream)>>>(stats, gamma, beta, out_a, out_b, N, C, Cg, (float)HW * (float)Cg, eps);
+  return check_launch("gn_finalize_kernel");
+}
+
+extern "C" int serl_maxpool_affine_bf16(const void* x, const float* a, const float* b, void* y, int N, int Hi, int Wi, int C, void* stream) {
+  const int Ho = Hi / 2, Wo = Wi / 2;
+  size_t total = (size_t)N * Ho * Wo * (C / 8);
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  maxpool_affine_bf16_kernel<<<blocks, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(x), a, b, static_cast<__nv_bfloat16*>(y), N, Hi, Wi, C, Ho, Wo);
+  return check_launch("maxpool_affine_bf16_kernel");
+}
+
+extern "C" int serl_block_combine_bf16(const void* y2, const float* a2, const float* b2, const void* res, const float* ar, const float* br,
+                                       void* out_bf16, float* out_f32, int N, int HW, int C, void* stream) {
+  size_t total = (size_t)N * HW * (C / 8);
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  block_combine_bf16_kernel<<<blocks, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(y2), a2, b2, static_cast<const __nv_bfloat16*>(res), ar, br,
+                                                            static_cast<__nv_bfloat16*>(out_bf16), out_f32, N, HW, C);
+  return check_launch("block_combine_bf16_kernel");
+}

@@ -1,0 +1,132 @@
+"""bf16 / tcgen05 build of the frozen ResNet-10 trunk: orchestration + one-time weight packing.
+
+Same layer algebra as the fp32 build (engine.Engine.trunk_forward; reference vision/resnet_v1.py:217-286),
+re-associated so that GroupNorm never makes its own pass over HBM:
+  conv (tensor cores) writes the raw bf16 output and accumulates the GroupNorm sums in its epilogue;
+  a tiny finalize kernel turns the sums into per-(image, channel) affines;
+  the NEXT conv applies relu(a*x+b) to its operand while gathering it (max-pool / block-combine do the same).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from .params import STAGES
+
+
+def _s():
+    return L.stream_ptr()
+
+
+def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
+    """HWIO fp32 (kh,kw,Ci,Co) -> bf16 [Co][kh*kw*Ci], K-major (K order = (kh, kw, ci), the im2col gather order)."""
+    kh, kw, ci, co = w.shape
+    return w.permute(3, 0, 1, 2).reshape(co, kh * kw * ci).to(torch.bfloat16).contiguous()
+
+
+def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
+    """conv_init (7,7,3,64) -> exact 4x4 space-to-depth kernel, bf16 [64][4 rows x 64] (48 valid K per row).
+    ws[r', s', p, q, c, co] = w8[2r'+p, 2s'+q, c, co] with w8 = w zero-extended to 8x8."""
+    co = w.shape[-1]
+    w8 = torch.zeros(8, 8, 3, co, dtype=w.dtype, device=w.device)
+    w8[:7, :7] = w
+    ws = w8.view(4, 2, 4, 2, 3, co).permute(0, 2, 1, 3, 4, 5)            # (r', s', p, q, c, co)
+    rows = ws.reshape(4, 48, co)                                        # k within a row = s'*12 + (p*2+q)*3 + c
+    out = torch.zeros(co, 4, 64, dtype=torch.float32, device=w.device)
+    out[:, :, :48] = rows.permute(2, 0, 1)
+    return out.reshape(co, 256).to(torch.bfloat16).contiguous()
+
+
+class _Plan:
+    """Per-(engine, N) bf16 activation buffers."""
+
+    def __init__(self, N, hw, dev):
+        bf = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)
+        s2 = hw // 2
+        self.hs = s2 + 3
+        self.xs = bf(N, self.hs, self.hs, 12)
+        self.y0 = bf(N, s2, s2, 64)
+        self.buf = [bf(N * (s2 // 2) * (s2 // 2) * 64) for _ in range(5)]
+        self.stats = torch.zeros(3, N, 4, 2, dtype=torch.float32, device=dev)
+        self.aff = torch.empty(3, 2, N, 512, dtype=torch.float32, device=dev)
+        self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+
+
+def _conv(plan, x, w, y, stats, N, Hi, Wi, Ci, Ho, Wo, Co, k, stride, pad_lo, in_ab=None, stem=False):
+    d = L.ConvTcDesc()
+    d.x, d.w, d.y, d.stats = x.data_ptr(), w.data_ptr(), y.data_ptr(), stats.data_ptr()
+    if in_ab is not None:
+        d.in_a, d.in_b = in_ab[0].data_ptr(), in_ab[1].data_ptr()
+    d.error = plan.error.data_ptr()
+    d.N, d.Hi, d.Wi, d.Ci, d.Ho, d.Wo, d.Co, d.kh, d.kw, d.stride, d.pad_lo, d.stem = N, Hi, Wi, Ci, Ho, Wo, Co, k, k, stride, pad_lo, int(stem)
+    L.call("serl_conv2d_tc_bf16", C.byref(d), _s())
+
+
+def _finalize(stats, gamma, beta, ab, N, Cc, HW):
+    a, b = ab[0].view(-1)[:N * Cc].view(N, Cc), ab[1].view(-1)[:N * Cc].view(N, Cc)
+    L.call("serl_gn_finalize", stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), a.data_ptr(), b.data_ptr(), N, Cc, HW, 1e-5, _s())
+    return a, b
+
+
+def packed_weights(engine, cam):
+    cache = engine.__dict__.setdefault("_tc_weights", {})
+    w = engine.trunk[cam]
+    ver = tuple(t._version for t in w.values())
+    if cam not in cache or cache[cam][0] != ver:
+        packed = {k: (pack_stem_weight(v) if k == "conv_init/kernel" else pack_conv_weight(v)) for k, v in w.items() if k.endswith("kernel")}
+        cache[cam] = (ver, packed)
+    return cache[cam][1]
+
+
+def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
+    """pix (N,hw,hw,3) uint8 -> feats[:N] (N,4,4,512) fp32."""
+    N, hw = pix.shape[0], pix.shape[1]
+    plans = engine.__dict__.setdefault("_tc_plans", {})
+    if N not in plans:
+        plans[N] = _Plan(N, hw, pix.device)
+    p = plans[N]
+    w, wp = engine.trunk[cam], packed_weights(engine, cam)
+    s = hw // 2
+    L.call("serl_trunk_stem_prep_bf16", pix.data_ptr(), p.xs.data_ptr(), N, hw, hw, _s())
+    p.stats.zero_()
+    _conv(p, p.xs, wp["conv_init/kernel"], p.y0, p.stats[0], N, p.hs, p.hs, 12, s, s, 64, 4, 1, 0, stem=True)
+    a0, b0 = _finalize(p.stats[0], w["norm_init/scale"], w["norm_init/bias"], p.aff[0], N, 64, s * s)
+    s //= 2
+    x = p.buf[0][:N * s * s * 64].view(N, s, s, 64)
+    L.call("serl_maxpool_affine_bf16", p.y0.data_ptr(), a0.data_ptr(), b0.data_ptr(), x.data_ptr(), N, 2 * s, 2 * s, 64, _s())
+    engine.launches += 5
+    free, cur, cin = [1, 2, 3, 4], 0, 64
+    for i, (f, stride) in enumerate(STAGES):
+        b = f"ResNetBlock_{i}"
+        so = s // stride
+        iy, iy2, ir, io = free
+        view = lambda j: p.buf[j][:N * so * so * f].view(N, so, so, f)
+        yA, yB, yP, out = view(iy), view(iy2), view(ir), view(io)
+        p.stats.zero_()
+        lo = 1 if stride == 1 else 0                                   # XLA SAME on even sizes: pad low 0 / high 1
+        _conv(p, x, wp[f"{b}/Conv_0/kernel"], yA, p.stats[0], N, s, s, cin, so, so, f, 3, stride, lo)
+        abA = _finalize(p.stats[0], w[f"{b}/MyGroupNorm_0/scale"], w[f"{b}/MyGroupNorm_0/bias"], p.aff[0], N, f, so * so)
+        _conv(p, yA, wp[f"{b}/Conv_1/kernel"], yB, p.stats[1], N, so, so, f, so, so, f, 3, 1, 1, in_ab=abA)
+        abB = _finalize(p.stats[1], w[f"{b}/MyGroupNorm_1/scale"], w[f"{b}/MyGroupNorm_1/bias"], p.aff[1], N, f, so * so)
+        last = i == len(STAGES) - 1
+        if stride != 1 or cin != f:
+            _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, p.stats[2], N, s, s, cin, so, so, f, 1, stride, 0)
+            abP = _finalize(p.stats[2], w[f"{b}/norm_proj/scale"], w[f"{b}/norm_proj/bias"], p.aff[2], N, f, so * so)
+            res, ar, br = yP, abP[0].data_ptr(), abP[1].data_ptr()
+            engine.launches += 2
+        else:
+            res, ar, br = x, None, None
+        L.call("serl_block_combine_bf16", yB.data_ptr(), abB[0].data_ptr(), abB[1].data_ptr(), res.data_ptr(), ar, br,
+               None if last else out.data_ptr(), feats.data_ptr() if last else None, N, so * so, f, _s())
+        engine.launches += 6
+        free, cur = [cur, iy, iy2, ir], io
+        x, s, cin = out, so, f
+    return feats
+
+
+def check_error(engine):
+    for p in engine.__dict__.get("_tc_plans", {}).values():
+        if int(p.error.item()):
+            raise L.SerlError("conv_tc_kernel: pipeline barrier timeout (flagged by the kernel)")

@@ -41,15 +41,28 @@ def _flat_grads(info, group_paths):
     return {k: info["_grads"][g][k] for g, paths in group_paths.items() for k in paths}
 
 
-def _compare_state(agent, ostate, what=""):
+def _compare_state(agent, ostate, oinfo, what=""):
+    """Post-step params / target / rng vs the oracle transition from the SAME pre-step state.
+
+    Adam normalises the step by |g|: an entry whose gradient is at fp32 noise level (|g| << max|g| of its leaf) can
+    legitimately move by up to ~2*lr in either direction in float32 (the JAX fp32 reference has the same property
+    against a float64 run), so such entries get an lr-sized allowance; well-conditioned entries must match tightly."""
     from serl_b200.params import flatten
     p, tp = flatten(agent.state.params), flatten(agent.state.target_params)
-    worst = 0.0
+    lr = agent._cfg.lr[0]
+    gsum = None
+    for g in oinfo.get("_grads_abs_all_calls", oinfo["_grads"]).values():
+        gsum = {k: np.abs(v.numpy()) for k, v in g.items()} if gsum is None else {k: gsum[k] + np.abs(g[k].numpy()) for k in gsum}
     for k in p:
-        scale = max(np.abs(ostate.params[k].numpy()).max(), 1e-3)
-        worst = max(worst, np.abs(p[k] - ostate.params[k].numpy()).max() / scale)
-        worst = max(worst, np.abs(tp[k] - ostate.target_params[k].numpy()).max() / scale)
-    assert worst < P_TOL, f"{what}: params/target deviate {worst:.2e}"
+        ref, tref = ostate.params[k].numpy(), ostate.target_params[k].numpy()
+        scale = max(np.abs(ref).max(), 1e-3)
+        g = gsum[k]
+        noisy = g < 2e-2 * max(g.max(), 1e-30)
+        allow = P_TOL * scale + lr * np.where(noisy, 2.2, 5e-3)
+        bad = np.abs(p[k] - ref) > allow
+        assert not bad.any(), f"{what}: {k}: {bad.sum()} entries off, worst {np.abs(p[k] - ref).max():.2e} (scale {scale:.2e})"
+        bad_t = np.abs(tp[k] - tref) > P_TOL * scale + agent._cfg.tau * allow
+        assert not bad_t.any(), f"{what}: target {k}: worst {np.abs(tp[k] - tref).max():.2e}"
     np.testing.assert_array_equal(agent.state.rng, ostate.rng)
 
 
@@ -59,9 +72,10 @@ def test_update_critics_matches_oracle(cams, B):
     from oracle.replay import unpack
     agent, rb = _setup(cams, B)
     _perturb(agent)
-    ostate, ocfg = oracle_state_from_agent(agent), oracle_cfg_from_agent(agent)
+    ocfg = oracle_cfg_from_agent(agent)
     it = rb.get_iterator(sample_args={"batch_size": B, "pack_obs_and_next_obs": True})
     for step in range(2):
+        ostate = oracle_state_from_agent(agent)
         batch = next(it)
         host = unpack(to_numpy_tree({k: v for k, v in batch.to_dict().items() if k != "_indices"}))
         agent, info = agent.update_critics(batch)
@@ -85,7 +99,7 @@ def test_update_critics_matches_oracle(cams, B):
                 ref = oinfo["_grads"]["critic"][leaf.path].numpy()
                 got = st.view(st.grad, leaf.path).cpu().numpy()
                 assert np.abs(got - ref).max() <= G_TOL * max(np.abs(ref).max(), 1e-8), leaf.path
-        _compare_state(agent, ostate, f"step {step}")
+        _compare_state(agent, ostate, oinfo, f"step {step}")
     assert agent.state.step == 2
     agent.check_status()
 
@@ -99,13 +113,16 @@ def test_learner_iteration_matches_oracle():
     cams, B = ("front",), 16
     agent, rb = _setup(cams, B, seed=7)
     _perturb(agent, seed=1)
-    ostate, ocfg = oracle_state_from_agent(agent), oracle_cfg_from_agent(agent)
+    ocfg = oracle_cfg_from_agent(agent)
     it = rb.get_iterator(sample_args={"batch_size": B, "pack_obs_and_next_obs": True})
     for rep in range(2):
+        ostate = oracle_state_from_agent(agent)
         batch = next(it)
         host = unpack(to_numpy_tree({k: v for k, v in batch.to_dict().items() if k != "_indices"}))
         agent, _ = agent.update_critics(batch)
-        O.update_critics(ostate, ocfg, host)
+        oc = O.update_critics(ostate, ocfg, host)
+        _compare_state(agent, ostate, oc, f"iteration {rep} critics")
+        ostate = oracle_state_from_agent(agent)
         batch = next(it)
         host = unpack(to_numpy_tree({k: v for k, v in batch.to_dict().items() if k != "_indices"}))
         agent, info = agent.update_high_utd(batch, utd_ratio=1)
@@ -124,7 +141,9 @@ def test_learner_iteration_matches_oracle():
                 ref = oinfo["_grads"]["actor" if leaf.group == 1 else "temperature"][leaf.path].numpy()
                 got = st.view(st.grad, leaf.path).cpu().numpy()
                 assert np.abs(got - ref).max() <= G_TOL * max(np.abs(ref).max(), 1e-8), leaf.path
-        _compare_state(agent, ostate, f"iteration {rep}")
+        # update_high_utd = two `update` calls; the oracle's gradient record is of the last one (actor+temperature),
+        # the critic-tx entries moved in the first: merge both records for the conditioning mask
+        _compare_state(agent, ostate, oinfo, f"iteration {rep}")
         assert float(info["critic_lr"]) == pytest.approx(3e-4)
 
 
@@ -151,15 +170,25 @@ def test_rlpd_concat_and_dict_batches():
     agent, info = agent.update_critics(both)
     oinfo = O.update_critics(ostate, ocfg, host)
     np.testing.assert_allclose(float(info["critic"]["critic_loss"]), oinfo["critic"]["critic_loss"], rtol=Q_TOL)
-    _compare_state(agent, ostate, "rlpd")
-    # same thing fed as a host dict (packed layout, as the reference's sample() returns it)
-    agent2, _ = _setup(cams, 2 * B, seed=9)
-    agent2.state.replace(params=oracle_tree(ostate.params), target_params=oracle_tree(ostate.target_params), rng=ostate.rng)
-    agent2._store.m.copy_(agent._store.m); agent2._store.v.copy_(agent._store.v); agent2._store.counts.copy_(agent._store.counts)
-    b3 = rb.sample(2 * B, pack_obs_and_next_obs=True)
+    _compare_state(agent, ostate, oinfo, "rlpd")
+
+
+def test_dict_batch_equals_handle_batch():
+    """A host dict in the reference's packed layout (what its sample() returns) gives bit-identical updates to the lazy handle."""
+    cams, B = ("front",), 8
+    agent, rb = _setup(cams, B, seed=9)
+    agent2, _ = _setup(cams, B, seed=9)
+    _perturb(agent, seed=2)
+    _perturb(agent2, seed=2)
+    torch.testing.assert_close(agent._store.params, agent2._store.params, rtol=0, atol=0)
+    b3 = rb.sample(B, pack_obs_and_next_obs=True)
     d3 = to_numpy_tree({k: v for k, v in b3.to_dict().items() if k != "_indices"})
     agent.update_critics(b3)
     agent2.update_critics(d3)
+    torch.testing.assert_close(agent._store.params, agent2._store.params, rtol=0, atol=0)
+    torch.testing.assert_close(agent._engines[B].q, agent2._engines[B].q, rtol=0, atol=0)
+    agent.update_high_utd(b3, utd_ratio=1)
+    agent2.update_high_utd(d3, utd_ratio=1)
     torch.testing.assert_close(agent._store.params, agent2._store.params, rtol=0, atol=0)
 
 
@@ -213,5 +242,5 @@ def test_state_sac_update_high_utd_matches_oracle():
     np.testing.assert_allclose(float(info["critic"]["critic_loss"]), oinfo["critic"]["critic_loss"], rtol=Q_TOL)
     np.testing.assert_allclose(float(info["actor"]["actor_loss"]), oinfo["actor"]["actor_loss"], rtol=Q_TOL, atol=1e-6)
     np.testing.assert_allclose(float(info["actor_lr"]), 3e-4 * (700 + utd) / 2000, rtol=1e-6)
-    _compare_state(agent, ostate, "state sac")
+    _compare_state(agent, ostate, oinfo, "state sac")
     assert agent.state.step == utd + 1
