@@ -119,3 +119,19 @@ def test_state_sac_high_utd_and_sample_actions(dry):
     assert tree["modules_critic"]["Dense_0"]["kernel"].shape == (10, 256, 1)
     os_ = agent.state.opt_states
     assert set(os_) == {"actor", "critic", "temperature"} and os_["actor"]["count"] == 0    # counts live on the (dry) device
+
+
+def test_bf16_trunk_call_sequence(dry):
+    from serl_b200.utils.launcher import make_drq_agent
+    cams = ("front",)
+    rb = _ring(cams, 64, 128)
+    trs = random_transitions(np.random.default_rng(0), 40, cams, 128)
+    for tr in trs:
+        rb.insert(tr)
+    agent = make_drq_agent(1, trs[0]["observations"], trs[0]["actions"], image_keys=cams, encoder_type="resnet-pretrained", device="cpu",
+                           precision="bf16")
+    del dry[:]
+    agent.update_critics(rb.sample(4, pack_obs_and_next_obs=True))
+    assert dry.count("serl_conv2d_tc_bf16") == 12 and dry.count("serl_conv2d_nhwc_f32") == 0
+    assert dry.count("serl_gn_finalize") == 12 and dry.count("serl_block_combine_bf16") == 4
+    assert dry.count("serl_trunk_stem_prep_bf16") == 1 and dry.count("serl_maxpool_affine_bf16") == 1
