@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("SERL_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("SERL_PRECISION", "fp32"), choices=["fp32", "bf16", "fp16"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--cams", type=int, default=1)
     ap.add_argument("--capacity", type=int, default=100_000)
@@ -286,7 +286,7 @@ def run_b200(args):
     samp_gbs = samp_bytes / 1e9 / (samp_ms / 1e3)
     line = {"metric": "drq_critic_grad_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic", "impl": "b200",
+            "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic", "impl": "b200",
             "config": workload_config(args),
             "clocks": clk,
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h / args.steps},

@@ -120,27 +120,29 @@ int serl_groupnorm_nhwc_f32(const float* x, float* y, const float* scale, const 
                             int N, int HW, int C, int groups, float eps, int relu, void* stream);
 int serl_maxpool3x3s2_nhwc_f32(const float* x, float* y, int N, int Hi, int Wi, int C, void* stream);
 
-/* ---- frozen ResNet-10 trunk, bf16 build on tcgen05 tensor cores (same layers as above) ------------ */
-/* uint8 crops (N,H,W,3) -> normalised bf16, 2x2 space-to-depth, zero padded: xs (N, H/2+3, W/2+3, 12) */
-int serl_trunk_stem_prep_bf16(const uint8_t* x, void* xs, int N, int H, int W, void* stream);
+/* ---- frozen ResNet-10 trunk, 16-bit build on tcgen05 tensor cores (same layers as above) ---------- */
+/* operand format of the kind::f16 MMAs: bf16, or fp16 (same throughput, 3 more mantissa bits; packs saturate) */
+enum { SERL_FMT_BF16 = 0, SERL_FMT_FP16 = 1 };
+/* uint8 crops (N,H,W,3) -> normalised 16-bit, 2x2 space-to-depth, zero padded: xs (N, H/2+3, W/2+3, 12) */
+int serl_trunk_stem_prep_h16(const uint8_t* x, void* xs, int N, int H, int W, int fmt, void* stream);
 typedef struct serl_conv_tc_desc {
-  const void* x;           /* bf16 NHWC (N,Hi,Wi,Ci); stem: the space-to-depth image (Hi,Wi = its dims, Ci ignored) */
-  const void* w;           /* bf16 [Co][K], K-major, K = kh*kw*Ci (stem: 4 x 64 with 48 valid per row)             */
-  void* y;                 /* bf16 (N,Ho,Wo,Co) raw convolution output (pre-GroupNorm)                              */
+  const void* x;           /* 16-bit NHWC (N,Hi,Wi,Ci); stem: the space-to-depth image (Hi,Wi = its dims, Ci ignored) */
+  const void* w;           /* 16-bit [Co][K], K-major, K = kh*kw*Ci (stem: 4 x 64 with 48 valid per row)             */
+  void* y;                 /* 16-bit (N,Ho,Wo,Co) raw convolution output (pre-GroupNorm)                              */
   float* stats;            /* (N,4,2) fp32 sum / sum-of-squares per GroupNorm group, accumulated (pre-zero it)       */
   const float* in_a;       /* optional (N,Ci): operand transform relu(in_a*x + in_b) = previous GroupNorm + ReLU      */
   const float* in_b;
   int32_t* error;          /* device int32, OR-ed with 2 if a pipeline barrier timed out                             */
-  int32_t N, Hi, Wi, Ci, Ho, Wo, Co, kh, kw, stride, pad_lo, stem;
+  int32_t N, Hi, Wi, Ci, Ho, Wo, Co, kh, kw, stride, pad_lo, stem, fmt;
 } serl_conv_tc_desc;
-int serl_conv2d_tc_bf16(const serl_conv_tc_desc* d, void* stream);
+int serl_conv2d_tc_h16(const serl_conv_tc_desc* d, void* stream);
 /* (N,4,2) sums -> per-(image, channel) affine a = rstd*gamma, b = beta - mean*a (flax GroupNorm statistics) */
 int serl_gn_finalize(const float* stats, const float* gamma, const float* beta, float* out_a, float* out_b, int N, int C,
                      int HW, float eps, void* stream);
-int serl_maxpool_affine_bf16(const void* x, const float* a, const float* b, void* y, int N, int Hi, int Wi, int C, void* stream);
-/* relu((a2*y2+b2) + residual), residual = res or ar*res+br; writes bf16 (next block) or fp32 (final features) */
-int serl_block_combine_bf16(const void* y2, const float* a2, const float* b2, const void* res, const float* ar, const float* br,
-                            void* out_bf16, float* out_f32, int N, int HW, int C, void* stream);
+int serl_maxpool_affine_h16(const void* x, const float* a, const float* b, void* y, int N, int Hi, int Wi, int C, int fmt, void* stream);
+/* relu((a2*y2+b2) + residual), residual = res or ar*res+br; writes 16-bit (next block) or fp32 (final features) */
+int serl_block_combine_h16(const void* y2, const float* a2, const float* b2, const void* res, const float* ar, const float* br,
+                           void* out_h16, float* out_f32, int N, int HW, int C, int fmt, void* stream);
 
 /* ---- dense algebra for the trainable heads (fp32) ---------------------------------------------- */
 typedef struct serl_gemm_desc {

@@ -15,6 +15,7 @@ ABI_VERSION = 1
 (KEY_CROP_OBS, KEY_CROP_NEXT, KEY_CRITIC_NEXT, KEY_CRITIC_SUBSAMPLE, KEY_ACTOR_DROPOUT, KEY_ACTOR_SAMPLE,
  KEY_TEMP_NEXT) = range(7)
 NUM_KEYS = 8
+FMT_BF16, FMT_FP16 = 0, 1
 
 vp, i32, i64, u32, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint32, C.c_uint64, C.c_float
 
@@ -53,7 +54,7 @@ class GemmDesc(C.Structure):
 class ConvTcDesc(C.Structure):
     _fields_ = [("x", vp), ("w", vp), ("y", vp), ("stats", vp), ("in_a", vp), ("in_b", vp), ("error", vp),
                 ("N", i32), ("Hi", i32), ("Wi", i32), ("Ci", i32), ("Ho", i32), ("Wo", i32), ("Co", i32), ("kh", i32),
-                ("kw", i32), ("stride", i32), ("pad_lo", i32), ("stem", i32)]
+                ("kw", i32), ("stride", i32), ("pad_lo", i32), ("stem", i32), ("fmt", i32)]
 
 
 class AdamDesc(C.Structure):
@@ -79,11 +80,11 @@ _PROTOS = {
     "serl_conv2d_nhwc_f32": [vp, C.c_int, vp, vp] + [C.c_int] * 10 + [vp],
     "serl_groupnorm_nhwc_f32": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, f32, C.c_int, vp],
     "serl_maxpool3x3s2_nhwc_f32": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
-    "serl_trunk_stem_prep_bf16": [vp, vp, C.c_int, C.c_int, C.c_int, vp],
-    "serl_conv2d_tc_bf16": [C.POINTER(ConvTcDesc), vp],
+    "serl_trunk_stem_prep_h16": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "serl_conv2d_tc_h16": [C.POINTER(ConvTcDesc), vp],
     "serl_gn_finalize": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp],
-    "serl_maxpool_affine_bf16": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
-    "serl_block_combine_bf16": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, vp],
+    "serl_maxpool_affine_h16": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "serl_block_combine_h16": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_gemm_f32": [C.POINTER(GemmDesc), vp],
     "serl_sle_fwd": [vp, vp, vp, f32, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_sle_bwd_kernel_grad": [vp, vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],

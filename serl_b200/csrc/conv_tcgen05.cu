@@ -15,6 +15,7 @@
 // 12 channels (zero-extended 8x8 kernel), which gives K = 4 kernel rows x (4 taps x 12 ch = 48, padded to 64).
 // bf16 operands, fp32 accumulation: the 1e-2 tolerance build (north_star); the fp32 build is trunk_fp32.cu.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 #include "serl_b200.h"
@@ -27,9 +28,9 @@ constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;          // 16 KiB
 constexpr int TC_THREADS = 160;
 
 struct ConvTcArgs {
-  const __nv_bfloat16* x;
-  const __nv_bfloat16* w;        // [Co][num_kb * 64], K-major
-  __nv_bfloat16* y;              // (M, Co) raw convolution output (pre-GroupNorm)
+  const uint16_t* x;             // 16-bit elements (bf16 or fp16, see the F template parameter)
+  const uint16_t* w;             // [Co][num_kb * 64], K-major
+  uint16_t* y;              // (M, Co) raw convolution output (pre-GroupNorm)
   float* stats;                  // (N, groups, 2): sum, sum of squares of the fp32 accumulators
   const float* in_a;             // optional (N, Ci): operand transform relu(a * x + b)
   const float* in_b;
@@ -82,19 +83,27 @@ __device__ inline void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ inline uint32_t pack_bf16x2(float lo, float hi) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
-__device__ inline float2 unpack_bf16x2(uint32_t u) {
-  return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
-}
-__device__ inline uint32_t affine_relu_bf16x2(uint32_t u, float a0, float b0, float a1, float b1) {
-  float2 f = unpack_bf16x2(u);
-  return pack_bf16x2(fmaxf(fmaf(f.x, a0, b0), 0.f), fmaxf(fmaf(f.y, a1, b1), 0.f));
+// 16-bit operand formats of kind::f16 MMAs: bf16 (8-bit mantissa) or fp16 (11-bit mantissa, same tensor throughput).
+struct Bf16 {
+  static constexpr uint32_t kUmmaFormat = 1;
+  __device__ static inline uint32_t pack(float lo, float hi) { __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&v); }
+  __device__ static inline float2 unpack(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
+};
+struct Fp16 {
+  static constexpr uint32_t kUmmaFormat = 0;
+  __device__ static inline uint32_t pack(float lo, float hi) {            // saturating: fp16 max is 65504
+    __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+  __device__ static inline float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+};
+template <class F>
+__device__ inline uint32_t affine_relu_x2(uint32_t u, float a0, float b0, float a1, float b1) {
+  float2 f = F::unpack(u);
+  return F::pack(fmaxf(fmaf(f.x, a0, b0), 0.f), fmaxf(fmaf(f.y, a1, b1), 0.f));
 }
 
-template <int BN, int STAGES, bool kStem, bool kAffine>
+template <class F, int BN, int STAGES, bool kStem, bool kAffine>
 __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -153,7 +162,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a)
           if (kStem) {
             // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 12 ch = 48 contiguous bf16 (96 B)
             if (chunk < 6) {
-              const __nv_bfloat16* src = a.x + (((size_t)rn[i] * a.Hi + (rh[i] + kb)) * a.Wi + rw[i]) * 12 + chunk * 8;
+              const uint16_t* src = a.x + (((size_t)rn[i] * a.Hi + (rh[i] + kb)) * a.Wi + rw[i]) * 12 + chunk * 8;
               const uint2 lo = *reinterpret_cast<const uint2*>(src), hi = *reinterpret_cast<const uint2*>(src + 4);
               v = make_uint4(lo.x, lo.y, hi.x, hi.y);
             }
@@ -167,10 +176,10 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a)
                 const float4 a1 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c + 4);
                 const float4 b0 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c);
                 const float4 b1 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c + 4);
-                v.x = affine_relu_bf16x2(v.x, a0.x, b0.x, a0.y, b0.y);
-                v.y = affine_relu_bf16x2(v.y, a0.z, b0.z, a0.w, b0.w);
-                v.z = affine_relu_bf16x2(v.z, a1.x, b1.x, a1.y, b1.y);
-                v.w = affine_relu_bf16x2(v.w, a1.z, b1.z, a1.w, b1.w);
+                v.x = affine_relu_x2<F>(v.x, a0.x, b0.x, a0.y, b0.y);
+                v.y = affine_relu_x2<F>(v.y, a0.z, b0.z, a0.w, b0.w);
+                v.z = affine_relu_x2<F>(v.z, a1.x, b1.x, a1.y, b1.y);
+                v.w = affine_relu_x2<F>(v.w, a1.z, b1.z, a1.w, b1.w);
               }
             }
           }
@@ -205,7 +214,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a)
       for (int j = 0; j < 8; ++j) {
         const float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
         s += f0 + f1; ss += f0 * f0 + f1 * f1;
-        pk[j] = pack_bf16x2(f0, f1);
+        pk[j] = F::pack(f0, f1);
       }
       if (!valid || !ok) { s = 0.f; ss = 0.f; }
       for (int o = seg >> 1; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
@@ -223,7 +232,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a)
   } else {
     // ------------------------------- MMA issuer ------------------------------
     // instruction descriptor: D=F32 (bit 4), A=B=BF16 (bits 7, 10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     bool ok = true;
     for (int kb = 0; kb < a.num_kb && ok; ++kb) {
       const int s = kb % STAGES;
@@ -251,7 +260,8 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a)
 }
 
 // ---- stem input: uint8 crops -> normalised bf16, 2x2 space-to-depth, zero padded: (N,67,67,12) ------------
-__global__ void stem_prep_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* __restrict__ xs, int N, int H, int W, int Hs, int Ws) {
+template <class F>
+__global__ void stem_prep_kernel(const uint8_t* __restrict__ x, uint16_t* __restrict__ xs, int N, int H, int W, int Hs, int Ws) {
   const size_t total = (size_t)N * Hs * Ws;
   const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -272,7 +282,7 @@ __global__ void stem_prep_kernel(const uint8_t* __restrict__ x, __nv_bfloat16* _
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int ei = base + c;
-        const uint32_t h = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(f[c]));
+        const uint32_t h = F::pack(f[c], 0.f) & 0xFFFFu;
         if (ei & 1) out[ei >> 1] |= h << 16; else out[ei >> 1] = h;
       }
     }
@@ -295,8 +305,9 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, const float*
 }
 
 // ---- max_pool 3x3/2 SAME over relu(a*x+b), bf16 in/out; thread per 8 channels ------------------------------
-__global__ void maxpool_affine_bf16_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ ga, const float* __restrict__ gb,
-                                           __nv_bfloat16* __restrict__ y, int N, int Hi, int Wi, int C, int Ho, int Wo) {
+template <class F>
+__global__ void maxpool_affine_kernel(const uint16_t* __restrict__ x, const float* __restrict__ ga, const float* __restrict__ gb,
+                                     uint16_t* __restrict__ y, int N, int Hi, int Wi, int C, int Ho, int Wo) {
   const int c8n = C >> 3;
   const size_t total = (size_t)N * Ho * Wo * c8n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -313,21 +324,22 @@ __global__ void maxpool_affine_bf16_kernel(const __nv_bfloat16* __restrict__ x, 
         const uint32_t u[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float2 f = unpack_bf16x2(u[j]);
+          const float2 f = F::unpack(u[j]);
           m[2 * j] = fmaxf(m[2 * j], fmaf(f.x, av[2 * j], bv[2 * j]));
           m[2 * j + 1] = fmaxf(m[2 * j + 1], fmaf(f.y, av[2 * j + 1], bv[2 * j + 1]));
         }
       }
     }
     *reinterpret_cast<uint4*>(y + (((size_t)n * Ho + ho) * Wo + wo) * C + c8 * 8) =
-        make_uint4(pack_bf16x2(m[0], m[1]), pack_bf16x2(m[2], m[3]), pack_bf16x2(m[4], m[5]), pack_bf16x2(m[6], m[7]));
+        make_uint4(F::pack(m[0], m[1]), F::pack(m[2], m[3]), F::pack(m[4], m[5]), F::pack(m[6], m[7]));
   }
 }
 
 // ---- block output: relu( (a2*y2 + b2) + residual ), residual = res (identity) or ar*res + br (projection) ----
-__global__ void block_combine_bf16_kernel(const __nv_bfloat16* __restrict__ y2, const float* __restrict__ a2, const float* __restrict__ b2,
-                                          const __nv_bfloat16* __restrict__ res, const float* __restrict__ ar, const float* __restrict__ br,
-                                          __nv_bfloat16* __restrict__ out_bf16, float* __restrict__ out_f32, int N, int HW, int C) {
+template <class F>
+__global__ void block_combine_kernel(const uint16_t* __restrict__ y2, const float* __restrict__ a2, const float* __restrict__ b2,
+                                     const uint16_t* __restrict__ res, const float* __restrict__ ar, const float* __restrict__ br,
+                                     uint16_t* __restrict__ out_bf16, float* __restrict__ out_f32, int N, int HW, int C) {
   const int c8n = C >> 3;
   const size_t total = (size_t)N * HW * c8n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -338,7 +350,7 @@ __global__ void block_combine_bf16_kernel(const __nv_bfloat16* __restrict__ y2, 
     float o[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float2 fy = unpack_bf16x2(yu[j]), fr = unpack_bf16x2(ru[j]);
+      const float2 fy = F::unpack(yu[j]), fr = F::unpack(ru[j]);
       float r0 = fr.x, r1 = fr.y;
       if (ar) { r0 = fmaf(r0, ar[co + 2 * j], br[co + 2 * j]); r1 = fmaf(r1, ar[co + 2 * j + 1], br[co + 2 * j + 1]); }
       o[2 * j] = fmaxf(fmaf(fy.x, a2[co + 2 * j], b2[co + 2 * j]) + r0, 0.f);
@@ -349,15 +361,15 @@ __global__ void block_combine_bf16_kernel(const __nv_bfloat16* __restrict__ y2, 
       *reinterpret_cast<float4*>(out_f32 + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
     } else {
       *reinterpret_cast<uint4*>(out_bf16 + off) =
-          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+          make_uint4(F::pack(o[0], o[1]), F::pack(o[2], o[3]), F::pack(o[4], o[5]), F::pack(o[6], o[7]));
     }
   }
 }
 
-template <int BN, int STAGES, bool kStem, bool kAffine>
+template <class F, int BN, int STAGES, bool kStem, bool kAffine>
 static int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
   constexpr size_t smem = (size_t)STAGES * (TC_A_STAGE + BN * TC_BK * 2) + 1024 + 128;
-  auto kern = conv_tc_kernel<BN, STAGES, kStem, kAffine>;
+  auto kern = conv_tc_kernel<F, BN, STAGES, kStem, kAffine>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv_tc)");
@@ -373,35 +385,41 @@ static int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
 using namespace serl;
 #define ST(s) static_cast<cudaStream_t>(s)
 
-extern "C" int serl_trunk_stem_prep_bf16(const uint8_t* x, void* xs, int N, int H, int W, void* stream) {
+template <class F>
+static int conv_tc_dispatch(const serl_conv_tc_desc* d, ConvTcArgs& a, cudaStream_t st) {
+  if (d->stem) {
+    a.num_kb = 4; a.cblocks = 1;
+    return launch_conv_tc<F, 64, 4, true, false>(a, st);
+  }
+  a.cblocks = d->Ci / 64; a.num_kb = d->kh * d->kw * a.cblocks;
+  const bool aff = d->in_a != nullptr;
+  if (d->Co == 64) return aff ? launch_conv_tc<F, 64, 4, false, true>(a, st) : launch_conv_tc<F, 64, 4, false, false>(a, st);
+  return aff ? launch_conv_tc<F, 128, 3, false, true>(a, st) : launch_conv_tc<F, 128, 3, false, false>(a, st);
+}
+
+extern "C" int serl_trunk_stem_prep_h16(const uint8_t* x, void* xs, int N, int H, int W, int fmt, void* stream) {
   const int Hs = H / 2 + 3, Ws = W / 2 + 3;
   size_t total = (size_t)N * Hs * Ws;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  stem_prep_kernel<<<blocks, 256, 0, ST(stream)>>>(x, static_cast<__nv_bfloat16*>(xs), N, H, W, Hs, Ws);
+  if (fmt == SERL_FMT_FP16) stem_prep_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(x, static_cast<uint16_t*>(xs), N, H, W, Hs, Ws);
+  else stem_prep_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(x, static_cast<uint16_t*>(xs), N, H, W, Hs, Ws);
   return check_launch("stem_prep_kernel");
 }
 
-extern "C" int serl_conv2d_tc_bf16(const serl_conv_tc_desc* d, void* stream) {
-  if (!d || !d->x || !d->w || !d->y || !d->stats || !d->error) { set_last_error("serl_conv2d_tc_bf16: invalid descriptor"); return SERL_ERR_INVALID; }
+extern "C" int serl_conv2d_tc_h16(const serl_conv_tc_desc* d, void* stream) {
+  if (!d || !d->x || !d->w || !d->y || !d->stats || !d->error) { set_last_error("serl_conv2d_tc_h16: invalid descriptor"); return SERL_ERR_INVALID; }
   ConvTcArgs a{};
-  a.x = static_cast<const __nv_bfloat16*>(d->x); a.w = static_cast<const __nv_bfloat16*>(d->w); a.y = static_cast<__nv_bfloat16*>(d->y);
+  a.x = static_cast<const uint16_t*>(d->x); a.w = static_cast<const uint16_t*>(d->w); a.y = static_cast<uint16_t*>(d->y);
   a.stats = d->stats; a.in_a = d->in_a; a.in_b = d->in_b; a.error = d->error;
   a.N = d->N; a.Hi = d->Hi; a.Wi = d->Wi; a.Ci = d->Ci; a.Co = d->Co; a.kh = d->kh; a.kw = d->kw; a.stride = d->stride; a.pad = d->pad_lo;
   a.Ho = d->Ho; a.Wo = d->Wo; a.M = d->N * d->Ho * d->Wo; a.Cg = d->Co / 4;
   const int HoWo = d->Ho * d->Wo;
   if (d->Co % 64 != 0 || (HoWo & (HoWo - 1)) != 0 || HoWo < 16) {
-    set_last_error("serl_conv2d_tc_bf16: unsupported shape (Co=%d Ho*Wo=%d)", d->Co, HoWo); return SERL_ERR_UNSUPPORTED;
+    set_last_error("serl_conv2d_tc_h16: unsupported shape (Co=%d Ho*Wo=%d)", d->Co, HoWo); return SERL_ERR_UNSUPPORTED;
   }
-  if (d->stem) {
-    a.num_kb = 4; a.cblocks = 1;
-    if (d->Co != 64) { set_last_error("serl_conv2d_tc_bf16: stem expects Co=64"); return SERL_ERR_UNSUPPORTED; }
-    return launch_conv_tc<64, 4, true, false>(a, ST(stream));
-  }
-  if (d->Ci % 64 != 0) { set_last_error("serl_conv2d_tc_bf16: Ci %% 64 != 0"); return SERL_ERR_UNSUPPORTED; }
-  a.cblocks = d->Ci / 64; a.num_kb = d->kh * d->kw * a.cblocks;
-  const bool aff = d->in_a != nullptr;
-  if (d->Co == 64) return aff ? launch_conv_tc<64, 4, false, true>(a, ST(stream)) : launch_conv_tc<64, 4, false, false>(a, ST(stream));
-  return aff ? launch_conv_tc<128, 3, false, true>(a, ST(stream)) : launch_conv_tc<128, 3, false, false>(a, ST(stream));
+  if (d->stem && d->Co != 64) { set_last_error("serl_conv2d_tc_h16: stem expects Co=64"); return SERL_ERR_UNSUPPORTED; }
+  if (!d->stem && d->Ci % 64 != 0) { set_last_error("serl_conv2d_tc_h16: Ci %% 64 != 0"); return SERL_ERR_UNSUPPORTED; }
+  return d->fmt == SERL_FMT_FP16 ? conv_tc_dispatch<Fp16>(d, a, ST(stream)) : conv_tc_dispatch<Bf16>(d, a, ST(stream));
 }
 
 extern "C" int serl_gn_finalize(const float* stats, const float* gamma, const float* beta, float* out_a, float* out_b, int N, int C,
@@ -411,19 +429,22 @@ extern "C" int serl_gn_finalize(const float* stats, const float* gamma, const fl
   return check_launch("gn_finalize_kernel");
 }
 
-extern "C" int serl_maxpool_affine_bf16(const void* x, const float* a, const float* b, void* y, int N, int Hi, int Wi, int C, void* stream) {
+extern "C" int serl_maxpool_affine_h16(const void* x, const float* a, const float* b, void* y, int N, int Hi, int Wi, int C, int fmt, void* stream) {
   const int Ho = Hi / 2, Wo = Wi / 2;
   size_t total = (size_t)N * Ho * Wo * (C / 8);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  maxpool_affine_bf16_kernel<<<blocks, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(x), a, b, static_cast<__nv_bfloat16*>(y), N, Hi, Wi, C, Ho, Wo);
-  return check_launch("maxpool_affine_bf16_kernel");
+  auto xi = static_cast<const uint16_t*>(x); auto yo = static_cast<uint16_t*>(y);
+  if (fmt == SERL_FMT_FP16) maxpool_affine_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(xi, a, b, yo, N, Hi, Wi, C, Ho, Wo);
+  else maxpool_affine_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(xi, a, b, yo, N, Hi, Wi, C, Ho, Wo);
+  return check_launch("maxpool_affine_kernel");
 }
 
-extern "C" int serl_block_combine_bf16(const void* y2, const float* a2, const float* b2, const void* res, const float* ar, const float* br,
-                                       void* out_bf16, float* out_f32, int N, int HW, int C, void* stream) {
+extern "C" int serl_block_combine_h16(const void* y2, const float* a2, const float* b2, const void* res, const float* ar, const float* br,
+                                      void* out_h16, float* out_f32, int N, int HW, int C, int fmt, void* stream) {
   size_t total = (size_t)N * HW * (C / 8);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  block_combine_bf16_kernel<<<blocks, 256, 0, ST(stream)>>>(static_cast<const __nv_bfloat16*>(y2), a2, b2, static_cast<const __nv_bfloat16*>(res), ar, br,
-                                                            static_cast<__nv_bfloat16*>(out_bf16), out_f32, N, HW, C);
-  return check_launch("block_combine_bf16_kernel");
+  auto yi = static_cast<const uint16_t*>(y2); auto ri = static_cast<const uint16_t*>(res); auto oo = static_cast<uint16_t*>(out_h16);
+  if (fmt == SERL_FMT_FP16) block_combine_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(yi, a2, b2, ri, ar, br, oo, out_f32, N, HW, C);
+  else block_combine_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(yi, a2, b2, ri, ar, br, oo, out_f32, N, HW, C);
+  return check_launch("block_combine_kernel");
 }

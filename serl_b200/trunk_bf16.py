@@ -20,13 +20,16 @@ def _s():
     return L.stream_ptr()
 
 
-def pack_conv_weight(w: torch.Tensor) -> torch.Tensor:
-    """HWIO fp32 (kh,kw,Ci,Co) -> bf16 [Co][kh*kw*Ci], K-major (K order = (kh, kw, ci), the im2col gather order)."""
+FMT = {"bf16": (L.FMT_BF16, torch.bfloat16), "fp16": (L.FMT_FP16, torch.float16)}
+
+
+def pack_conv_weight(w: torch.Tensor, dt=torch.bfloat16) -> torch.Tensor:
+    """HWIO fp32 (kh,kw,Ci,Co) -> 16-bit [Co][kh*kw*Ci], K-major (K order = (kh, kw, ci), the im2col gather order)."""
     kh, kw, ci, co = w.shape
-    return w.permute(3, 0, 1, 2).reshape(co, kh * kw * ci).to(torch.bfloat16).contiguous()
+    return w.permute(3, 0, 1, 2).reshape(co, kh * kw * ci).to(dt).contiguous()
 
 
-def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
+def pack_stem_weight(w: torch.Tensor, dt=torch.bfloat16) -> torch.Tensor:
     """conv_init (7,7,3,64) -> exact 4x4 space-to-depth kernel, bf16 [64][4 rows x 64] (48 valid K per row).
     ws[r', s', p, q, c, co] = w8[2r'+p, 2s'+q, c, co] with w8 = w zero-extended to 8x8."""
     co = w.shape[-1]
@@ -36,14 +39,15 @@ def pack_stem_weight(w: torch.Tensor) -> torch.Tensor:
     rows = ws.reshape(4, 48, co)                                        # k within a row = s'*12 + (p*2+q)*3 + c
     out = torch.zeros(co, 4, 64, dtype=torch.float32, device=w.device)
     out[:, :, :48] = rows.permute(2, 0, 1)
-    return out.reshape(co, 256).to(torch.bfloat16).contiguous()
+    return out.reshape(co, 256).to(dt).contiguous()
 
 
 class _Plan:
     """Per-(engine, N) bf16 activation buffers."""
 
-    def __init__(self, N, hw, dev):
-        bf = lambda *s: torch.empty(*s, dtype=torch.bfloat16, device=dev)
+    def __init__(self, N, hw, dev, precision="bf16"):
+        self.fmt, self.dt = FMT[precision]
+        bf = lambda *s: torch.empty(*s, dtype=self.dt, device=dev)
         s2 = hw // 2
         self.hs = s2 + 3
         self.xs = bf(N, self.hs, self.hs, 12)
@@ -60,8 +64,8 @@ def _conv(plan, x, w, y, stats, N, Hi, Wi, Ci, Ho, Wo, Co, k, stride, pad_lo, in
     if in_ab is not None:
         d.in_a, d.in_b = in_ab[0].data_ptr(), in_ab[1].data_ptr()
     d.error = plan.error.data_ptr()
-    d.N, d.Hi, d.Wi, d.Ci, d.Ho, d.Wo, d.Co, d.kh, d.kw, d.stride, d.pad_lo, d.stem = N, Hi, Wi, Ci, Ho, Wo, Co, k, k, stride, pad_lo, int(stem)
-    L.call("serl_conv2d_tc_bf16", C.byref(d), _s())
+    d.N, d.Hi, d.Wi, d.Ci, d.Ho, d.Wo, d.Co, d.kh, d.kw, d.stride, d.pad_lo, d.stem, d.fmt = N, Hi, Wi, Ci, Ho, Wo, Co, k, k, stride, pad_lo, int(stem), plan.fmt
+    L.call("serl_conv2d_tc_h16", C.byref(d), _s())
 
 
 def _finalize(stats, gamma, beta, ab, N, Cc, HW):
@@ -73,9 +77,10 @@ def _finalize(stats, gamma, beta, ab, N, Cc, HW):
 def packed_weights(engine, cam):
     cache = engine.__dict__.setdefault("_tc_weights", {})
     w = engine.trunk[cam]
+    dt = FMT[engine.cfg.precision][1]
     ver = tuple(t._version for t in w.values())
     if cam not in cache or cache[cam][0] != ver:
-        packed = {k: (pack_stem_weight(v) if k == "conv_init/kernel" else pack_conv_weight(v)) for k, v in w.items() if k.endswith("kernel")}
+        packed = {k: (pack_stem_weight(v, dt) if k == "conv_init/kernel" else pack_conv_weight(v, dt)) for k, v in w.items() if k.endswith("kernel")}
         cache[cam] = (ver, packed)
     return cache[cam][1]
 
@@ -85,17 +90,17 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
     N, hw = pix.shape[0], pix.shape[1]
     plans = engine.__dict__.setdefault("_tc_plans", {})
     if N not in plans:
-        plans[N] = _Plan(N, hw, pix.device)
+        plans[N] = _Plan(N, hw, pix.device, engine.cfg.precision)
     p = plans[N]
     w, wp = engine.trunk[cam], packed_weights(engine, cam)
     s = hw // 2
-    L.call("serl_trunk_stem_prep_bf16", pix.data_ptr(), p.xs.data_ptr(), N, hw, hw, _s())
+    L.call("serl_trunk_stem_prep_h16", pix.data_ptr(), p.xs.data_ptr(), N, hw, hw, p.fmt, _s())
     p.stats.zero_()
     _conv(p, p.xs, wp["conv_init/kernel"], p.y0, p.stats[0], N, p.hs, p.hs, 12, s, s, 64, 4, 1, 0, stem=True)
     a0, b0 = _finalize(p.stats[0], w["norm_init/scale"], w["norm_init/bias"], p.aff[0], N, 64, s * s)
     s //= 2
     x = p.buf[0][:N * s * s * 64].view(N, s, s, 64)
-    L.call("serl_maxpool_affine_bf16", p.y0.data_ptr(), a0.data_ptr(), b0.data_ptr(), x.data_ptr(), N, 2 * s, 2 * s, 64, _s())
+    L.call("serl_maxpool_affine_h16", p.y0.data_ptr(), a0.data_ptr(), b0.data_ptr(), x.data_ptr(), N, 2 * s, 2 * s, 64, p.fmt, _s())
     engine.launches += 5
     free, cur, cin = [1, 2, 3, 4], 0, 64
     for i, (f, stride) in enumerate(STAGES):
@@ -118,8 +123,8 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
             engine.launches += 2
         else:
             res, ar, br = x, None, None
-        L.call("serl_block_combine_bf16", yB.data_ptr(), abB[0].data_ptr(), abB[1].data_ptr(), res.data_ptr(), ar, br,
-               None if last else out.data_ptr(), feats.data_ptr() if last else None, N, so * so, f, _s())
+        L.call("serl_block_combine_h16", yB.data_ptr(), abB[0].data_ptr(), abB[1].data_ptr(), res.data_ptr(), ar, br,
+               None if last else out.data_ptr(), feats.data_ptr() if last else None, N, so * so, f, p.fmt, _s())
         engine.launches += 6
         free, cur = [cur, iy, iy2, ir], io
         x, s, cin = out, so, f
