@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--cams", type=int, default=1)
     ap.add_argument("--capacity", type=int, default=100_000)
-    ap.add_argument("--ref-rows", type=int, default=32, help="rows of the batch the CPU reference processes per step")
+    ap.add_argument("--ref-rows", type=int, default=16, help="rows of the batch the CPU reference processes per step")
     return ap.parse_args()
 
 
@@ -64,13 +64,13 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle port of the reference step (sample on host + update_critics), bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps(args, steps, warmup, rows):
+def cpu_reference_steps(args, steps, warmup, rows, budget_s=None):
     import torch
     from helpers import random_transitions
     from oracle import drq as O
     from oracle.replay import OracleFrameRing, unpack
     from serl_b200.params import init_trainable, init_trunk, trainable_spec
-    cores = os.cpu_count() or 1
+    cores = min(os.cpu_count() or 1, 32)                  # beyond ~32 threads the small convs of a bounded sample only contend
     torch.set_num_threads(cores)
     cams = tuple(f"cam{i}" for i in range(args.cams))
     rng = np.random.default_rng(0)
@@ -84,7 +84,7 @@ def cpu_reference_steps(args, steps, warmup, rows):
     ring = OracleFrameRing(1200, cams, (128, 128, 3), 1, 7, 4)
     for tr in random_transitions(rng, 1000, cams, mean_ep=100):
         ring.insert(tr)
-    times = []
+    times, t_begin = [], time.perf_counter()
     for s in range(warmup + steps):
         t0 = time.perf_counter()
         _, packed = ring.sample(0, s, rows)
@@ -92,17 +92,19 @@ def cpu_reference_steps(args, steps, warmup, rows):
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
+        if budget_s is not None and times and time.perf_counter() - t_begin > budget_s:
+            break                                          # bounded sample: stop once the time budget is spent
     t = sum(times) / len(times)
     # a full step processes `batch` rows; the sample processed `rows`: scale linearly (trunk-dominated, per-row cost)
-    return (rows / args.batch) / t, t, cores
+    return (rows / args.batch) / t, t, cores, len(times)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    v, t, cores = cpu_reference_steps(args, args.steps, args.warmup, args.ref_rows)
-    sample = (f"{args.ref_rows} of {args.batch} rows per step (host numpy sampling + torch-CPU fp32 restatement of update_critics, "
+    v, t, cores, done = cpu_reference_steps(args, args.steps, min(args.warmup, 1), args.ref_rows, budget_s=150.0)
+    sample = (f"{done} timed steps (150 s budget) of {args.ref_rows} of {args.batch} rows per step (host numpy sampling + torch-CPU fp32 restatement of update_critics, "
               f"trunk shared between policy/critic/target like the B200 path; the JAX reference recomputes it 3x); "
               f"steps/s scaled by rows/batch")
     line = {"metric": "drq_critic_grad_steps_per_sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -218,22 +220,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput -----------------------------------------------------------------
+    # ---- device-resident throughput (whole step replayed as one CUDA graph) -------------------------------------
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    trunk_ev, samp_ev = [], []
-    orig_features, orig_load = agent._features, agent._load_batch
-
-    def timed_features(e):
-        a, b = ev(), ev(); a.record(); orig_features(e); b.record(); trunk_ev.append((a, b))
-
-    def timed_load(e, batch, **kw):
-        a, b = ev(), ev(); a.record(); orig_load(e, batch, **kw); b.record(); samp_ev.append((a, b))
-
     clocks = ClockSampler(local)
     clocks.start()
-    for _ in range(args.warmup):
+    for _ in range(max(args.warmup, 3)):
         agent.update_critics(next(it))
-    agent._features, agent._load_batch = timed_features, timed_load
     launches0 = agent.kernel_launches
     barrier()
     w0 = time.time()
@@ -244,12 +236,29 @@ def run_b200(args):
     t1.record()
     barrier()
     clk = clocks.stop(w0, time.time())
-    agent._features, agent._load_batch = orig_features, orig_load
     ms = t0.elapsed_time(t1)
     launches = agent.kernel_launches - launches0
+    agent.check_status()
+
+    # ---- per-kernel-group durations: the same steps launched eagerly with CUDA events around the sections -----------
+    trunk_ev, samp_ev = [], []
+    orig_features, orig_load = agent._features, agent._load_batch
+
+    def timed_features(e):
+        a, b = ev(), ev(); a.record(); orig_features(e); b.record(); trunk_ev.append((a, b))
+
+    def timed_load(e, batch, **kw):
+        a, b = ev(), ev(); a.record(); orig_load(e, batch, **kw); b.record(); samp_ev.append((a, b))
+
+    agent.use_cuda_graphs = False
+    agent._features, agent._load_batch = timed_features, timed_load
+    for _ in range(min(args.steps, 20)):
+        agent.update_critics(next(it))
+    barrier()
+    agent._features, agent._load_batch = orig_features, orig_load
+    agent.use_cuda_graphs = True
     trunk_ms = sum(a.elapsed_time(b) for a, b in trunk_ev) / len(trunk_ev)
     samp_ms = sum(a.elapsed_time(b) for a, b in samp_ev) / len(samp_ev)
-    agent.check_status()
 
     # ---- end to end through the public API with host buffers --------------------------------------------
     pinned = []
@@ -290,17 +299,21 @@ def run_b200(args):
             "config": workload_config(args),
             "clocks": clk,
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h / args.steps},
-            "gpu_launches": launches,
+            "gpu_launches": launches, "cuda_graph": True,
             "roofline": {"kernel": "frozen ResNet-10 trunk (conv_igemm + groupnorm + maxpool kernels)", "bound": "tensor",
                          "achieved": trunk_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": trunk_tflops / pk["tensor"],
                          "traffic": None, "peak_source": pk["src"], "ms_per_step": trunk_ms,
+                         "timing": "CUDA events around the trunk section of eagerly launched steps (the headline loop replays a CUDA graph)",
                          "algorithmic": f"{images} images x {TRUNK_GFLOP_PER_IMAGE} GFLOP"},
             "sampler": {"kernel": "sample_gather_crop_kernel", "bound": "hbm", "achieved": samp_gbs, "peak": pk["hbm"], "unit": "GB/s",
                         "frac": samp_gbs / pk["hbm"], "ms_per_step": samp_ms, "algorithmic_bytes": samp_bytes}}
     try:
-        v, t, cores = cpu_reference_steps(args, 3, 1, args.ref_rows)
+        if os.environ.get("SERL_BENCH_SKIP_CPU"):
+            raise RuntimeError("skipped (SERL_BENCH_SKIP_CPU)")
+        v, t, cores, done = cpu_reference_steps(args, 4, 1, 8, budget_s=20.0)
         line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                                "sample": f"3 steps of {args.ref_rows}/{args.batch} rows (oracle torch-CPU fp32 restatement; jax not installable), scaled by rows/batch"}
+                                "sample": f"{done} timed steps of 8/{args.batch} rows, ~20 s budget (oracle torch-CPU fp32 restatement of sample + update_critics; "
+                                          "jax not installable), steps/s scaled by rows/batch"}
     except Exception as e:                      # noqa: BLE001
         line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)

@@ -56,11 +56,17 @@ class DrQAgent(SACAgent):
         """drq.py:296-328: unpack + augment + update{critic}."""
         B = batch.batch_size if isinstance(batch, BatchHandle) else int(np.asarray(_leaf(batch, "rewards")).shape[0])
         eng = self._engine(B)
-        ops.rng_schedule(self.state._rng, self._keys, True, True)        # split(rng,3) then update's split(rng,4)
-        eng.launches += 1
-        self._load_batch(eng, batch, augment=True, keys=self._keys)
-        self._features(eng)
-        info = self._update_on_engine(eng, frozenset({"critic"}), pmap_axis, schedule_keys=False)
+        nets = frozenset({"critic"})
+
+        def body(batch, graph_mode):
+            ops.rng_schedule(self.state._rng, self._keys, True, True)    # split(rng,3) then update's split(rng,4)
+            eng.launches += 1
+            self._load_batch(eng, batch, augment=True, keys=self._keys, graph_mode=graph_mode)
+            self._features(eng)
+            self._update_on_engine(eng, nets, pmap_axis, schedule_keys=False, want_info=False)
+
+        self._run_step(self._graph_key(("update_critics", pmap_axis), batch), batch, body)
+        info = self._info(eng, nets)
         del info["actor"], info["temperature"]
         return self, info
 

@@ -47,6 +47,8 @@ class SACAgent:
         self._seed_key = torch.zeros(2, dtype=torch.uint32, device=device)
         self.data_parallel = False          # set True to all-reduce(mean) gradients + infos (reference: pmap_axis)
         self.explicit_randomness = None     # tests: dict with eps / dropout / subsample (and crop offsets)
+        self.use_cuda_graphs = True         # replay the whole step as one CUDA graph from its 3rd identical call on
+        self._graphs = {}
 
     # ---- construction (sac.py:322-400,486-542) ------------------------------------------------------
     @classmethod
@@ -111,8 +113,48 @@ class SACAgent:
     def kernel_launches(self) -> int:
         return sum(e.launches for e in self._engines.values())
 
+    # ---- CUDA graphs: the ~150 launches of a step are captured once and replayed -------------------------
+    def _graph_key(self, tag, batch):
+        """Batches that can be replayed: lazy handles whose index draw reads the ring's device-resident counters."""
+        if not self.use_cuda_graphs or self.explicit_randomness is not None or not isinstance(batch, BatchHandle):
+            return None
+        if any(p.get("indx") is not None for p in batch.parts):
+            return None
+        return (tag, batch.batch_size, tuple((id(p["ring"]), p["batch"]) for p in batch.parts))
+
+    def _run_step(self, key, batch, body):
+        """body(batch, graph_mode) enqueues one step.  1st call with a key: eager (warm-up: lazy allocations, function
+        attributes); 2nd: capture + replay; later: replay only."""
+        if key is None:
+            return body(batch, False)
+        entry = self._graphs.get(key)
+        if entry is None:
+            self._graphs[key] = "warm"
+            return body(batch, False)
+        for p in batch.parts:                                    # device draw counter := this handle's step
+            ring = p["ring"]
+            if ring._dev_step_mirror != p["step"]:
+                ring.step_dev.fill_(p["step"])
+            ring._dev_step_mirror = p["step"] + 1
+        if entry == "warm":
+            g = torch.cuda.CUDAGraph()
+            l0, s0 = {b: e.launches for b, e in self._engines.items()}, self.state.step
+            with torch.cuda.graph(g):
+                body(batch, True)
+            entry = (g, {b: e.launches - l0.get(b, 0) for b, e in self._engines.items()}, self.state.step - s0)
+            self._graphs[key] = entry
+            self.state.step = s0
+            for b, e in self._engines.items():
+                e.launches = l0.get(b, e.launches)
+        g, launches, steps = entry
+        g.replay()
+        for b, n in launches.items():
+            self._engines[b].launches += n
+        self.state.step += steps
+        return None
+
     # ---- batch ingestion -------------------------------------------------------------------------------
-    def _load_batch(self, eng: Engine, batch, *, augment: bool, keys) -> None:
+    def _load_batch(self, eng: Engine, batch, *, augment: bool, keys, graph_mode: bool = False) -> None:
         """Fills the engine's batch buffers.  Pixel agents: obs crops to pix rows [0,B), next crops to [B,2B)."""
         cfg, B = self._cfg, eng.B
         if not isinstance(batch, BatchHandle):
@@ -142,8 +184,12 @@ class SACAgent:
             if cfg.pixel and ring.T != 1:
                 raise NotImplementedError("the trunk kernels take one frame per observation (obs_horizon=1), like every SERL example")
             ring.launch_sample(part, out, crop_total=B, out_row_offset=row, key_obs=ops.key_ptr(keys, L.KEY_CROP_OBS),
-                               key_next=ops.key_ptr(keys, L.KEY_CROP_NEXT), explicit_off=expl)
+                               key_next=ops.key_ptr(keys, L.KEY_CROP_NEXT), explicit_off=expl,
+                               step_dev=ring.step_dev if graph_mode else None, record_event=not graph_mode)
             eng.launches += 1
+            if graph_mode:
+                ops.counter_add(ring.step_dev, 1)
+                eng.launches += 1
             row += part["batch"]
 
     def _handle_from_dict(self, batch: dict) -> BatchHandle:
@@ -196,7 +242,7 @@ class SACAgent:
         dist.all_reduce(g, op=dist.ReduceOp.AVG)                 # jax.lax.pmean(grads_and_aux) (common.py:213-214)
         dist.all_reduce(eng.info[:12], op=dist.ReduceOp.AVG)
 
-    def _update_on_engine(self, eng: Engine, nets: FrozenSet[str], pmap_axis=None, schedule_keys: bool = True):
+    def _update_on_engine(self, eng: Engine, nets: FrozenSet[str], pmap_axis=None, schedule_keys: bool = True, want_info: bool = True):
         assert nets.issubset(ALL_NETS), f"Invalid gradient steps: {nets}"
         if schedule_keys:
             ops.rng_schedule(self.state._rng, self._keys, False, True)
@@ -216,7 +262,7 @@ class SACAgent:
                 self._allreduce(eng, st.seg_end[0], st.seg_end[2])
         eng.optimizer_step([int("critic" in nets), int("actor" in nets), int("temperature" in nets)], polyak="critic" in nets)
         self.state.step += 1
-        return self._info(eng, nets)
+        return self._info(eng, nets) if want_info else None
 
     def _info(self, eng: Engine, nets) -> dict:
         snap = eng.info.clone()
@@ -235,13 +281,16 @@ class SACAgent:
         nets = frozenset(networks_to_update)
         B = batch.batch_size if isinstance(batch, BatchHandle) else int(np.asarray(_leaf(batch, "rewards")).shape[0])
         eng = self._engine(B)
-        ops.rng_schedule(self.state._rng, self._keys, False, True)
-        eng.launches += 1
-        self._load_batch(eng, batch, augment=False, keys=self._keys)
-        self._features(eng)
-        info = self._update_on_engine(eng, nets, pmap_axis, schedule_keys=False)
-        self._check(eng)
-        return self, info
+
+        def body(batch, graph_mode):
+            ops.rng_schedule(self.state._rng, self._keys, False, True)
+            eng.launches += 1
+            self._load_batch(eng, batch, augment=False, keys=self._keys, graph_mode=graph_mode)
+            self._features(eng)
+            self._update_on_engine(eng, nets, pmap_axis, schedule_keys=False, want_info=False)
+
+        self._run_step(self._graph_key(("update", tuple(sorted(nets)), pmap_axis), batch), batch, body)
+        return self, self._info(eng, nets)
 
     def _check(self, eng: Engine):
         pass   # draw failures are surfaced lazily by check_status() to avoid a sync per step
@@ -257,15 +306,34 @@ class SACAgent:
         B = batch.batch_size if isinstance(batch, BatchHandle) else int(np.asarray(_leaf(batch, "rewards")).shape[0])
         assert B % utd_ratio == 0, f"Batch size {B} must be divisible by UTD ratio {utd_ratio}"
         full = self._engine(B)
+        mb = B // utd_ratio
+        if utd_ratio == 1:                                         # the DrQ learner's case: one graph for the whole call
+            def body(batch, graph_mode):
+                if _augment:
+                    ops.rng_schedule(self.state._rng, self._keys, True, False)      # drq.py:279
+                    full.launches += 1
+                self._load_batch(full, batch, augment=_augment, keys=self._keys, graph_mode=graph_mode)
+                self._features(full)
+                self._update_on_engine(full, frozenset({"critic"}), pmap_axis, want_info=False)
+                full.info_hist.copy_(full.info)                                      # critic infos of the scan step
+                self._update_on_engine(full, frozenset({"actor", "temperature"}), pmap_axis, want_info=False)
+
+            self._run_step(self._graph_key(("high_utd", _augment, pmap_axis), batch), batch, body)
+            at = self._info(full, frozenset({"actor", "temperature"}))
+            snap = full.info_hist.clone()
+            info = {"critic": {"critic_loss": snap[0], "predicted_qs": snap[1], "target_qs": snap[2]},
+                    "actor": at["actor"], "temperature": at["temperature"]}
+            for k in ("critic_lr", "actor_lr", "temperature_lr"):
+                info[k] = at[k]
+            return self, info
         if _augment:
             ops.rng_schedule(self.state._rng, self._keys, True, False)          # drq.py:279
             full.launches += 1
         self._load_batch(full, batch, augment=_augment, keys=self._keys)
         self._features(full)
-        mb = B // utd_ratio
         crit_infos = []
         for i in range(utd_ratio):
-            eng = full if utd_ratio == 1 else self._minibatch_engine(full, i, mb)
+            eng = self._minibatch_engine(full, i, mb)
             crit_infos.append(self._update_on_engine(eng, frozenset({"critic"}), pmap_axis))
         at = self._update_on_engine(full, frozenset({"actor", "temperature"}), pmap_axis)
         crit = {k: torch.stack([c["critic"][k] for c in crit_infos]).mean() for k in crit_infos[0]["critic"]}

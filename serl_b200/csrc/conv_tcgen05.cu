@@ -147,52 +147,72 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a)
       } else { rn[i] = -1; rh[i] = 0; rw[i] = 0; }
     }
     bool ok = true;
+    const size_t Kp = (size_t)a.num_kb * TC_BK;
     for (int kb = 0; kb < a.num_kb && ok; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-      ok = tc_mbar_wait(&empty[s], ph ^ 1u, a.error);
-      uint8_t* As = sA + s * TC_A_STAGE;
       int r = 0, sx = 0, c0 = 0;
       if (!kStem) { const int tap = kb / a.cblocks; c0 = (kb - tap * a.cblocks) * TC_BK; r = tap / a.kw; sx = tap - r * a.kw; }
+      // ---- phase 1: issue EVERY global load of this k-block before anything consumes one (memory-level parallelism:
+      //      the gather is latency-bound, so all 8 A rows + the B rows of a thread must be in flight together)
+      uint4 va[8], vb[BN / 16];
+      bool inb[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int row = rsub + 16 * i;
-        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        va[i] = make_uint4(0u, 0u, 0u, 0u);
+        inb[i] = false;
         if (rn[i] >= 0) {
           if (kStem) {
-            // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 12 ch = 48 contiguous bf16 (96 B)
+            // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 12 ch = 48 contiguous 16-bit values (96 B)
             if (chunk < 6) {
               const uint16_t* src = a.x + (((size_t)rn[i] * a.Hi + (rh[i] + kb)) * a.Wi + rw[i]) * 12 + chunk * 8;
               const uint2 lo = *reinterpret_cast<const uint2*>(src), hi = *reinterpret_cast<const uint2*>(src + 4);
-              v = make_uint4(lo.x, lo.y, hi.x, hi.y);
+              va[i] = make_uint4(lo.x, lo.y, hi.x, hi.y);
             }
           } else {
             const int hi_ = rh[i] + r, wi_ = rw[i] + sx;
             if (hi_ >= 0 && hi_ < a.Hi && wi_ >= 0 && wi_ < a.Wi) {
-              const int c = c0 + chunk * 8;
-              v = *reinterpret_cast<const uint4*>(a.x + (((size_t)rn[i] * a.Hi + hi_) * a.Wi + wi_) * a.Ci + c);
-              if (kAffine) {
-                const float4 a0 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c);
-                const float4 a1 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c + 4);
-                const float4 b0 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c);
-                const float4 b1 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c + 4);
-                v.x = affine_relu_x2<F>(v.x, a0.x, b0.x, a0.y, b0.y);
-                v.y = affine_relu_x2<F>(v.y, a0.z, b0.z, a0.w, b0.w);
-                v.z = affine_relu_x2<F>(v.z, a1.x, b1.x, a1.y, b1.y);
-                v.w = affine_relu_x2<F>(v.w, a1.z, b1.z, a1.w, b1.w);
-              }
+              inb[i] = true;
+              va[i] = *reinterpret_cast<const uint4*>(a.x + (((size_t)rn[i] * a.Hi + hi_) * a.Wi + wi_) * a.Ci + c0 + chunk * 8);
             }
           }
         }
-        *reinterpret_cast<uint4*>(As + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4)) = v;
       }
-      uint8_t* Bs = sB + s * B_STAGE;
-      const size_t Kp = (size_t)a.num_kb * TC_BK;
 #pragma unroll
       for (int j = 0; j < BN / 16; ++j) {
         const int idx = tid + 128 * j, brow = idx >> 3, bch = idx & 7;
-        const uint4 v = *reinterpret_cast<const uint4*>(a.w + (size_t)(n0 + brow) * Kp + (size_t)kb * TC_BK + bch * 8);
-        *reinterpret_cast<uint4*>(Bs + (brow >> 3) * 1024 + (brow & 7) * 128 + ((bch ^ (brow & 7)) << 4)) = v;
+        vb[j] = *reinterpret_cast<const uint4*>(a.w + (size_t)(n0 + brow) * Kp + (size_t)kb * TC_BK + bch * 8);
+      }
+      // ---- phase 2: previous GroupNorm + ReLU on the operand (zero padding stays zero) ----
+      if (kAffine) {
+        const int c = c0 + chunk * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (inb[i]) {
+            const float4 a0 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c);
+            const float4 a1 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c);
+            const float4 b1 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c + 4);
+            va[i].x = affine_relu_x2<F>(va[i].x, a0.x, b0.x, a0.y, b0.y);
+            va[i].y = affine_relu_x2<F>(va[i].y, a0.z, b0.z, a0.w, b0.w);
+            va[i].z = affine_relu_x2<F>(va[i].z, a1.x, b1.x, a1.y, b1.y);
+            va[i].w = affine_relu_x2<F>(va[i].w, a1.z, b1.z, a1.w, b1.w);
+          }
+        }
+      }
+      // ---- phase 3: the stage must be free only now ----
+      ok = tc_mbar_wait(&empty[s], ph ^ 1u, a.error);
+      uint8_t* As = sA + s * TC_A_STAGE;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int row = rsub + 16 * i;
+        *reinterpret_cast<uint4*>(As + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4)) = va[i];
+      }
+      uint8_t* Bs = sB + s * B_STAGE;
+#pragma unroll
+      for (int j = 0; j < BN / 16; ++j) {
+        const int idx = tid + 128 * j, brow = idx >> 3, bch = idx & 7;
+        *reinterpret_cast<uint4*>(Bs + (brow >> 3) * 1024 + (brow & 7) * 128 + ((bch ^ (brow & 7)) << 4)) = vb[j];
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
       __syncwarp();

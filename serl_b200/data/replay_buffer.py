@@ -91,6 +91,7 @@ class DeviceRing:
         self._insert_index = 0
         self._seed = int(seed) if seed is not None else int(np.random.SeedSequence().entropy % (1 << 63))
         self._draw_step = 0
+        self._dev_step_mirror = 0                                         # host mirror of step_dev (graph replays)
         self._lock = threading.RLock()
         # pinned staging (struct of arrays) + device mirror
         n = self.STAGE
@@ -236,7 +237,7 @@ class DeviceRing:
 
     # ---- kernel launch used by the agents ---------------------------------------------------------
     def launch_sample(self, part: dict, out: L.BatchOut, *, crop_total: int, out_row_offset: int, key_obs=None, key_next=None,
-                      explicit_off=None, padding: int = 4, step_dev=None):
+                      explicit_off=None, padding: int = 4, step_dev=None, record_event: bool = True):
         with self._lock:
             rq = L.SampleRequest()
             rq.seed, rq.step, rq.lane_offset, rq.batch = part["seed"], part["step"], 0, part["batch"]
@@ -249,9 +250,10 @@ class DeviceRing:
             rq.crop_total, rq.out_row_offset, rq.padding = crop_total, out_row_offset, padding
             v = self.view()
             L.call("serl_replay_sample_crop", C.byref(v), C.byref(rq), C.byref(out), L.stream_ptr())
-            evt = L.new_event()
-            evt.record()
-            self._sample_evt = evt
+            if record_event:
+                evt = L.new_event()
+                evt.record()
+                self._sample_evt = evt
 
     def _gather_dict(self, part: dict, pack: bool) -> dict:
         """Un-augmented materialisation in the reference's batch layout (memory_efficient_replay_buffer.py:126-164)."""

@@ -105,6 +105,7 @@ class Engine:
         self.dmu, self.dls = e(B, A), e(B, A)
         self.pdh, self.pdz, self.pdy = e(B, 256), e(B, 256), e(B, 256)
         self.info = torch.zeros(16, dtype=f32, device=device)      # [0:3] critic, [4:7] actor, [8] temp, [12:15] lrs
+        self.info_hist = torch.zeros(16, dtype=f32, device=device)
         self.launches = 0
 
     # ------------------------------------------------------------------------------------------
