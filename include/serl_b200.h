@@ -139,6 +139,8 @@ int serl_conv2d_tc_h16(const serl_conv_tc_desc* d, void* stream);
 /* (N,4,2) sums -> per-(image, channel) affine a = rstd*gamma, b = beta - mean*a (flax GroupNorm statistics) */
 int serl_gn_finalize(const float* stats, const float* gamma, const float* beta, float* out_a, float* out_b, int N, int C,
                      int HW, float eps, void* stream);
+/* in place: x <- relu(a*x + b) (GroupNorm + ReLU of a raw conv output, materialised for the next conv's operand gather) */
+int serl_affine_relu_h16(void* x, const float* a, const float* b, int N, int HW, int C, int fmt, void* stream);
 int serl_maxpool_affine_h16(const void* x, const float* a, const float* b, void* y, int N, int Hi, int Wi, int C, int fmt, void* stream);
 /* relu((a2*y2+b2) + residual), residual = res or ar*res+br; writes 16-bit (next block) or fp32 (final features) */
 int serl_block_combine_h16(const void* y2, const float* a2, const float* b2, const void* res, const float* ar, const float* br,

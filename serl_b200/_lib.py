@@ -83,6 +83,7 @@ _PROTOS = {
     "serl_trunk_stem_prep_h16": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_conv2d_tc_h16": [C.POINTER(ConvTcDesc), vp],
     "serl_gn_finalize": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp],
+    "serl_affine_relu_h16": [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_maxpool_affine_h16": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_block_combine_h16": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_gemm_f32": [C.POINTER(GemmDesc), vp],

@@ -324,6 +324,23 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, const float*
   oa[e] = a; ob[e] = beta[c] - mean * a;
 }
 
+// ---- GroupNorm + ReLU applied in place on the raw 16-bit conv output: x <- relu(a*x + b); thread per 8 channels ----
+template <class F>
+__global__ void affine_relu_kernel(uint16_t* __restrict__ x, const float* __restrict__ ga, const float* __restrict__ gb, int N, int HW, int C) {
+  const int c8n = C >> 3;
+  const size_t total = (size_t)N * HW * c8n;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(e % c8n); const size_t pix = e / c8n; const int n = (int)(pix / HW);
+    const size_t off = pix * C + c8 * 8, co = (size_t)n * C + c8 * 8;
+    uint4 v = *reinterpret_cast<const uint4*>(x + off);
+    const float4 a0 = *reinterpret_cast<const float4*>(ga + co), a1 = *reinterpret_cast<const float4*>(ga + co + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(gb + co), b1 = *reinterpret_cast<const float4*>(gb + co + 4);
+    v.x = affine_relu_x2<F>(v.x, a0.x, b0.x, a0.y, b0.y); v.y = affine_relu_x2<F>(v.y, a0.z, b0.z, a0.w, b0.w);
+    v.z = affine_relu_x2<F>(v.z, a1.x, b1.x, a1.y, b1.y); v.w = affine_relu_x2<F>(v.w, a1.z, b1.z, a1.w, b1.w);
+    *reinterpret_cast<uint4*>(x + off) = v;
+  }
+}
+
 // ---- max_pool 3x3/2 SAME over relu(a*x+b), bf16 in/out; thread per 8 channels ------------------------------
 template <class F>
 __global__ void maxpool_affine_kernel(const uint16_t* __restrict__ x, const float* __restrict__ ga, const float* __restrict__ gb,
@@ -447,6 +464,14 @@ extern "C" int serl_gn_finalize(const float* stats, const float* gamma, const fl
   const int Cg = C / 4;
   gn_finalize_kernel<<<ceil_div(N * C, 256), 256, 0, ST(stream)>>>(stats, gamma, beta, out_a, out_b, N, C, Cg, (float)HW * (float)Cg, eps);
   return check_launch("gn_finalize_kernel");
+}
+
+extern "C" int serl_affine_relu_h16(void* x, const float* a, const float* b, int N, int HW, int C, int fmt, void* stream) {
+  size_t total = (size_t)N * HW * (C / 8);
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  if (fmt == SERL_FMT_FP16) affine_relu_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(static_cast<uint16_t*>(x), a, b, N, HW, C);
+  else affine_relu_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(static_cast<uint16_t*>(x), a, b, N, HW, C);
+  return check_launch("affine_relu_kernel");
 }
 
 extern "C" int serl_maxpool_affine_h16(const void* x, const float* a, const float* b, void* y, int N, int Hi, int Wi, int C, int fmt, void* stream) {

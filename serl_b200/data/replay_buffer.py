@@ -100,6 +100,8 @@ class DeviceRing:
                         state=pin(n, self.T * self.S), next_state=pin(n, self.T * self.S), actions=pin(n, self.A),
                         rewards=pin(n), masks=pin(n), dones=pin(n, dt=torch.uint8), valid=pin(n, dt=torch.uint8),
                         dst=pin(n, dt=torch.int32), src=pin(n, dt=torch.int32))
+        # numpy views of the pinned staging area: host-side writes never go through the torch dispatcher
+        self._stn = {k: ({c: t.numpy() for c, t in v.items()} if isinstance(v, dict) else v.numpy()) for k, v in self._st.items()}
         self._sd = {k: ({c: torch.empty_like(t, device=dev) for c, t in v.items()} if isinstance(v, dict)
                         else torch.empty_like(v, device=dev)) for k, v in self._st.items()}
         self._touched_host = pin(n * 4, dt=torch.int32)
@@ -130,14 +132,14 @@ class DeviceRing:
                 or len(self._touched) > 3 * self.STAGE):
             self.flush()
         k = self._n_pending
-        st = self._st
+        st = self._stn
         st["dst"][k], st["src"][k] = dst, src_slot
         if src_slot < 0:
             for c in self.cams:
-                st["frames"][c][k] = torch.from_numpy(np.ascontiguousarray(frames[c]))
-            st["state"][k] = torch.from_numpy(np.asarray(state, np.float32).reshape(-1))
-            st["next_state"][k] = torch.from_numpy(np.asarray(next_state, np.float32).reshape(-1))
-            st["actions"][k] = torch.from_numpy(np.asarray(action, np.float32).reshape(-1))
+                st["frames"][c][k] = frames[c]
+            st["state"][k] = np.asarray(state, np.float32).reshape(-1)
+            st["next_state"][k] = np.asarray(next_state, np.float32).reshape(-1)
+            st["actions"][k] = np.asarray(action, np.float32).reshape(-1)
             st["rewards"][k], st["masks"][k], st["dones"][k] = float(reward), float(mask), int(bool(done))
         st["valid"][k] = int(valid)
         self._valid_host[dst] = valid
@@ -194,8 +196,8 @@ class DeviceRing:
             if self._touched:
                 slots = np.fromiter(self._touched, dtype=np.int32)
                 m = len(slots)
-                self._touched_host[:m] = torch.from_numpy(slots)
-                self._touched_val_host[:m] = torch.from_numpy(self._valid_host[slots].astype(np.uint8))
+                self._touched_host.numpy()[:m] = slots
+                self._touched_val_host.numpy()[:m] = self._valid_host[slots]
                 self._touched_dev[:m].copy_(self._touched_host[:m], non_blocking=True)
                 self._touched_val_dev[:m].copy_(self._touched_val_host[:m], non_blocking=True)
                 L.call("serl_replay_set_valid", self.valid.data_ptr(), self._touched_dev.data_ptr(), self._touched_val_dev.data_ptr(),
