@@ -136,6 +136,10 @@ typedef struct serl_conv_tc_desc {
   int32_t N, Hi, Wi, Ci, Ho, Wo, Co, kh, kw, stride, pad_lo, stem, fmt;
 } serl_conv_tc_desc;
 int serl_conv2d_tc_h16(const serl_conv_tc_desc* d, void* stream);
+/* Stride-1 3x3 SAME convolution without im2col redundancy: the input patch of a 128-position raster tile is staged once
+ * in shared memory and the nine taps are shifted UMMA descriptors over it; weights arrive by TMA.  Same descriptor as
+ * above (kh=kw=3, stride=1, pad_lo=1, no operand transform).  base_offset_mode: 0 = descriptor base_offset field left 0. */
+int serl_conv3x3s1_tc_h16(const serl_conv_tc_desc* d, int base_offset_mode, void* stream);
 /* (N,4,2) sums -> per-(image, channel) affine a = rstd*gamma, b = beta - mean*a (flax GroupNorm statistics) */
 int serl_gn_finalize(const float* stats, const float* gamma, const float* beta, float* out_a, float* out_b, int N, int C,
                      int HW, float eps, void* stream);

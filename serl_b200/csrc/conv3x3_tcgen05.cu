@@ -1,0 +1,333 @@
+// Stride-1 3x3 convolution on tcgen05 tensor cores WITHOUT im2col redundancy ("shifted window").
+//
+// The (zero-padded) input of an image is viewed as a 1-D raster with pitch P = W+1 and R = H+1 rows per image: the
+// extra column / row are zeros shared between neighbours (column W of row h is both the right pad of row h and the left
+// pad of row h+1; row H of image n is both its bottom pad and the top pad of image n+1).  In that raster the input of
+// output position q under tap (r, s) is simply position q + (r-1)*P + (s-1), so for a tile of 128 consecutive raster
+// positions ALL NINE taps read windows of ONE contiguous patch of 128 + 2P + 2 positions.  The producers stage that
+// patch once per 64-channel block into 128B-swizzled shared memory (one 128-byte row per position) and the nine taps are
+// nine UMMA descriptors whose start address is shifted by (r*P + s) rows - no data is gathered twice.  Weights arrive by
+// TMA (cp.async.bulk.tensor, 128B swizzle) through their own mbarrier ring.  Outputs at pad positions are computed and
+// discarded (M efficiency H*W / ((H+1)(W+1)): 94% at 32x32, 64% at 4x4).
+//
+//   warps 0-3  stage the patch (coalesced 128-bit gathers, zeros at pad positions), later the epilogue
+//              (tcgen05.ld, GroupNorm partial sums segmented by image, 16-bit pack, NHWC store of valid positions)
+//   warp 4     tcgen05.mma issuer (9 taps x 4 K-steps per channel block), commits
+//   warp 5     TMA issuer for the weight tiles
+//
+// Replaces the conv of vision/resnet_v1.py:142-147 (ResNetBlock 3x3 convs with stride 1, SAME padding).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "serl_b200.h"
+
+namespace serl {
+
+struct Conv3Args {
+  const uint16_t* x;       // (N,H,W,Ci) 16-bit, already activated
+  uint16_t* y;             // (N,H,W,Co) raw conv output
+  float* stats;            // (N,4,2)
+  int32_t* error;
+  int N, H, W, Ci, Co, P, R, cblocks, Cg, Lp, patch_bytes, base_offset_mode;
+  long long Q;
+};
+
+struct C3Bf16 {
+  static constexpr uint32_t kUmmaFormat = 1;
+  __device__ static inline uint32_t pack(float lo, float hi) { __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&v); }
+};
+struct C3Fp16 {
+  static constexpr uint32_t kUmmaFormat = 0;
+  __device__ static inline uint32_t pack(float lo, float hi) {
+    __half2 v = __floats2half2_rn(fminf(fmaxf(lo, -65504.f), 65504.f), fminf(fmaxf(hi, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+
+__device__ inline uint32_t c3_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ inline void c3_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(c3_smem(bar)), "r"(count));
+}
+__device__ inline void c3_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(c3_smem(bar)) : "memory");
+}
+__device__ inline void c3_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(c3_smem(bar)), "r"(bytes) : "memory");
+}
+__device__ inline bool c3_mbar_wait(uint64_t* bar, uint32_t parity, int32_t* error) {
+  const uint32_t addr = c3_smem(bar);
+  const long long t0 = clock64();
+#pragma unroll 1
+  for (;;) {
+    uint32_t done;
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return true;
+    if (clock64() - t0 > 4000000000ll) break;
+  }
+  atomicOr(error, 4);
+  return false;
+}
+__device__ inline uint64_t c3_desc(uint32_t saddr, uint32_t base_offset) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | ((uint64_t)(base_offset & 7) << 49) | (2ull << 61);
+}
+__device__ inline void c3_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ inline void c3_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(c3_smem(bar)) : "memory");
+}
+__device__ inline void c3_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ inline void c3_tma_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(c3_smem(smem_dst)), "l"(map), "r"(c3_smem(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+constexpr int C3_MAXR = 13;           // patch rows per producer thread: ceil((128 + 2*33 + 2) / 16)
+constexpr int C3_THREADS = 192;
+
+template <class F, int BN, int BSTAGES>
+__global__ void __launch_bounds__(C3_THREADS) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap wmap, const Conv3Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int B_STAGE = BN * 128;
+  uint8_t* sP = smem;                                   // 2 patches
+  uint8_t* sB = smem + 2 * a.patch_bytes;
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(sB + BSTAGES * B_STAGE);
+  uint64_t* pempty = pfull + 2;
+  uint64_t* bfull = pempty + 2;
+  uint64_t* bempty = bfull + BSTAGES;
+  uint64_t* tmem_full = bempty + BSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long q0 = (long long)blockIdx.x * 128;      // first raster position of this tile
+  const int n0 = blockIdx.y * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) { c3_mbar_init(&pfull[s], 4); c3_mbar_init(&pempty[s], 1); }
+    for (int s = 0; s < BSTAGES; ++s) { c3_mbar_init(&bfull[s], 1); c3_mbar_init(&bempty[s], 1); }
+    c3_mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(c3_smem(tmem_slot)), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 5 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int taps = 9;
+
+  if (warp < 4) {
+    // ------------------------------- patch producers -------------------------------
+    const int tid = threadIdx.x, chunk = tid & 7, rsub = tid >> 3;
+    long long poff[C3_MAXR];                               // element offset of the pixel (channel 0) or -1 for a zero row
+#pragma unroll
+    for (int i = 0; i < C3_MAXR; ++i) {
+      const int j = rsub + 16 * i;
+      const long long q = q0 - a.P - 1 + j;
+      poff[i] = -1;
+      if (j < a.Lp && q >= 0 && q < a.Q) {
+        const long long rr = q / a.P; const int wcol = (int)(q - rr * a.P);
+        const int n = (int)(rr / a.R), hrow = (int)(rr - (long long)n * a.R);
+        if (wcol < a.W && hrow < a.H) poff[i] = (((long long)n * a.H + hrow) * a.W + wcol) * a.Ci;
+      }
+    }
+    bool ok = true;
+    for (int cb = 0; cb < a.cblocks && ok; ++cb) {
+      const int ps = cb & 1;
+      uint4 v[C3_MAXR];
+#pragma unroll
+      for (int i = 0; i < C3_MAXR; ++i) {
+        v[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (poff[i] >= 0) v[i] = *reinterpret_cast<const uint4*>(a.x + poff[i] + cb * 64 + chunk * 8);
+      }
+      ok = c3_mbar_wait(&pempty[ps], (uint32_t)((cb >> 1) & 1) ^ 1u, a.error);
+      uint8_t* Ps = sP + ps * a.patch_bytes;
+#pragma unroll
+      for (int i = 0; i < C3_MAXR; ++i) {
+        const int j = rsub + 16 * i;
+        if (j < a.Lp) *reinterpret_cast<uint4*>(Ps + (j >> 3) * 1024 + (j & 7) * 128 + ((chunk ^ (j & 7)) << 4)) = v[i];
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) c3_mbar_arrive(&pfull[ps]);
+    }
+    // ------------------------------- epilogue --------------------------------------
+    ok = ok && c3_mbar_wait(tmem_full, 0u, a.error);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int row = warp * 32 + lane;
+    const long long q = q0 + row;
+    bool valid = false; int n_img = 0; long long opix = 0;
+    if (q < a.Q) {
+      const long long rr = q / a.P; const int wcol = (int)(q - rr * a.P);
+      n_img = (int)(rr / a.R); const int hrow = (int)(rr - (long long)n_img * a.R);
+      valid = wcol < a.W && hrow < a.H;
+      opix = ((long long)n_img * a.H + hrow) * a.W + wcol;
+    } else { n_img = a.N - 1; }
+    valid = valid && ok;
+    constexpr int MAXG = 4;
+    float gs[MAXG], gss[MAXG];
+#pragma unroll
+    for (int g = 0; g < MAXG; ++g) { gs[g] = 0.f; gss[g] = 0.f; }
+    const int g_first = n0 / a.Cg;
+#pragma unroll
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      c3_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      float s = 0.f, ss = 0.f;
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+        s += f0 + f1; ss += f0 * f0 + f1 * f1;
+        pk[j] = F::pack(f0, f1);
+      }
+      if (valid) {
+        const int g = (n0 + c0) / a.Cg - g_first;
+#pragma unroll
+        for (int gg = 0; gg < MAXG; ++gg) if (gg == g) { gs[gg] += s; gss[gg] += ss; }
+        uint4* dst = reinterpret_cast<uint4*>(a.y + opix * a.Co + n0 + c0);
+        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+    }
+    // GroupNorm sums, segmented by image: a warp's 32 consecutive raster positions touch at most 3 images
+    const int ngroups = (BN + a.Cg - 1) / a.Cg;
+    const int id_lo = __shfl_sync(0xffffffffu, n_img, 0), id_hi = __shfl_sync(0xffffffffu, n_img, 31);
+    for (int id = id_lo; id <= id_hi; ++id) {
+      for (int g = 0; g < ngroups; ++g) {
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int gg = 0; gg < MAXG; ++gg) if (gg == g && n_img == id && valid) { s = gs[gg]; ss = gss[gg]; }
+        s = warp_sum(s); ss = warp_sum(ss);
+        if (lane == 0 && (s != 0.f || ss != 0.f)) {
+          float* st = a.stats + ((size_t)id * 4 + g_first + g) * 2;
+          atomicAdd(st, s); atomicAdd(st + 1, ss);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  } else if (warp == 4) {
+    // ------------------------------- MMA issuer -----------------------------------
+    const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    bool ok = true;
+    int it = 0;
+    for (int cb = 0; cb < a.cblocks && ok; ++cb) {
+      const int ps = cb & 1;
+      ok = c3_mbar_wait(&pfull[ps], (uint32_t)((cb >> 1) & 1), a.error);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t pbase = c3_smem(sP + ps * a.patch_bytes);
+      for (int tap = 0; tap < taps && ok; ++tap, ++it) {
+        const int sb = it % BSTAGES;
+        ok = c3_mbar_wait(&bfull[sb], (uint32_t)((it / BSTAGES) & 1), a.error);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0 && ok) {
+          const int r = tap / 3, s = tap - 3 * r;
+          const uint32_t off = (uint32_t)(r * a.P + s);               // window shift in patch rows
+          const uint64_t ad = c3_desc(pbase + off * 128u, a.base_offset_mode ? off : 0u);
+          const uint64_t bd = c3_desc(c3_smem(sB + sb * B_STAGE), 0u);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) c3_mma(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((it | k) != 0));
+          c3_commit(&bempty[sb]);
+        }
+        __syncwarp();
+      }
+      if (lane == 0 && ok) c3_commit(&pempty[ps]);
+      __syncwarp();
+    }
+    if (lane == 0) { if (ok) c3_commit(tmem_full); else c3_mbar_arrive(tmem_full); }
+  } else {
+    // ------------------------------- weight TMA issuer ----------------------------
+    if (lane == 0) {
+      bool ok = true;
+      int it = 0;
+      for (int cb = 0; cb < a.cblocks && ok; ++cb) {
+        for (int tap = 0; tap < taps && ok; ++tap, ++it) {
+          const int sb = it % BSTAGES;
+          ok = c3_mbar_wait(&bempty[sb], (uint32_t)((it / BSTAGES) & 1) ^ 1u, a.error);
+          if (!ok) break;
+          c3_mbar_expect_tx(&bfull[sb], (uint32_t)B_STAGE);
+          c3_tma_2d(sB + sb * B_STAGE, &wmap, tap * a.Ci + cb * 64, n0, &bfull[sb]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+template <class F, int BN, int BSTAGES>
+static int launch_conv3(const CUtensorMap& map, const Conv3Args& a, cudaStream_t st) {
+  const size_t smem = (size_t)2 * a.patch_bytes + (size_t)BSTAGES * BN * 128 + 1024 + 256;
+  auto kern = conv3x3_tc_kernel<F, BN, BSTAGES>;
+  static size_t configured = 0;
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv3x3_tc)");
+    configured = smem;
+  }
+  dim3 grid((unsigned)((a.Q + 127) / 128), a.Co / BN);
+  kern<<<grid, C3_THREADS, smem, st>>>(map, a);
+  return check_launch("conv3x3_tc_kernel");
+}
+
+}  // namespace serl
+
+using namespace serl;
+
+extern "C" int serl_conv3x3s1_tc_h16(const serl_conv_tc_desc* d, int base_offset_mode, void* stream) {
+  if (!d || !d->x || !d->w || !d->y || !d->stats || !d->error) { set_last_error("serl_conv3x3s1_tc_h16: invalid descriptor"); return SERL_ERR_INVALID; }
+  if (d->kh != 3 || d->kw != 3 || d->stride != 1 || d->pad_lo != 1 || d->Ho != d->Hi || d->Wo != d->Wi || d->Ci % 64 || d->Co % 64 || d->Wi > 32 || d->in_a) {
+    set_last_error("serl_conv3x3s1_tc_h16: needs a 3x3 stride-1 SAME conv, Ci,Co %% 64 == 0, W <= 32, no operand transform"); return SERL_ERR_UNSUPPORTED;
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_last_error("serl_conv3x3s1_tc_h16: cuTensorMapEncodeTiled unavailable"); return SERL_ERR_CUDA; }
+  Conv3Args a{};
+  a.x = static_cast<const uint16_t*>(d->x); a.y = static_cast<uint16_t*>(d->y); a.stats = d->stats; a.error = d->error;
+  a.N = d->N; a.H = d->Hi; a.W = d->Wi; a.Ci = d->Ci; a.Co = d->Co; a.P = d->Wi + 1; a.R = d->Hi + 1;
+  a.cblocks = d->Ci / 64; a.Cg = d->Co / 4; a.Lp = 128 + 2 * a.P + 2; a.patch_bytes = ((a.Lp * 128 + 1023) / 1024) * 1024;
+  a.Q = (long long)d->N * a.R * a.P; a.base_offset_mode = base_offset_mode;
+  const int BN = d->Co == 64 ? 64 : 128;
+  CUtensorMap map;
+  const cuuint64_t gdim[2] = {(cuuint64_t)9 * d->Ci, (cuuint64_t)d->Co};
+  const cuuint64_t gstr[1] = {(cuuint64_t)9 * d->Ci * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)BN};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(&map, d->fmt == SERL_FMT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(d->w),
+                   gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("serl_conv3x3s1_tc_h16: cuTensorMapEncodeTiled failed (%d)", (int)r); return SERL_ERR_CUDA; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (d->fmt == SERL_FMT_FP16) return BN == 64 ? launch_conv3<C3Fp16, 64, 6>(map, a, st) : launch_conv3<C3Fp16, 128, 3>(map, a, st);
+  return BN == 64 ? launch_conv3<C3Bf16, 64, 6>(map, a, st) : launch_conv3<C3Bf16, 128, 3>(map, a, st);
+}

@@ -24,6 +24,10 @@ def _s():
 # coefficients are staged in shared memory the materialised variant is faster (profiles/r01_*).
 FUSE_OPERAND_GROUPNORM = False
 
+# Stride-1 3x3 convs: "shifted window" kernel (conv3x3_tcgen05.cu) instead of the im2col-gather kernel.
+USE_SHIFTED_WINDOW = True
+BASE_OFFSET_MODE = 0
+
 FMT = {"bf16": (L.FMT_BF16, torch.bfloat16), "fp16": (L.FMT_FP16, torch.float16)}
 
 
@@ -69,7 +73,10 @@ def _conv(plan, x, w, y, stats, N, Hi, Wi, Ci, Ho, Wo, Co, k, stride, pad_lo, in
         d.in_a, d.in_b = in_ab[0].data_ptr(), in_ab[1].data_ptr()
     d.error = plan.error.data_ptr()
     d.N, d.Hi, d.Wi, d.Ci, d.Ho, d.Wo, d.Co, d.kh, d.kw, d.stride, d.pad_lo, d.stem, d.fmt = N, Hi, Wi, Ci, Ho, Wo, Co, k, k, stride, pad_lo, int(stem), plan.fmt
-    L.call("serl_conv2d_tc_h16", C.byref(d), _s())
+    if USE_SHIFTED_WINDOW and k == 3 and stride == 1 and pad_lo == 1 and in_ab is None and not stem and Wi <= 32 and Ci % 64 == 0:
+        L.call("serl_conv3x3s1_tc_h16", C.byref(d), BASE_OFFSET_MODE, _s())
+    else:
+        L.call("serl_conv2d_tc_h16", C.byref(d), _s())
 
 
 def _finalize(stats, gamma, beta, ab, N, Cc, HW):
