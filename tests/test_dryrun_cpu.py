@@ -132,6 +132,7 @@ def test_bf16_trunk_call_sequence(dry):
                            precision="bf16")
     del dry[:]
     agent.update_critics(rb.sample(4, pack_obs_and_next_obs=True))
-    assert dry.count("serl_conv2d_tc_h16") == 12 and dry.count("serl_conv2d_nhwc_f32") == 0
+    assert dry.count("serl_conv2d_tc_h16") + dry.count("serl_conv3x3s1_tc_h16") == 12 and dry.count("serl_conv2d_nhwc_f32") == 0
+    assert dry.count("serl_conv3x3s1_tc_h16") == 5        # the stride-1 3x3 convs take the shifted-window kernel
     assert dry.count("serl_gn_finalize") == 12 and dry.count("serl_block_combine_h16") == 4
     assert dry.count("serl_trunk_stem_prep_h16") == 1 and dry.count("serl_maxpool_affine_h16") == 1
