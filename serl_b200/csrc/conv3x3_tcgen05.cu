@@ -133,16 +133,22 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_tc_kernel(const __grid_con
   if (warp < 4) {
     // ------------------------------- patch producers -------------------------------
     const int tid = threadIdx.x, chunk = tid & 7, rsub = tid >> 3;
-    long long poff[C3_MAXR];                               // element offset of the pixel (channel 0) or -1 for a zero row
+    int poff[C3_MAXR];                                     // element offset of the pixel (channel 0) or -1 for a zero row
+    {
+      // decode the first row once (two 32-bit divisions), then walk the raster 16 positions at a time
+      const int qs = (int)q0 - a.P - 1 + rsub;              // may be negative: shift by whole images to keep the math unsigned
+      const int per_img = a.R * a.P;
+      int q = qs + per_img;                                 // >= 0 because per_img > P + 1
+      int n = q / per_img - 1; int rem = q - (n + 1) * per_img;
+      int hrow = rem / a.P; int wcol = rem - hrow * a.P;
 #pragma unroll
-    for (int i = 0; i < C3_MAXR; ++i) {
-      const int j = rsub + 16 * i;
-      const long long q = q0 - a.P - 1 + j;
-      poff[i] = -1;
-      if (j < a.Lp && q >= 0 && q < a.Q) {
-        const long long rr = q / a.P; const int wcol = (int)(q - rr * a.P);
-        const int n = (int)(rr / a.R), hrow = (int)(rr - (long long)n * a.R);
-        if (wcol < a.W && hrow < a.H) poff[i] = (((long long)n * a.H + hrow) * a.W + wcol) * a.Ci;
+      for (int i = 0; i < C3_MAXR; ++i) {
+        const int j = rsub + 16 * i;
+        poff[i] = -1;
+        if (j < a.Lp && n >= 0 && n < a.N && wcol < a.W && hrow < a.H) poff[i] = ((n * a.H + hrow) * a.W + wcol) * a.Ci;
+        wcol += 16;
+        while (wcol >= a.P) { wcol -= a.P; ++hrow; }
+        while (hrow >= a.R) { hrow -= a.R; ++n; }
       }
     }
     bool ok = true;
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_tc_kernel(const __grid_con
 #pragma unroll
       for (int i = 0; i < C3_MAXR; ++i) {
         v[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (poff[i] >= 0) v[i] = *reinterpret_cast<const uint4*>(a.x + poff[i] + cb * 64 + chunk * 8);
+        if (poff[i] >= 0) v[i] = *reinterpret_cast<const uint4*>(a.x + (size_t)(uint32_t)(poff[i] + cb * 64 + chunk * 8));
       }
       ok = c3_mbar_wait(&pempty[ps], (uint32_t)((cb >> 1) & 1) ^ 1u, a.error);
       uint8_t* Ps = sP + ps * a.patch_bytes;
@@ -169,13 +175,14 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_tc_kernel(const __grid_con
     ok = ok && c3_mbar_wait(tmem_full, 0u, a.error);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int row = warp * 32 + lane;
-    const long long q = q0 + row;
-    bool valid = false; int n_img = 0; long long opix = 0;
-    if (q < a.Q) {
-      const long long rr = q / a.P; const int wcol = (int)(q - rr * a.P);
-      n_img = (int)(rr / a.R); const int hrow = (int)(rr - (long long)n_img * a.R);
+    const int q = (int)q0 + row;
+    bool valid = false; int n_img = 0; int opix = 0;
+    if (q < (int)a.Q) {
+      const int per_img = a.R * a.P;
+      n_img = q / per_img; const int rem = q - n_img * per_img;
+      const int hrow = rem / a.P, wcol = rem - hrow * a.P;
       valid = wcol < a.W && hrow < a.H;
-      opix = ((long long)n_img * a.H + hrow) * a.W + wcol;
+      opix = (n_img * a.H + hrow) * a.W + wcol;
     } else { n_img = a.N - 1; }
     valid = valid && ok;
     constexpr int MAXG = 4;
@@ -199,7 +206,7 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_tc_kernel(const __grid_con
         const int g = (n0 + c0) / a.Cg - g_first;
 #pragma unroll
         for (int gg = 0; gg < MAXG; ++gg) if (gg == g) { gs[gg] += s; gss[gg] += ss; }
-        uint4* dst = reinterpret_cast<uint4*>(a.y + opix * a.Co + n0 + c0);
+        uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)opix * a.Co + n0 + c0);
         dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
       }
@@ -317,6 +324,7 @@ extern "C" int serl_conv3x3s1_tc_h16(const serl_conv_tc_desc* d, int base_offset
   a.N = d->N; a.H = d->Hi; a.W = d->Wi; a.Ci = d->Ci; a.Co = d->Co; a.P = d->Wi + 1; a.R = d->Hi + 1;
   a.cblocks = d->Ci / 64; a.Cg = d->Co / 4; a.Lp = 128 + 2 * a.P + 2; a.patch_bytes = ((a.Lp * 128 + 1023) / 1024) * 1024;
   a.Q = (long long)d->N * a.R * a.P; a.base_offset_mode = base_offset_mode;
+  if (a.Q + 4096 >= (1ll << 31) || (long long)d->N * d->Hi * d->Wi * d->Ci >= (1ll << 31)) { set_last_error("serl_conv3x3s1_tc_h16: tensor too large for 32-bit raster indexing"); return SERL_ERR_UNSUPPORTED; }
   const int BN = d->Co == 64 ? 64 : 128;
   CUtensorMap map;
   const cuuint64_t gdim[2] = {(cuuint64_t)9 * d->Ci, (cuuint64_t)d->Co};

@@ -137,22 +137,31 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a)
     const int tid = threadIdx.x;
     const int chunk = tid & 7, rsub = tid >> 3;
     const int HoWo = a.Ho * a.Wo;
-    int rn[8], rh[8], rw[8];
+    int rn[8], rh[8], rw[8], rbase[8];                      // image, top-left input coords, element offset of (rh, rw, ch 0)
+    {
+      const int gm0 = m0 + rsub;
+      int n = gm0 / HoWo; int rem = gm0 - n * HoWo; int ho = rem / a.Wo; int wo = rem - ho * a.Wo;
+      const int cpp = kStem ? 12 : a.Ci;                    // channels per input pixel
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int gm = m0 + rsub + 16 * i;
-      if (gm < a.M) {
-        const int n = gm / HoWo, rem = gm - n * HoWo, ho = rem / a.Wo, wo = rem - ho * a.Wo;
-        rn[i] = n; rh[i] = ho * a.stride - a.pad; rw[i] = wo * a.stride - a.pad;
-      } else { rn[i] = -1; rh[i] = 0; rw[i] = 0; }
+      for (int i = 0; i < 8; ++i) {                         // rows rsub + 16 i: walk the output raster instead of dividing
+        if (m0 + rsub + 16 * i < a.M) {
+          rn[i] = n; rh[i] = ho * a.stride - a.pad; rw[i] = wo * a.stride - a.pad;
+          rbase[i] = ((n * a.Hi + rh[i]) * a.Wi + rw[i]) * cpp;
+        } else { rn[i] = -1; rh[i] = 0; rw[i] = 0; rbase[i] = 0; }
+        wo += 16;
+        while (wo >= a.Wo) { wo -= a.Wo; ++ho; }
+        while (ho >= a.Ho) { ho -= a.Ho; ++n; }
+      }
     }
+    int tap_r = 0, tap_s = 0, cblk = 0;                     // k-block -> (kernel row, kernel col, channel block), advanced incrementally
     bool ok = true;
     const size_t Kp = (size_t)a.num_kb * TC_BK;
     for (int kb = 0; kb < a.num_kb && ok; ++kb) {
       const int s = kb % STAGES;
       const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-      int r = 0, sx = 0, c0 = 0;
-      if (!kStem) { const int tap = kb / a.cblocks; c0 = (kb - tap * a.cblocks) * TC_BK; r = tap / a.kw; sx = tap - r * a.kw; }
+      const int r = tap_r, sx = tap_s, c0 = cblk * TC_BK;
+      const int tap_off = kStem ? kb * a.Wi * 12 : (r * a.Wi + sx) * a.Ci + c0;
+      if (!kStem) { if (++cblk == a.cblocks) { cblk = 0; if (++tap_s == a.kw) { tap_s = 0; ++tap_r; } } }
       // ---- phase 1: issue EVERY global load of this k-block before anything consumes one (memory-level parallelism:
       //      the gather is latency-bound, so all 8 A rows + the B rows of a thread must be in flight together)
       uint4 va[8], vb[BN / 16];
@@ -165,7 +174,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a)
           if (kStem) {
             // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 12 ch = 48 contiguous 16-bit values (96 B)
             if (chunk < 6) {
-              const uint16_t* src = a.x + (((size_t)rn[i] * a.Hi + (rh[i] + kb)) * a.Wi + rw[i]) * 12 + chunk * 8;
+              const uint16_t* src = a.x + (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8);
               const uint2 lo = *reinterpret_cast<const uint2*>(src), hi = *reinterpret_cast<const uint2*>(src + 4);
               va[i] = make_uint4(lo.x, lo.y, hi.x, hi.y);
             }
@@ -173,7 +182,7 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a)
             const int hi_ = rh[i] + r, wi_ = rw[i] + sx;
             if (hi_ >= 0 && hi_ < a.Hi && wi_ >= 0 && wi_ < a.Wi) {
               inb[i] = true;
-              va[i] = *reinterpret_cast<const uint4*>(a.x + (((size_t)rn[i] * a.Hi + hi_) * a.Wi + wi_) * a.Ci + c0 + chunk * 8);
+              va[i] = *reinterpret_cast<const uint4*>(a.x + (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8));
             }
           }
         }
