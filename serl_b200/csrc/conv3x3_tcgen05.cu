@@ -93,10 +93,13 @@ __device__ inline void c3_tma_2d(void* smem_dst, const CUtensorMap* map, int c0,
 }
 
 constexpr int C3_MAXR = 13;           // patch rows per producer thread: ceil((128 + 2*33 + 2) / 16)
-constexpr int C3_THREADS = 192;
+constexpr int C3_THREADS = 320;       // warps 0-3 epilogue | 4-7 patch producers | 8 MMA issuer | 9 weight-TMA issuer
 
+// Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the four roles run decoupled through mbarrier rings
+// (patch full/empty x2, weight full/empty xBSTAGES, accumulator full/empty x2 - TMEM holds two accumulators), so the
+// gather of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
 template <class F, int BN, int BSTAGES>
-__global__ void __launch_bounds__(C3_THREADS) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap wmap, const Conv3Args a) {
+__global__ void __launch_bounds__(C3_THREADS, 2) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap wmap, const Conv3Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_STAGE = BN * 128;
@@ -106,176 +109,196 @@ __global__ void __launch_bounds__(C3_THREADS) conv3x3_tc_kernel(const __grid_con
   uint64_t* pempty = pfull + 2;
   uint64_t* bfull = pempty + 2;
   uint64_t* bempty = bfull + BSTAGES;
-  uint64_t* tmem_full = bempty + BSTAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* afull = bempty + BSTAGES;
+  uint64_t* aempty = afull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long q0 = (long long)blockIdx.x * 128;      // first raster position of this tile
-  const int n0 = blockIdx.y * BN;
+  const int n_tiles_n = a.Co / BN;
+  const int n_tiles = (int)((a.Q + 127) / 128) * n_tiles_n;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { c3_mbar_init(&pfull[s], 4); c3_mbar_init(&pempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { c3_mbar_init(&pfull[s], 4); c3_mbar_init(&pempty[s], 1); c3_mbar_init(&afull[s], 1); c3_mbar_init(&aempty[s], 4); }
     for (int s = 0; s < BSTAGES; ++s) { c3_mbar_init(&bfull[s], 1); c3_mbar_init(&bempty[s], 1); }
-    c3_mbar_init(tmem_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(c3_smem(tmem_slot)), "r"((uint32_t)BN) : "memory");
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(c3_smem(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  if (warp == 5 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+  if (warp == 9 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  const int taps = 9;
+  const int per_img = a.R * a.P;
 
-  if (warp < 4) {
+  if (warp >= 4 && warp < 8) {
     // ------------------------------- patch producers -------------------------------
-    const int tid = threadIdx.x, chunk = tid & 7, rsub = tid >> 3;
-    int poff[C3_MAXR];                                     // element offset of the pixel (channel 0) or -1 for a zero row
-    {
-      // decode the first row once (two 32-bit divisions), then walk the raster 16 positions at a time
-      const int qs = (int)q0 - a.P - 1 + rsub;              // may be negative: shift by whole images to keep the math unsigned
-      const int per_img = a.R * a.P;
-      int q = qs + per_img;                                 // >= 0 because per_img > P + 1
-      int n = q / per_img - 1; int rem = q - (n + 1) * per_img;
-      int hrow = rem / a.P; int wcol = rem - hrow * a.P;
-#pragma unroll
-      for (int i = 0; i < C3_MAXR; ++i) {
-        const int j = rsub + 16 * i;
-        poff[i] = -1;
-        if (j < a.Lp && n >= 0 && n < a.N && wcol < a.W && hrow < a.H) poff[i] = ((n * a.H + hrow) * a.W + wcol) * a.Ci;
-        wcol += 16;
-        while (wcol >= a.P) { wcol -= a.P; ++hrow; }
-        while (hrow >= a.R) { hrow -= a.R; ++n; }
-      }
-    }
+    const int tid = threadIdx.x - 128, chunk = tid & 7, rsub = tid >> 3;
     bool ok = true;
-    for (int cb = 0; cb < a.cblocks && ok; ++cb) {
-      const int ps = cb & 1;
-      uint4 v[C3_MAXR];
+    int pc = 0;                                            // patches produced so far (ring position)
+    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+      const int q0 = (tile / n_tiles_n) * 128;
+      int poff[C3_MAXR];                                   // element offset of the pixel (channel 0) or -1 for a zero row
+      {
+        int q = q0 - a.P - 1 + rsub + per_img;             // shifted by one image so it is non-negative
+        int n = q / per_img - 1; const int rem = q - (n + 1) * per_img;
+        int hrow = rem / a.P; int wcol = rem - hrow * a.P;
 #pragma unroll
-      for (int i = 0; i < C3_MAXR; ++i) {
-        v[i] = make_uint4(0u, 0u, 0u, 0u);
-        if (poff[i] >= 0) v[i] = *reinterpret_cast<const uint4*>(a.x + (size_t)(uint32_t)(poff[i] + cb * 64 + chunk * 8));
+        for (int i = 0; i < C3_MAXR; ++i) {                // walk the raster 16 positions at a time
+          const int j = rsub + 16 * i;
+          poff[i] = -1;
+          if (j < a.Lp && n >= 0 && n < a.N && wcol < a.W && hrow < a.H) poff[i] = ((n * a.H + hrow) * a.W + wcol) * a.Ci;
+          wcol += 16;
+          while (wcol >= a.P) { wcol -= a.P; ++hrow; }
+          while (hrow >= a.R) { hrow -= a.R; ++n; }
+        }
       }
-      ok = c3_mbar_wait(&pempty[ps], (uint32_t)((cb >> 1) & 1) ^ 1u, a.error);
-      uint8_t* Ps = sP + ps * a.patch_bytes;
+      for (int cb = 0; cb < a.cblocks && ok; ++cb, ++pc) {
+        const int ps = pc & 1;
+        uint4 v[C3_MAXR];
 #pragma unroll
-      for (int i = 0; i < C3_MAXR; ++i) {
-        const int j = rsub + 16 * i;
-        if (j < a.Lp) *reinterpret_cast<uint4*>(Ps + (j >> 3) * 1024 + (j & 7) * 128 + ((chunk ^ (j & 7)) << 4)) = v[i];
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) c3_mbar_arrive(&pfull[ps]);
-    }
-    // ------------------------------- epilogue --------------------------------------
-    ok = ok && c3_mbar_wait(tmem_full, 0u, a.error);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = warp * 32 + lane;
-    const int q = (int)q0 + row;
-    bool valid = false; int n_img = 0; int opix = 0;
-    if (q < (int)a.Q) {
-      const int per_img = a.R * a.P;
-      n_img = q / per_img; const int rem = q - n_img * per_img;
-      const int hrow = rem / a.P, wcol = rem - hrow * a.P;
-      valid = wcol < a.W && hrow < a.H;
-      opix = (n_img * a.H + hrow) * a.W + wcol;
-    } else { n_img = a.N - 1; }
-    valid = valid && ok;
-    constexpr int MAXG = 4;
-    float gs[MAXG], gss[MAXG];
+        for (int i = 0; i < C3_MAXR; ++i) {
+          v[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (poff[i] >= 0) v[i] = *reinterpret_cast<const uint4*>(a.x + (size_t)(uint32_t)(poff[i] + cb * 64 + chunk * 8));
+        }
+        ok = c3_mbar_wait(&pempty[ps], (uint32_t)((pc >> 1) & 1) ^ 1u, a.error);
+        uint8_t* Ps = sP + ps * a.patch_bytes;
 #pragma unroll
-    for (int g = 0; g < MAXG; ++g) { gs[g] = 0.f; gss[g] = 0.f; }
-    const int g_first = n0 / a.Cg;
-#pragma unroll
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
-      c3_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      float s = 0.f, ss = 0.f;
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
-        s += f0 + f1; ss += f0 * f0 + f1 * f1;
-        pk[j] = F::pack(f0, f1);
-      }
-      if (valid) {
-        const int g = (n0 + c0) / a.Cg - g_first;
-#pragma unroll
-        for (int gg = 0; gg < MAXG; ++gg) if (gg == g) { gs[gg] += s; gss[gg] += ss; }
-        uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)opix * a.Co + n0 + c0);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        for (int i = 0; i < C3_MAXR; ++i) {
+          const int j = rsub + 16 * i;
+          if (j < a.Lp) *reinterpret_cast<uint4*>(Ps + (j >> 3) * 1024 + (j & 7) * 128 + ((chunk ^ (j & 7)) << 4)) = v[i];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) c3_mbar_arrive(&pfull[ps]);
       }
     }
-    // GroupNorm sums, segmented by image: a warp's 32 consecutive raster positions touch at most 3 images
-    const int ngroups = (BN + a.Cg - 1) / a.Cg;
-    const int id_lo = __shfl_sync(0xffffffffu, n_img, 0), id_hi = __shfl_sync(0xffffffffu, n_img, 31);
-    for (int id = id_lo; id <= id_hi; ++id) {
-      for (int g = 0; g < ngroups; ++g) {
+  } else if (warp < 4) {
+    // ------------------------------- epilogue ---------------------------------------
+    bool ok = true;
+    int ac = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ac) {
+      const int as = ac & 1;
+      const int q0 = (tile / n_tiles_n) * 128, n0 = (tile % n_tiles_n) * BN;
+      ok = ok && c3_mbar_wait(&afull[as], (uint32_t)((ac >> 1) & 1), a.error);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = warp * 32 + lane;
+      const int q = q0 + row;
+      bool valid = false; int n_img = a.N - 1; int opix = 0;
+      if (q < (int)a.Q) {
+        n_img = q / per_img; const int rem = q - n_img * per_img;
+        const int hrow = rem / a.P, wcol = rem - hrow * a.P;
+        valid = wcol < a.W && hrow < a.H;
+        opix = (n_img * a.H + hrow) * a.W + wcol;
+      }
+      valid = valid && ok;
+      constexpr int MAXG = 4;
+      float gs[MAXG], gss[MAXG];
+#pragma unroll
+      for (int g = 0; g < MAXG; ++g) { gs[g] = 0.f; gss[g] = 0.f; }
+      const int g_first = n0 / a.Cg;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        c3_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c0), v);
         float s = 0.f, ss = 0.f;
+        uint32_t pk[8];
 #pragma unroll
-        for (int gg = 0; gg < MAXG; ++gg) if (gg == g && n_img == id && valid) { s = gs[gg]; ss = gss[gg]; }
-        s = warp_sum(s); ss = warp_sum(ss);
-        if (lane == 0 && (s != 0.f || ss != 0.f)) {
-          float* st = a.stats + ((size_t)id * 4 + g_first + g) * 2;
-          atomicAdd(st, s); atomicAdd(st + 1, ss);
+        for (int j = 0; j < 8; ++j) {
+          const float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+          s += f0 + f1; ss += f0 * f0 + f1 * f1;
+          pk[j] = F::pack(f0, f1);
+        }
+        if (valid) {
+          const int g = (n0 + c0) / a.Cg - g_first;
+#pragma unroll
+          for (int gg = 0; gg < MAXG; ++gg) if (gg == g) { gs[gg] += s; gss[gg] += ss; }
+          uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)opix * a.Co + n0 + c0);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      // accumulator drained: hand the TMEM stage back before the (slower) statistics
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) c3_mbar_arrive(&aempty[as]);
+      // GroupNorm sums, segmented by image: a warp's 32 consecutive raster positions touch at most 3 images
+      const int ngroups = (BN + a.Cg - 1) / a.Cg;
+      const int id_lo = __shfl_sync(0xffffffffu, n_img, 0), id_hi = __shfl_sync(0xffffffffu, n_img, 31);
+      for (int id = id_lo; id <= id_hi; ++id) {
+        for (int g = 0; g < ngroups; ++g) {
+          float s = 0.f, ss = 0.f;
+#pragma unroll
+          for (int gg = 0; gg < MAXG; ++gg) if (gg == g && n_img == id && valid) { s = gs[gg]; ss = gss[gg]; }
+          s = warp_sum(s); ss = warp_sum(ss);
+          if (lane == 0 && (s != 0.f || ss != 0.f)) {
+            float* st = a.stats + ((size_t)id * 4 + g_first + g) * 2;
+            atomicAdd(st, s); atomicAdd(st + 1, ss);
+          }
         }
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else if (warp == 4) {
+  } else if (warp == 8) {
     // ------------------------------- MMA issuer -----------------------------------
     const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
     bool ok = true;
-    int it = 0;
-    for (int cb = 0; cb < a.cblocks && ok; ++cb) {
-      const int ps = cb & 1;
-      ok = c3_mbar_wait(&pfull[ps], (uint32_t)((cb >> 1) & 1), a.error);
+    int it = 0, pc = 0, ac = 0;
+    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++ac) {
+      const int as = ac & 1;
+      ok = c3_mbar_wait(&aempty[as], (uint32_t)((ac >> 1) & 1) ^ 1u, a.error);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t pbase = c3_smem(sP + ps * a.patch_bytes);
-      for (int tap = 0; tap < taps && ok; ++tap, ++it) {
-        const int sb = it % BSTAGES;
-        ok = c3_mbar_wait(&bfull[sb], (uint32_t)((it / BSTAGES) & 1), a.error);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      for (int cb = 0; cb < a.cblocks && ok; ++cb, ++pc) {
+        const int ps = pc & 1;
+        ok = c3_mbar_wait(&pfull[ps], (uint32_t)((pc >> 1) & 1), a.error);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0 && ok) {
-          const int r = tap / 3, s = tap - 3 * r;
-          const uint32_t off = (uint32_t)(r * a.P + s);               // window shift in patch rows
-          const uint64_t ad = c3_desc(pbase + off * 128u, a.base_offset_mode ? off : 0u);
-          const uint64_t bd = c3_desc(c3_smem(sB + sb * B_STAGE), 0u);
+        const uint32_t pbase = c3_smem(sP + ps * a.patch_bytes);
+        for (int tap = 0; tap < 9 && ok; ++tap, ++it) {
+          const int sb = it % BSTAGES;
+          ok = c3_mbar_wait(&bfull[sb], (uint32_t)((it / BSTAGES) & 1), a.error);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          if (lane == 0 && ok) {
+            const int r = tap / 3, s = tap - 3 * r;
+            const uint32_t off = (uint32_t)(r * a.P + s);             // window shift in patch rows
+            const uint64_t ad = c3_desc(pbase + off * 128u, a.base_offset_mode ? off : 0u);
+            const uint64_t bd = c3_desc(c3_smem(sB + sb * B_STAGE), 0u);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) c3_mma(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((it | k) != 0));
-          c3_commit(&bempty[sb]);
+            for (int k = 0; k < 4; ++k) c3_mma(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((cb | tap | k) != 0));
+            c3_commit(&bempty[sb]);
+          }
+          __syncwarp();
         }
+        if (lane == 0 && ok) c3_commit(&pempty[ps]);
         __syncwarp();
       }
-      if (lane == 0 && ok) c3_commit(&pempty[ps]);
+      if (lane == 0) { if (ok) c3_commit(&afull[as]); else c3_mbar_arrive(&afull[as]); }
       __syncwarp();
     }
-    if (lane == 0) { if (ok) c3_commit(tmem_full); else c3_mbar_arrive(tmem_full); }
   } else {
     // ------------------------------- weight TMA issuer ----------------------------
     if (lane == 0) {
       bool ok = true;
       int it = 0;
-      for (int cb = 0; cb < a.cblocks && ok; ++cb) {
-        for (int tap = 0; tap < taps && ok; ++tap, ++it) {
-          const int sb = it % BSTAGES;
-          ok = c3_mbar_wait(&bempty[sb], (uint32_t)((it / BSTAGES) & 1) ^ 1u, a.error);
-          if (!ok) break;
-          c3_mbar_expect_tx(&bfull[sb], (uint32_t)B_STAGE);
-          c3_tma_2d(sB + sb * B_STAGE, &wmap, tap * a.Ci + cb * 64, n0, &bfull[sb]);
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles_n) * BN;
+        for (int cb = 0; cb < a.cblocks && ok; ++cb) {
+          for (int tap = 0; tap < 9 && ok; ++tap, ++it) {
+            const int sb = it % BSTAGES;
+            ok = c3_mbar_wait(&bempty[sb], (uint32_t)((it / BSTAGES) & 1) ^ 1u, a.error);
+            if (!ok) break;
+            c3_mbar_expect_tx(&bfull[sb], (uint32_t)B_STAGE);
+            c3_tma_2d(sB + sb * B_STAGE, &wmap, tap * a.Ci + cb * 64, n0, &bfull[sb]);
+          }
         }
       }
     }
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
   }
 }
 
@@ -303,7 +326,10 @@ static int launch_conv3(const CUtensorMap& map, const Conv3Args& a, cudaStream_t
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv3x3_tc)");
     configured = smem;
   }
-  dim3 grid((unsigned)((a.Q + 127) / 128), a.Co / BN);
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const long long tiles = ((a.Q + 127) / 128) * (a.Co / BN);
+  const int grid = (int)(tiles < 2ll * sms ? tiles : 2ll * sms);          // persistent: 2 CTAs per SM walk the tile list
   kern<<<grid, C3_THREADS, smem, st>>>(map, a);
   return check_launch("conv3x3_tc_kernel");
 }
