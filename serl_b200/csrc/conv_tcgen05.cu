@@ -14,6 +14,7 @@
 // The 7x7/2 stem on 3 channels is rewritten exactly as a 4x4/1 convolution over a 2x2 space-to-depth image with
 // 12 channels (zero-extended 8x8 kernel), which gives K = 4 kernel rows x (4 taps x 12 ch = 48, padded to 64).
 // bf16 operands, fp32 accumulation: the 1e-2 tolerance build (north_star); the fp32 build is trunk_fp32.cu.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -25,7 +26,7 @@ namespace serl {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;
 constexpr int TC_A_STAGE = TC_BM * TC_BK * 2;          // 16 KiB
-constexpr int TC_THREADS = 160;
+constexpr int TC_THREADS = 320;
 
 struct ConvTcArgs {
   const uint16_t* x;             // 16-bit elements (bf16 or fp16, see the F template parameter)
@@ -103,8 +104,22 @@ __device__ inline uint32_t affine_relu_x2(uint32_t u, float a0, float b0, float 
   return F::pack(fmaxf(fmaf(f.x, a0, b0), 0.f), fmaxf(fmaf(f.y, a1, b1), 0.f));
 }
 
+__device__ inline void tc_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ inline void tc_tma_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+// Persistent, role-decoupled implicit-GEMM convolution (im2col gather).  320 threads:
+//   warps 0-3  epilogue (TMEM -> registers, GroupNorm partial sums, 16-bit pack, NHWC store)
+//   warps 4-7  A-operand producers (gather 128 pixels x 64 K into 128B-swizzled smem, optional GN+ReLU on the operand)
+//   warp 8     tcgen05.mma issuer       warp 9   TMA issuer for the weight (B) tile of every k-block
+// A/B share one stage ring (full = 4 producer-warp arrivals + 1 expect_tx arrival, empty = tcgen05.commit); TMEM holds
+// two accumulators (afull / aempty) so tile i+1's mainloop overlaps tile i's epilogue.
 template <class F, int BN, int STAGES, bool kStem, bool kAffine>
-__global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const ConvTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_STAGE = BN * TC_BK * 2;
@@ -112,179 +127,205 @@ __global__ void __launch_bounds__(TC_THREADS) conv_tc_kernel(const ConvTcArgs a)
   uint8_t* sB = smem + STAGES * TC_A_STAGE;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
   uint64_t* empty = full + STAGES;
-  uint64_t* tmem_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* afull = empty + STAGES;
+  uint64_t* aempty = afull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BM, n0 = blockIdx.y * BN;
+  const int n_tiles_n = a.Co / BN;
+  const int n_tiles = ceil_div(a.M, TC_BM) * n_tiles_n;
+  const int HoWo = a.Ho * a.Wo;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { tc_mbar_init(&full[s], 4); tc_mbar_init(&empty[s], 1); }
-    tc_mbar_init(tmem_full, 1);
+    for (int s = 0; s < STAGES; ++s) { tc_mbar_init(&full[s], 5); tc_mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc_mbar_init(&afull[s], 1); tc_mbar_init(&aempty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  if (warp == 9 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ------------------------------- producers -------------------------------
-    const int tid = threadIdx.x;
+  if (warp >= 4 && warp < 8) {
+    // ------------------------------- A producers -------------------------------
+    const int tid = threadIdx.x - 128;
     const int chunk = tid & 7, rsub = tid >> 3;
-    const int HoWo = a.Ho * a.Wo;
-    int rn[8], rh[8], rw[8], rbase[8];                      // image, top-left input coords, element offset of (rh, rw, ch 0)
-    {
-      const int gm0 = m0 + rsub;
-      int n = gm0 / HoWo; int rem = gm0 - n * HoWo; int ho = rem / a.Wo; int wo = rem - ho * a.Wo;
-      const int cpp = kStem ? 12 : a.Ci;                    // channels per input pixel
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {                         // rows rsub + 16 i: walk the output raster instead of dividing
-        if (m0 + rsub + 16 * i < a.M) {
-          rn[i] = n; rh[i] = ho * a.stride - a.pad; rw[i] = wo * a.stride - a.pad;
-          rbase[i] = ((n * a.Hi + rh[i]) * a.Wi + rw[i]) * cpp;
-        } else { rn[i] = -1; rh[i] = 0; rw[i] = 0; rbase[i] = 0; }
-        wo += 16;
-        while (wo >= a.Wo) { wo -= a.Wo; ++ho; }
-        while (ho >= a.Ho) { ho -= a.Ho; ++n; }
-      }
-    }
-    int tap_r = 0, tap_s = 0, cblk = 0;                     // k-block -> (kernel row, kernel col, channel block), advanced incrementally
+    const int cpp = kStem ? 12 : a.Ci;                      // channels per input pixel
     bool ok = true;
-    const size_t Kp = (size_t)a.num_kb * TC_BK;
-    for (int kb = 0; kb < a.num_kb && ok; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-      const int r = tap_r, sx = tap_s, c0 = cblk * TC_BK;
-      const int tap_off = kStem ? kb * a.Wi * 12 : (r * a.Wi + sx) * a.Ci + c0;
-      if (!kStem) { if (++cblk == a.cblocks) { cblk = 0; if (++tap_s == a.kw) { tap_s = 0; ++tap_r; } } }
-      // ---- phase 1: issue EVERY global load of this k-block before anything consumes one (memory-level parallelism:
-      //      the gather is latency-bound, so all 8 A rows + the B rows of a thread must be in flight together)
-      uint4 va[8], vb[BN / 16];
-      bool inb[8];
+    int it = 0;                                             // k-blocks produced so far (ring position)
+    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+      const int m0 = (tile / n_tiles_n) * TC_BM;
+      int rn[8], rh[8], rw[8], rbase[8];                    // image, top-left input coords, element offset of (rh, rw, ch 0)
+      {
+        const int gm0 = m0 + rsub;
+        int n = gm0 / HoWo; const int rem = gm0 - n * HoWo; int ho = rem / a.Wo; int wo = rem - ho * a.Wo;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        va[i] = make_uint4(0u, 0u, 0u, 0u);
-        inb[i] = false;
-        if (rn[i] >= 0) {
-          if (kStem) {
-            // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 12 ch = 48 contiguous 16-bit values (96 B)
-            if (chunk < 6) {
-              const uint16_t* src = a.x + (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8);
-              const uint2 lo = *reinterpret_cast<const uint2*>(src), hi = *reinterpret_cast<const uint2*>(src + 4);
-              va[i] = make_uint4(lo.x, lo.y, hi.x, hi.y);
-            }
-          } else {
-            const int hi_ = rh[i] + r, wi_ = rw[i] + sx;
-            if (hi_ >= 0 && hi_ < a.Hi && wi_ >= 0 && wi_ < a.Wi) {
-              inb[i] = true;
-              va[i] = *reinterpret_cast<const uint4*>(a.x + (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8));
-            }
-          }
+        for (int i = 0; i < 8; ++i) {                       // rows rsub + 16 i: walk the output raster instead of dividing
+          if (m0 + rsub + 16 * i < a.M) {
+            rn[i] = n; rh[i] = ho * a.stride - a.pad; rw[i] = wo * a.stride - a.pad;
+            rbase[i] = ((n * a.Hi + rh[i]) * a.Wi + rw[i]) * cpp;
+          } else { rn[i] = -1; rh[i] = 0; rw[i] = 0; rbase[i] = 0; }
+          wo += 16;
+          while (wo >= a.Wo) { wo -= a.Wo; ++ho; }
+          while (ho >= a.Ho) { ho -= a.Ho; ++n; }
         }
       }
-#pragma unroll
-      for (int j = 0; j < BN / 16; ++j) {
-        const int idx = tid + 128 * j, brow = idx >> 3, bch = idx & 7;
-        vb[j] = *reinterpret_cast<const uint4*>(a.w + (size_t)(n0 + brow) * Kp + (size_t)kb * TC_BK + bch * 8);
-      }
-      // ---- phase 2: previous GroupNorm + ReLU on the operand (zero padding stays zero) ----
-      if (kAffine) {
-        const int c = c0 + chunk * 8;
+      int tap_r = 0, tap_s = 0, cblk = 0;                   // k-block -> (kernel row, kernel col, channel block)
+      for (int kb = 0; kb < a.num_kb && ok; ++kb, ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const int r = tap_r, sx = tap_s, c0 = cblk * TC_BK;
+        const int tap_off = kStem ? kb * a.Wi * 12 : (r * a.Wi + sx) * a.Ci + c0;
+        if (!kStem) { if (++cblk == a.cblocks) { cblk = 0; if (++tap_s == a.kw) { tap_s = 0; ++tap_r; } } }
+        // phase 1: every global load of this k-block is issued before anything consumes one
+        uint4 va[8];
+        bool inb[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          if (inb[i]) {
-            const float4 a0 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c);
-            const float4 a1 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c + 4);
-            const float4 b0 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c);
-            const float4 b1 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c + 4);
-            va[i].x = affine_relu_x2<F>(va[i].x, a0.x, b0.x, a0.y, b0.y);
-            va[i].y = affine_relu_x2<F>(va[i].y, a0.z, b0.z, a0.w, b0.w);
-            va[i].z = affine_relu_x2<F>(va[i].z, a1.x, b1.x, a1.y, b1.y);
-            va[i].w = affine_relu_x2<F>(va[i].w, a1.z, b1.z, a1.w, b1.w);
+          va[i] = make_uint4(0u, 0u, 0u, 0u);
+          inb[i] = false;
+          if (rn[i] >= 0) {
+            if (kStem) {
+              // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 12 ch = 48 contiguous 16-bit values (96 B)
+              if (chunk < 6) {
+                const uint16_t* src = a.x + (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8);
+                const uint2 lo = *reinterpret_cast<const uint2*>(src), hi = *reinterpret_cast<const uint2*>(src + 4);
+                va[i] = make_uint4(lo.x, lo.y, hi.x, hi.y);
+              }
+            } else {
+              const int hi_ = rh[i] + r, wi_ = rw[i] + sx;
+              if (hi_ >= 0 && hi_ < a.Hi && wi_ >= 0 && wi_ < a.Wi) {
+                inb[i] = true;
+                va[i] = *reinterpret_cast<const uint4*>(a.x + (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8));
+              }
+            }
           }
         }
-      }
-      // ---- phase 3: the stage must be free only now ----
-      ok = tc_mbar_wait(&empty[s], ph ^ 1u, a.error);
-      uint8_t* As = sA + s * TC_A_STAGE;
+        // phase 2: previous GroupNorm + ReLU on the operand (zero padding stays zero)
+        if (kAffine) {
+          const int c = c0 + chunk * 8;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int row = rsub + 16 * i;
-        *reinterpret_cast<uint4*>(As + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4)) = va[i];
-      }
-      uint8_t* Bs = sB + s * B_STAGE;
-#pragma unroll
-      for (int j = 0; j < BN / 16; ++j) {
-        const int idx = tid + 128 * j, brow = idx >> 3, bch = idx & 7;
-        *reinterpret_cast<uint4*>(Bs + (brow >> 3) * 1024 + (brow & 7) * 128 + ((bch ^ (brow & 7)) << 4)) = vb[j];
-      }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy stores -> visible to the tensor core
-      __syncwarp();
-      if (lane == 0) tc_mbar_arrive(&full[s]);
-    }
-    // ------------------------------- epilogue --------------------------------
-    ok = ok && tc_mbar_wait(tmem_full, 0u, a.error);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = warp * 32 + lane, gm = m0 + row;
-    const bool valid = gm < a.M;
-    const int n_img = valid ? gm / HoWo : 0;
-    const int seg = HoWo < 32 ? HoWo : 32;                  // lanes sharing one image (power of two >= 16)
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
-      tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      float s = 0.f, ss = 0.f;
-      uint32_t pk[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
-        s += f0 + f1; ss += f0 * f0 + f1 * f1;
-        pk[j] = F::pack(f0, f1);
-      }
-      if (!valid || !ok) { s = 0.f; ss = 0.f; }
-      for (int o = seg >> 1; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
-      if (valid && ok) {
-        if ((lane & (seg - 1)) == 0) {
-          float* st = a.stats + ((size_t)n_img * 4 + (n0 + c0) / a.Cg) * 2;
-          atomicAdd(st, s); atomicAdd(st + 1, ss);
+          for (int i = 0; i < 8; ++i) {
+            if (inb[i]) {
+              const float4 a0 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c);
+              const float4 a1 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c + 4);
+              const float4 b0 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c);
+              const float4 b1 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c + 4);
+              va[i].x = affine_relu_x2<F>(va[i].x, a0.x, b0.x, a0.y, b0.y);
+              va[i].y = affine_relu_x2<F>(va[i].y, a0.z, b0.z, a0.w, b0.w);
+              va[i].z = affine_relu_x2<F>(va[i].z, a1.x, b1.x, a1.y, b1.y);
+              va[i].w = affine_relu_x2<F>(va[i].w, a1.z, b1.z, a1.w, b1.w);
+            }
+          }
         }
-        uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)gm * a.Co + n0 + c0);
-        dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        // phase 3: the stage must be free only now
+        ok = tc_mbar_wait(&empty[s], ph ^ 1u, a.error);
+        uint8_t* As = sA + s * TC_A_STAGE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rsub + 16 * i;
+          *reinterpret_cast<uint4*>(As + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4)) = va[i];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&full[s]);
       }
     }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  } else {
+  } else if (warp < 4) {
+    // ------------------------------- epilogue --------------------------------
+    bool ok = true;
+    int ac = 0;
+    const int seg = HoWo < 32 ? HoWo : 32;                  // lanes sharing one image (power of two >= 16)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ac) {
+      const int as = ac & 1;
+      const int m0 = (tile / n_tiles_n) * TC_BM, n0 = (tile % n_tiles_n) * BN;
+      ok = ok && tc_mbar_wait(&afull[as], (uint32_t)((ac >> 1) & 1), a.error);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int row = warp * 32 + lane, gm = m0 + row;
+      const bool valid = gm < a.M && ok;
+      const int n_img = valid ? gm / HoWo : 0;
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        float s = 0.f, ss = 0.f;
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+          s += f0 + f1; ss += f0 * f0 + f1 * f1;
+          pk[j] = F::pack(f0, f1);
+        }
+        if (!valid) { s = 0.f; ss = 0.f; }
+        for (int o = seg >> 1; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+        if (valid) {
+          if ((lane & (seg - 1)) == 0) {
+            float* st = a.stats + ((size_t)n_img * 4 + (n0 + c0) / a.Cg) * 2;
+            atomicAdd(st, s); atomicAdd(st + 1, ss);
+          }
+          uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)gm * a.Co + n0 + c0);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&aempty[as]);
+    }
+  } else if (warp == 8) {
     // ------------------------------- MMA issuer ------------------------------
-    // instruction descriptor: D=F32 (bit 4), A=B=BF16 (bits 7, 10), K-major both, N>>3 at bit 17, M>>4 at bit 24
+    // instruction descriptor: D=F32 (bit 4), A/B format (bits 7, 10), K-major both, N>>3 at bit 17, M>>4 at bit 24
     const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
     bool ok = true;
-    for (int kb = 0; kb < a.num_kb && ok; ++kb) {
-      const int s = kb % STAGES;
-      const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-      ok = tc_mbar_wait(&full[s], ph, a.error);
+    int it = 0, ac = 0;
+    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++ac) {
+      const int as = ac & 1;
+      ok = tc_mbar_wait(&aempty[as], (uint32_t)((ac >> 1) & 1) ^ 1u, a.error);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (lane == 0 && ok) {
-        const uint64_t ad = make_smem_desc(smem_u32(sA + s * TC_A_STAGE));
-        const uint64_t bd = make_smem_desc(smem_u32(sB + s * B_STAGE));
+      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+      for (int kb = 0; kb < a.num_kb && ok; ++kb, ++it) {
+        const int s = it % STAGES;
+        ok = tc_mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u, a.error);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (lane == 0 && ok) {
+          const uint64_t ad = make_smem_desc(smem_u32(sA + s * TC_A_STAGE));
+          const uint64_t bd = make_smem_desc(smem_u32(sB + s * B_STAGE));
 #pragma unroll
-        for (int k = 0; k < TC_BK / 16; ++k)                 // UMMA_K = 16 bf16 = 32 B: advance the start address by 2 (x16 B)
-          tc_mma_bf16(tmem_base, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
-        tc_commit(&empty[s]);                                // stage reusable once these MMAs retire
-        if (kb == a.num_kb - 1) tc_commit(tmem_full);        // accumulator complete
+          for (int k = 0; k < TC_BK / 16; ++k)               // UMMA_K = 16 elements = 32 B: advance the start address by 2 (x16 B)
+            tc_mma_bf16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          tc_commit(&empty[s]);                              // stage reusable once these MMAs retire
+        }
+        __syncwarp();
       }
+      if (lane == 0) { if (ok) tc_commit(&afull[as]); else tc_mbar_arrive(&afull[as]); }
       __syncwarp();
     }
-    if (!ok && lane == 0) tc_mbar_arrive(tmem_full);         // let the epilogue warps out after a flagged timeout
+  } else {
+    // ------------------------------- weight TMA issuer ------------------------
+    if (lane == 0) {
+      bool ok = true;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+        const int n0 = (tile % n_tiles_n) * BN;
+        for (int kb = 0; kb < a.num_kb && ok; ++kb, ++it) {
+          const int s = it % STAGES;
+          ok = tc_mbar_wait(&empty[s], ((uint32_t)(it / STAGES) & 1u) ^ 1u, a.error);
+          if (!ok) break;
+          tc_mbar_expect_tx(&full[s], (uint32_t)B_STAGE);
+          tc_tma_2d(sB + s * B_STAGE, &wmap, kb * TC_BK, n0, &full[s]);
+        }
+      }
+    }
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
   }
 }
 
@@ -412,17 +453,46 @@ __global__ void block_combine_kernel(const uint16_t* __restrict__ y2, const floa
   }
 }
 
+typedef CUresult (*TcEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TcEncodeTiledFn tc_get_encode() {
+  static TcEncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<TcEncodeTiledFn>(p);
+  }
+  return fn;
+}
+
 template <class F, int BN, int STAGES, bool kStem, bool kAffine>
-static int launch_conv_tc(const ConvTcArgs& a, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (TC_A_STAGE + BN * TC_BK * 2) + 1024 + 128;
+static int launch_conv_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
+  constexpr size_t smem = (size_t)STAGES * (TC_A_STAGE + BN * TC_BK * 2) + 1024 + 256;
   auto kern = conv_tc_kernel<F, BN, STAGES, kStem, kAffine>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv_tc)");
     configured = true;
   }
-  dim3 grid(ceil_div(a.M, TC_BM), a.Co / BN);
-  kern<<<grid, TC_THREADS, smem, st>>>(a);
+  TcEncodeTiledFn enc = tc_get_encode();
+  if (!enc) { set_last_error("serl_conv2d_tc_h16: cuTensorMapEncodeTiled unavailable"); return SERL_ERR_CUDA; }
+  CUtensorMap map;
+  const cuuint64_t Kp = (cuuint64_t)a.num_kb * TC_BK;
+  const cuuint64_t gdim[2] = {Kp, (cuuint64_t)a.Co};
+  const cuuint64_t gstr[1] = {Kp * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(&map, fmt == SERL_FMT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<uint16_t*>(a.w), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("serl_conv2d_tc_h16: cuTensorMapEncodeTiled failed (%d)", (int)r); return SERL_ERR_CUDA; }
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int tiles = ceil_div(a.M, TC_BM) * (a.Co / BN);
+  const int grid = tiles < 2 * sms ? tiles : 2 * sms;                 // persistent: 2 CTAs per SM walk the tile list
+  kern<<<grid, TC_THREADS, smem, st>>>(map, a);
   return check_launch("conv_tc_kernel");
 }
 
@@ -435,12 +505,12 @@ template <class F>
 static int conv_tc_dispatch(const serl_conv_tc_desc* d, ConvTcArgs& a, cudaStream_t st) {
   if (d->stem) {
     a.num_kb = 4; a.cblocks = 1;
-    return launch_conv_tc<F, 64, 4, true, false>(a, st);
+    return launch_conv_tc<F, 64, 4, true, false>(a, d->fmt, st);
   }
   a.cblocks = d->Ci / 64; a.num_kb = d->kh * d->kw * a.cblocks;
   const bool aff = d->in_a != nullptr;
-  if (d->Co == 64) return aff ? launch_conv_tc<F, 64, 4, false, true>(a, st) : launch_conv_tc<F, 64, 4, false, false>(a, st);
-  return aff ? launch_conv_tc<F, 128, 3, false, true>(a, st) : launch_conv_tc<F, 128, 3, false, false>(a, st);
+  if (d->Co == 64) return aff ? launch_conv_tc<F, 64, 4, false, true>(a, d->fmt, st) : launch_conv_tc<F, 64, 4, false, false>(a, d->fmt, st);
+  return aff ? launch_conv_tc<F, 128, 3, false, true>(a, d->fmt, st) : launch_conv_tc<F, 128, 3, false, false>(a, d->fmt, st);
 }
 
 extern "C" int serl_trunk_stem_prep_h16(const uint8_t* x, void* xs, int N, int H, int W, int fmt, void* stream) {
