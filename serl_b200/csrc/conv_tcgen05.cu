@@ -114,9 +114,9 @@ __device__ inline void tc_tma_2d(void* smem_dst, const CUtensorMap* map, int c0,
 
 // Persistent, role-decoupled implicit-GEMM convolution (im2col gather).  320 threads:
 //   warps 0-3  epilogue (TMEM -> registers, GroupNorm partial sums, 16-bit pack, NHWC store)
-//   warps 4-7  A-operand producers (gather 128 pixels x 64 K into 128B-swizzled smem, optional GN+ReLU on the operand)
+//   warps 4-7  A-operand producers (cp.async gather of 128 pixels x 64 K into 128B-swizzled smem, zero-fill at the padding)
 //   warp 8     tcgen05.mma issuer       warp 9   TMA issuer for the weight (B) tile of every k-block
-// A/B share one stage ring (full = 4 producer-warp arrivals + 1 expect_tx arrival, empty = tcgen05.commit); TMEM holds
+// A/B share one stage ring (full = 128 deferred cp.async arrivals + 1 expect_tx arrival, empty = tcgen05.commit); TMEM holds
 // two accumulators (afull / aempty) so tile i+1's mainloop overlaps tile i's epilogue.
 template <class F, int BN, int STAGES, bool kStem, bool kAffine>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const ConvTcArgs a) {
@@ -137,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
   const int HoWo = a.Ho * a.Wo;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { tc_mbar_init(&full[s], 5); tc_mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { tc_mbar_init(&full[s], 129); tc_mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { tc_mbar_init(&afull[s], 1); tc_mbar_init(&aempty[s], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -153,6 +153,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
 
   if (warp >= 4 && warp < 8) {
     // ------------------------------- A producers -------------------------------
+    // cp.async (LDGSTS) straight into the swizzled stage: no register staging, so a producer never waits for its own loads;
+    // it only waits for a free stage, and up to STAGES k-blocks of gathers are in flight per CTA.  Completion is signalled
+    // by cp.async.mbarrier.arrive.noinc (one deferred arrival per producer thread).
     const int tid = threadIdx.x - 128;
     const int chunk = tid & 7, rsub = tid >> 3;
     const int cpp = kStem ? 12 : a.Ci;                      // channels per input pixel
@@ -160,16 +163,16 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     int it = 0;                                             // k-blocks produced so far (ring position)
     for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
       const int m0 = (tile / n_tiles_n) * TC_BM;
-      int rn[8], rh[8], rw[8], rbase[8];                    // image, top-left input coords, element offset of (rh, rw, ch 0)
+      int rh[8], rw[8], rbase[8];                           // top-left input coords (rh = -100000 for rows past M), element offset
       {
         const int gm0 = m0 + rsub;
         int n = gm0 / HoWo; const int rem = gm0 - n * HoWo; int ho = rem / a.Wo; int wo = rem - ho * a.Wo;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {                       // rows rsub + 16 i: walk the output raster instead of dividing
           if (m0 + rsub + 16 * i < a.M) {
-            rn[i] = n; rh[i] = ho * a.stride - a.pad; rw[i] = wo * a.stride - a.pad;
+            rh[i] = ho * a.stride - a.pad; rw[i] = wo * a.stride - a.pad;
             rbase[i] = ((n * a.Hi + rh[i]) * a.Wi + rw[i]) * cpp;
-          } else { rn[i] = -1; rh[i] = 0; rw[i] = 0; rbase[i] = 0; }
+          } else { rh[i] = -100000; rw[i] = 0; rbase[i] = 0; }
           wo += 16;
           while (wo >= a.Wo) { wo -= a.Wo; ++ho; }
           while (ho >= a.Ho) { ho -= a.Ho; ++n; }
@@ -179,63 +182,33 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
       for (int kb = 0; kb < a.num_kb && ok; ++kb, ++it) {
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        const int r = tap_r, sx = tap_s, c0 = cblk * TC_BK;
-        const int tap_off = kStem ? kb * a.Wi * 12 : (r * a.Wi + sx) * a.Ci + c0;
+        const int r = tap_r, sx = tap_s;
+        const int tap_off = kStem ? kb * a.Wi * 12 : (r * a.Wi + sx) * a.Ci + cblk * TC_BK;
         if (!kStem) { if (++cblk == a.cblocks) { cblk = 0; if (++tap_s == a.kw) { tap_s = 0; ++tap_r; } } }
-        // phase 1: every global load of this k-block is issued before anything consumes one
-        uint4 va[8];
-        bool inb[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          va[i] = make_uint4(0u, 0u, 0u, 0u);
-          inb[i] = false;
-          if (rn[i] >= 0) {
-            if (kStem) {
-              // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 12 ch = 48 contiguous 16-bit values (96 B)
-              if (chunk < 6) {
-                const uint16_t* src = a.x + (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8);
-                const uint2 lo = *reinterpret_cast<const uint2*>(src), hi = *reinterpret_cast<const uint2*>(src + 4);
-                va[i] = make_uint4(lo.x, lo.y, hi.x, hi.y);
-              }
-            } else {
-              const int hi_ = rh[i] + r, wi_ = rw[i] + sx;
-              if (hi_ >= 0 && hi_ < a.Hi && wi_ >= 0 && wi_ < a.Wi) {
-                inb[i] = true;
-                va[i] = *reinterpret_cast<const uint4*>(a.x + (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8));
-              }
-            }
-          }
-        }
-        // phase 2: previous GroupNorm + ReLU on the operand (zero padding stays zero)
-        if (kAffine) {
-          const int c = c0 + chunk * 8;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (inb[i]) {
-              const float4 a0 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c);
-              const float4 a1 = *reinterpret_cast<const float4*>(a.in_a + (size_t)rn[i] * a.Ci + c + 4);
-              const float4 b0 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c);
-              const float4 b1 = *reinterpret_cast<const float4*>(a.in_b + (size_t)rn[i] * a.Ci + c + 4);
-              va[i].x = affine_relu_x2<F>(va[i].x, a0.x, b0.x, a0.y, b0.y);
-              va[i].y = affine_relu_x2<F>(va[i].y, a0.z, b0.z, a0.w, b0.w);
-              va[i].z = affine_relu_x2<F>(va[i].z, a1.x, b1.x, a1.y, b1.y);
-              va[i].w = affine_relu_x2<F>(va[i].w, a1.z, b1.z, a1.w, b1.w);
-            }
-          }
-        }
-        // phase 3: the stage must be free only now
         ok = tc_mbar_wait(&empty[s], ph ^ 1u, a.error);
-        uint8_t* As = sA + s * TC_A_STAGE;
+        const uint32_t As = smem_u32(sA + s * TC_A_STAGE);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int row = rsub + 16 * i;
-          *reinterpret_cast<uint4*>(As + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4)) = va[i];
+          const uint32_t dst = As + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4);
+          if (kStem) {
+            // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 12 ch = 48 contiguous 16-bit values (96 B, 8 B aligned)
+            const bool inb = rh[i] > -100000 && chunk < 6;
+            const uint16_t* src = a.x + (inb ? (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8) : 0);
+            const uint32_t n = inb ? 8u : 0u;               // src-size 0 -> zero fill
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8), "l"(src + 4), "r"(n) : "memory");
+          } else {
+            const int hi_ = rh[i] + r, wi_ = rw[i] + sx;
+            const bool inb = hi_ >= 0 && hi_ < a.Hi && wi_ >= 0 && wi_ < a.Wi;
+            const uint16_t* src = a.x + (inb ? (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8) : 0);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(inb ? 16u : 0u) : "memory");
+          }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
-        __syncwarp();
-        if (lane == 0) tc_mbar_arrive(&full[s]);
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[s])) : "memory");
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp < 4) {
     // ------------------------------- epilogue --------------------------------
     bool ok = true;
@@ -291,6 +264,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
       for (int kb = 0; kb < a.num_kb && ok; ++kb, ++it) {
         const int s = it % STAGES;
         ok = tc_mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u, a.error);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (lane == 0 && ok) {
           const uint64_t ad = make_smem_desc(smem_u32(sA + s * TC_A_STAGE));
@@ -508,9 +482,9 @@ static int conv_tc_dispatch(const serl_conv_tc_desc* d, ConvTcArgs& a, cudaStrea
     return launch_conv_tc<F, 64, 4, true, false>(a, d->fmt, st);
   }
   a.cblocks = d->Ci / 64; a.num_kb = d->kh * d->kw * a.cblocks;
-  const bool aff = d->in_a != nullptr;
-  if (d->Co == 64) return aff ? launch_conv_tc<F, 64, 4, false, true>(a, d->fmt, st) : launch_conv_tc<F, 64, 4, false, false>(a, d->fmt, st);
-  return aff ? launch_conv_tc<F, 128, 3, false, true>(a, d->fmt, st) : launch_conv_tc<F, 128, 3, false, false>(a, d->fmt, st);
+  if (d->in_a) { set_last_error("serl_conv2d_tc_h16: operand transform is not supported (materialise GroupNorm+ReLU with serl_affine_relu_h16)"); return SERL_ERR_UNSUPPORTED; }
+  if (d->Co == 64) return launch_conv_tc<F, 64, 4, false, false>(a, d->fmt, st);
+  return launch_conv_tc<F, 128, 3, false, false>(a, d->fmt, st);
 }
 
 extern "C" int serl_trunk_stem_prep_h16(const uint8_t* x, void* xs, int N, int H, int W, int fmt, void* stream) {

@@ -20,10 +20,6 @@ def _s():
     return L.stream_ptr()
 
 
-# Applying the previous GroupNorm+ReLU inside the operand gather costs 4 coefficient loads per gathered row; until the
-# coefficients are staged in shared memory the materialised variant is faster (profiles/r01_*).
-FUSE_OPERAND_GROUPNORM = False
-
 # Stride-1 3x3 convs: "shifted window" kernel (conv3x3_tcgen05.cu) instead of the im2col-gather kernel.
 USE_SHIFTED_WINDOW = True
 BASE_OFFSET_MODE = 0
@@ -124,12 +120,10 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
         lo = 1 if stride == 1 else 0                                   # XLA SAME on even sizes: pad low 0 / high 1
         _conv(p, x, wp[f"{b}/Conv_0/kernel"], yA, p.stats[0], N, s, s, cin, so, so, f, 3, stride, lo)
         abA = _finalize(p.stats[0], w[f"{b}/MyGroupNorm_0/scale"], w[f"{b}/MyGroupNorm_0/bias"], p.aff[0], N, f, so * so)
-        if FUSE_OPERAND_GROUPNORM:
-            _conv(p, yA, wp[f"{b}/Conv_1/kernel"], yB, p.stats[1], N, so, so, f, so, so, f, 3, 1, 1, in_ab=abA)
-        else:                       # materialise relu(GN(yA)) in place (one HBM-speed pass), then a plain operand gather
-            L.call("serl_affine_relu_h16", yA.data_ptr(), abA[0].data_ptr(), abA[1].data_ptr(), N, so * so, f, p.fmt, _s())
-            _conv(p, yA, wp[f"{b}/Conv_1/kernel"], yB, p.stats[1], N, so, so, f, so, so, f, 3, 1, 1)
-            engine.launches += 1
+        # materialise relu(GN(yA)) in place (one HBM-speed pass); the conv operands are then plain async copies
+        L.call("serl_affine_relu_h16", yA.data_ptr(), abA[0].data_ptr(), abA[1].data_ptr(), N, so * so, f, p.fmt, _s())
+        _conv(p, yA, wp[f"{b}/Conv_1/kernel"], yB, p.stats[1], N, so, so, f, so, so, f, 3, 1, 1)
+        engine.launches += 1
         abB = _finalize(p.stats[1], w[f"{b}/MyGroupNorm_1/scale"], w[f"{b}/MyGroupNorm_1/bias"], p.aff[1], N, f, so * so)
         last = i == len(STAGES) - 1
         if stride != 1 or cin != f:

@@ -55,8 +55,10 @@ def test_conv_tc_matches_16bit_restated(N, Hi, Ci, Co, k, stride, lo, hi, prec):
     np.testing.assert_allclose(stats[:, :, 1].cpu().numpy(), (G * G).sum(dim=(1, 3)).numpy(), rtol=1e-3)
 
 
-def test_conv_tc_fused_groupnorm_relu_operand():
+def test_affine_relu_pass_then_conv():
+    """GroupNorm+ReLU is materialised in place by serl_affine_relu_h16 and the conv gathers the activated operand."""
     from oracle.drq import conv_nhwc
+    from serl_b200 import _lib as L
     rng = np.random.default_rng(1)
     N, Hi, Ci, Co = 5, 16, 128, 128
     x = _bf(rng.standard_normal((N, Hi, Hi, Ci)).astype(np.float32))
@@ -64,8 +66,14 @@ def test_conv_tc_fused_groupnorm_relu_operand():
     b = (0.2 * rng.standard_normal((N, Ci))).astype(np.float32)
     w = (rng.standard_normal((3, 3, Ci, Co)) * np.sqrt(2.0 / (9 * Ci))).astype(np.float32)
     xt = torch.relu(x.float() * torch.as_tensor(a)[:, None, None, :] + torch.as_tensor(b)[:, None, None, :]).to(torch.bfloat16)
-    ref = conv_nhwc(xt.double(), _bf(w).double(), 1, 1, 1)
-    y, _ = _run_conv(x, w, 1, 1, 1, in_ab=(torch.as_tensor(a).cuda(), torch.as_tensor(b).cuda()))
+    xd = x.cuda().contiguous()
+    L.call("serl_affine_relu_h16", xd.data_ptr(), torch.as_tensor(a).cuda().data_ptr(), torch.as_tensor(b).cuda().data_ptr(), N, Hi * Hi, Ci,
+           L.FMT_BF16, L.stream_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(xd.float().cpu().numpy(), xt.float().numpy(), rtol=8e-3, atol=1e-3)     # fma vs mul+add: <= 1 bf16 ulp
+    xt = xd.cpu()
+    ref = conv_nhwc(xt.double(), _bf(w).double(), 2, 0, 1)
+    y, _ = _run_conv(xt, w, 2, 0, 1)
     assert rel_err(y.float().cpu().numpy(), ref.numpy()) < 6e-3
 
 
