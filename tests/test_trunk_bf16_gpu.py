@@ -67,8 +67,8 @@ def test_affine_relu_pass_then_conv():
     w = (rng.standard_normal((3, 3, Ci, Co)) * np.sqrt(2.0 / (9 * Ci))).astype(np.float32)
     xt = torch.relu(x.float() * torch.as_tensor(a)[:, None, None, :] + torch.as_tensor(b)[:, None, None, :]).to(torch.bfloat16)
     xd = x.cuda().contiguous()
-    L.call("serl_affine_relu_h16", xd.data_ptr(), torch.as_tensor(a).cuda().data_ptr(), torch.as_tensor(b).cuda().data_ptr(), N, Hi * Hi, Ci,
-           L.FMT_BF16, L.stream_ptr())
+    ad, bd = torch.as_tensor(a).cuda(), torch.as_tensor(b).cuda()
+    L.call("serl_affine_relu_h16", xd.data_ptr(), ad.data_ptr(), bd.data_ptr(), N, Hi * Hi, Ci, L.FMT_BF16, L.stream_ptr())
     torch.cuda.synchronize()
     np.testing.assert_allclose(xd.float().cpu().numpy(), xt.float().numpy(), rtol=8e-3, atol=1e-3)     # fma vs mul+add: <= 1 bf16 ulp
     xt = xd.cpu()
