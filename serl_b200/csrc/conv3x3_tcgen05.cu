@@ -10,10 +10,10 @@
 // TMA (cp.async.bulk.tensor, 128B swizzle) through their own mbarrier ring.  Outputs at pad positions are computed and
 // discarded (M efficiency H*W / ((H+1)(W+1)): 94% at 32x32, 64% at 4x4).
 //
-//   warps 0-3  stage the patch (coalesced 128-bit gathers, zeros at pad positions), later the epilogue
-//              (tcgen05.ld, GroupNorm partial sums segmented by image, 16-bit pack, NHWC store of valid positions)
-//   warp 4     tcgen05.mma issuer (9 taps x 4 K-steps per channel block), commits
-//   warp 5     TMA issuer for the weight tiles
+//   warps 0-3  epilogue (tcgen05.ld, GroupNorm partial sums segmented by image, 16-bit pack, NHWC store of valid positions)
+//   warps 4-7  stage the patch with cp.async (coalesced 16-byte copies, zero-fill at pad positions)
+//   warp 8     tcgen05.mma issuer (9 taps x 4 K-steps per channel block), commits
+//   warp 9     TMA issuer for the weight tiles
 //
 // Replaces the conv of vision/resnet_v1.py:142-147 (ResNetBlock 3x3 convs with stride 1, SAME padding).
 #include <cuda.h>
@@ -98,16 +98,16 @@ constexpr int C3_THREADS = 320;       // warps 0-3 epilogue | 4-7 patch producer
 // Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the four roles run decoupled through mbarrier rings
 // (patch full/empty x2, weight full/empty xBSTAGES, accumulator full/empty x2 - TMEM holds two accumulators), so the
 // gather of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
-template <class F, int BN, int BSTAGES>
+template <class F, int BN, int BSTAGES, int PSTAGES>
 __global__ void __launch_bounds__(C3_THREADS, 2) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap wmap, const Conv3Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_STAGE = BN * 128;
-  uint8_t* sP = smem;                                   // 2 patches
-  uint8_t* sB = smem + 2 * a.patch_bytes;
+  uint8_t* sP = smem;                                   // PSTAGES patches
+  uint8_t* sB = smem + PSTAGES * a.patch_bytes;
   uint64_t* pfull = reinterpret_cast<uint64_t*>(sB + BSTAGES * B_STAGE);
-  uint64_t* pempty = pfull + 2;
-  uint64_t* bfull = pempty + 2;
+  uint64_t* pempty = pfull + PSTAGES;
+  uint64_t* bfull = pempty + PSTAGES;
   uint64_t* bempty = bfull + BSTAGES;
   uint64_t* afull = bempty + BSTAGES;
   uint64_t* aempty = afull + 2;
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(C3_THREADS, 2) conv3x3_tc_kernel(const __grid_
   const int n_tiles = (int)((a.Q + 127) / 128) * n_tiles_n;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) { c3_mbar_init(&pfull[s], 4); c3_mbar_init(&pempty[s], 1); c3_mbar_init(&afull[s], 1); c3_mbar_init(&aempty[s], 4); }
+    for (int s = 0; s < PSTAGES; ++s) { c3_mbar_init(&pfull[s], 128); c3_mbar_init(&pempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { c3_mbar_init(&afull[s], 1); c3_mbar_init(&aempty[s], 4); }
     for (int s = 0; s < BSTAGES; ++s) { c3_mbar_init(&bfull[s], 1); c3_mbar_init(&bempty[s], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -156,25 +157,23 @@ __global__ void __launch_bounds__(C3_THREADS, 2) conv3x3_tc_kernel(const __grid_
         }
       }
       for (int cb = 0; cb < a.cblocks && ok; ++cb, ++pc) {
-        const int ps = pc & 1;
-        uint4 v[C3_MAXR];
+        const int ps = pc % PSTAGES;
+        ok = c3_mbar_wait(&pempty[ps], (uint32_t)((pc / PSTAGES) & 1) ^ 1u, a.error);
+        const uint32_t Ps = c3_smem(sP + ps * a.patch_bytes);
 #pragma unroll
-        for (int i = 0; i < C3_MAXR; ++i) {
-          v[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (poff[i] >= 0) v[i] = *reinterpret_cast<const uint4*>(a.x + (size_t)(uint32_t)(poff[i] + cb * 64 + chunk * 8));
-        }
-        ok = c3_mbar_wait(&pempty[ps], (uint32_t)((pc >> 1) & 1) ^ 1u, a.error);
-        uint8_t* Ps = sP + ps * a.patch_bytes;
-#pragma unroll
-        for (int i = 0; i < C3_MAXR; ++i) {
+        for (int i = 0; i < C3_MAXR; ++i) {                 // cp.async: no register staging, zero-fill at pad positions
           const int j = rsub + 16 * i;
-          if (j < a.Lp) *reinterpret_cast<uint4*>(Ps + (j >> 3) * 1024 + (j & 7) * 128 + ((chunk ^ (j & 7)) << 4)) = v[i];
+          if (j < a.Lp) {
+            const bool inb = poff[i] >= 0;
+            const uint16_t* src = a.x + (inb ? (size_t)(uint32_t)(poff[i] + cb * 64 + chunk * 8) : 0);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                         ::"r"(Ps + (j >> 3) * 1024 + (j & 7) * 128 + ((chunk ^ (j & 7)) << 4)), "l"(src), "r"(inb ? 16u : 0u) : "memory");
+          }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        __syncwarp();
-        if (lane == 0) c3_mbar_arrive(&pfull[ps]);
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(c3_smem(&pfull[ps])) : "memory");
       }
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
   } else if (warp < 4) {
     // ------------------------------- epilogue ---------------------------------------
     bool ok = true;
@@ -251,8 +250,9 @@ __global__ void __launch_bounds__(C3_THREADS, 2) conv3x3_tc_kernel(const __grid_
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
       for (int cb = 0; cb < a.cblocks && ok; ++cb, ++pc) {
-        const int ps = pc & 1;
-        ok = c3_mbar_wait(&pfull[ps], (uint32_t)((pc >> 1) & 1), a.error);
+        const int ps = pc % PSTAGES;
+        ok = c3_mbar_wait(&pfull[ps], (uint32_t)((pc / PSTAGES) & 1), a.error);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // cp.async (generic proxy) writes -> tensor-core reads
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t pbase = c3_smem(sP + ps * a.patch_bytes);
         for (int tap = 0; tap < 9 && ok; ++tap, ++it) {
@@ -317,10 +317,10 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <class F, int BN, int BSTAGES>
+template <class F, int BN, int BSTAGES, int PSTAGES>
 static int launch_conv3(const CUtensorMap& map, const Conv3Args& a, cudaStream_t st) {
-  const size_t smem = (size_t)2 * a.patch_bytes + (size_t)BSTAGES * BN * 128 + 1024 + 256;
-  auto kern = conv3x3_tc_kernel<F, BN, BSTAGES>;
+  const size_t smem = (size_t)PSTAGES * a.patch_bytes + (size_t)BSTAGES * BN * 128 + 1024 + 256;
+  auto kern = conv3x3_tc_kernel<F, BN, BSTAGES, PSTAGES>;
   static size_t configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv3x3_tc)");
@@ -362,6 +362,7 @@ extern "C" int serl_conv3x3s1_tc_h16(const serl_conv_tc_desc* d, int base_offset
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("serl_conv3x3s1_tc_h16: cuTensorMapEncodeTiled failed (%d)", (int)r); return SERL_ERR_CUDA; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (d->fmt == SERL_FMT_FP16) return BN == 64 ? launch_conv3<C3Fp16, 64, 6>(map, a, st) : launch_conv3<C3Fp16, 128, 3>(map, a, st);
-  return BN == 64 ? launch_conv3<C3Bf16, 64, 6>(map, a, st) : launch_conv3<C3Bf16, 128, 3>(map, a, st);
+  // BN=64 (Ci=Co=64, 32x32 maps): 3 patches (25 KiB each) + 4 weight stages (8 KiB); BN=128: 2 patches + 3 weight stages (16 KiB)
+  if (d->fmt == SERL_FMT_FP16) return BN == 64 ? launch_conv3<C3Fp16, 64, 4, 3>(map, a, st) : launch_conv3<C3Fp16, 128, 3, 2>(map, a, st);
+  return BN == 64 ? launch_conv3<C3Bf16, 64, 4, 3>(map, a, st) : launch_conv3<C3Bf16, 128, 3, 2>(map, a, st);
 }

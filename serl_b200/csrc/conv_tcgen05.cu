@@ -374,15 +374,24 @@ __global__ void maxpool_affine_kernel(const uint16_t* __restrict__ x, const floa
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(e % c8n); size_t r = e / c8n;
     const int wo = (int)(r % Wo); r /= Wo; const int ho = (int)(r % Ho); const int n = (int)(r / Ho);
-    float av[8], bv[8], m[8];
+    const float4 a0 = *reinterpret_cast<const float4*>(ga + (size_t)n * C + c8 * 8), a1 = *reinterpret_cast<const float4*>(ga + (size_t)n * C + c8 * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(gb + (size_t)n * C + c8 * 8), b1 = *reinterpret_cast<const float4*>(gb + (size_t)n * C + c8 * 8 + 4);
+    const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float m[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { av[j] = ga[(size_t)n * C + c8 * 8 + j]; bv[j] = gb[(size_t)n * C + c8 * 8 + j]; m[j] = 0.f; }   // relu output >= 0
-    for (int dh = 0; dh < 3; ++dh) {
-      const int hi = ho * 2 + dh; if (hi >= Hi) continue;                 // SAME on even sizes: pad low 0 / high 1
-      for (int dw = 0; dw < 3; ++dw) {
-        const int wi = wo * 2 + dw; if (wi >= Wi) continue;
-        const uint4 v = *reinterpret_cast<const uint4*>(x + (((size_t)n * Hi + hi) * Wi + wi) * C + c8 * 8);
-        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    for (int j = 0; j < 8; ++j) m[j] = 0.f;                               // relu output >= 0
+    uint4 v[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {                                         // all nine loads in flight before the first use
+      const int hi = ho * 2 + t / 3, wi = wo * 2 + t % 3;                 // SAME on even sizes: pad low 0 / high 1
+      v[t] = make_uint4(0u, 0u, 0u, 0u);
+      if (hi < Hi && wi < Wi) v[t] = *reinterpret_cast<const uint4*>(x + (((size_t)n * Hi + hi) * Wi + wi) * C + c8 * 8);
+    }
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int hi = ho * 2 + t / 3, wi = wo * 2 + t % 3;
+      if (hi < Hi && wi < Wi) {
+        const uint32_t u[4] = {v[t].x, v[t].y, v[t].z, v[t].w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = F::unpack(u[j]);
@@ -408,14 +417,26 @@ __global__ void block_combine_kernel(const uint16_t* __restrict__ y2, const floa
     const size_t off = pix * C + c8 * 8, co = (size_t)n * C + c8 * 8;
     const uint4 yv = *reinterpret_cast<const uint4*>(y2 + off), rv = *reinterpret_cast<const uint4*>(res + off);
     const uint32_t yu[4] = {yv.x, yv.y, yv.z, yv.w}, ru[4] = {rv.x, rv.y, rv.z, rv.w};
+    const float4 p0 = *reinterpret_cast<const float4*>(a2 + co), p1 = *reinterpret_cast<const float4*>(a2 + co + 4);
+    const float4 q0 = *reinterpret_cast<const float4*>(b2 + co), q1 = *reinterpret_cast<const float4*>(b2 + co + 4);
+    const float ya[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w}, yb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    float ra[8], rb[8];
+    if (ar) {
+      const float4 r0 = *reinterpret_cast<const float4*>(ar + co), r1 = *reinterpret_cast<const float4*>(ar + co + 4);
+      const float4 s0 = *reinterpret_cast<const float4*>(br + co), s1 = *reinterpret_cast<const float4*>(br + co + 4);
+      ra[0] = r0.x; ra[1] = r0.y; ra[2] = r0.z; ra[3] = r0.w; ra[4] = r1.x; ra[5] = r1.y; ra[6] = r1.z; ra[7] = r1.w;
+      rb[0] = s0.x; rb[1] = s0.y; rb[2] = s0.z; rb[3] = s0.w; rb[4] = s1.x; rb[5] = s1.y; rb[6] = s1.z; rb[7] = s1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { ra[j] = 1.f; rb[j] = 0.f; }
+    }
     float o[8];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float2 fy = F::unpack(yu[j]), fr = F::unpack(ru[j]);
-      float r0 = fr.x, r1 = fr.y;
-      if (ar) { r0 = fmaf(r0, ar[co + 2 * j], br[co + 2 * j]); r1 = fmaf(r1, ar[co + 2 * j + 1], br[co + 2 * j + 1]); }
-      o[2 * j] = fmaxf(fmaf(fy.x, a2[co + 2 * j], b2[co + 2 * j]) + r0, 0.f);
-      o[2 * j + 1] = fmaxf(fmaf(fy.y, a2[co + 2 * j + 1], b2[co + 2 * j + 1]) + r1, 0.f);
+      const float r0 = ar ? fmaf(fr.x, ra[2 * j], rb[2 * j]) : fr.x, r1 = ar ? fmaf(fr.y, ra[2 * j + 1], rb[2 * j + 1]) : fr.y;
+      o[2 * j] = fmaxf(fmaf(fy.x, ya[2 * j], yb[2 * j]) + r0, 0.f);
+      o[2 * j + 1] = fmaxf(fmaf(fy.y, ya[2 * j + 1], yb[2 * j + 1]) + r1, 0.f);
     }
     if (out_f32) {
       *reinterpret_cast<float4*>(out_f32 + off) = make_float4(o[0], o[1], o[2], o[3]);
