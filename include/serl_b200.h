@@ -123,7 +123,8 @@ int serl_maxpool3x3s2_nhwc_f32(const float* x, float* y, int N, int Hi, int Wi, 
 /* ---- frozen ResNet-10 trunk, 16-bit build on tcgen05 tensor cores (same layers as above) ---------- */
 /* operand format of the kind::f16 MMAs: bf16, or fp16 (same throughput, 3 more mantissa bits; packs saturate) */
 enum { SERL_FMT_BF16 = 0, SERL_FMT_FP16 = 1 };
-/* uint8 crops (N,H,W,3) -> normalised 16-bit, 2x2 space-to-depth, zero padded: xs (N, H/2+3, W/2+3, 12) */
+/* uint8 crops (N,H,W,3) -> normalised 16-bit, 2x2 space-to-depth, zero padded: xs (N, H/2+3, W/2+3, 16)
+ * (12 real channels (p,q,c) + 4 zero channels, so four taps are one aligned 128-byte operand row) */
 int serl_trunk_stem_prep_h16(const uint8_t* x, void* xs, int N, int H, int W, int fmt, void* stream);
 typedef struct serl_conv_tc_desc {
   const void* x;           /* 16-bit NHWC (N,Hi,Wi,Ci); stem: the space-to-depth image (Hi,Wi = its dims, Ci ignored) */

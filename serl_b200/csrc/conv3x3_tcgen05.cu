@@ -98,8 +98,10 @@ constexpr int C3_THREADS = 320;       // warps 0-3 epilogue | 4-7 patch producer
 // Persistent: each CTA walks tiles blockIdx.x, +gridDim.x, ...; the four roles run decoupled through mbarrier rings
 // (patch full/empty x2, weight full/empty xBSTAGES, accumulator full/empty x2 - TMEM holds two accumulators), so the
 // gather of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
-template <class F, int BN, int BSTAGES, int PSTAGES>
-__global__ void __launch_bounds__(C3_THREADS, 2) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap wmap, const Conv3Args a) {
+// kResidentB (Ci == 64, Co == BN): the whole 9-tap weight tensor (9 x BN x 128 B) is loaded ONCE per CTA and stays in
+// shared memory - a persistent CTA then streams only input patches (1 CTA / SM, BSTAGES must be 9).
+template <class F, int BN, int BSTAGES, int PSTAGES, bool kResidentB>
+__global__ void __launch_bounds__(C3_THREADS, kResidentB ? 1 : 2) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap wmap, const Conv3Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_STAGE = BN * 128;
@@ -256,9 +258,11 @@ __global__ void __launch_bounds__(C3_THREADS, 2) conv3x3_tc_kernel(const __grid_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t pbase = c3_smem(sP + ps * a.patch_bytes);
         for (int tap = 0; tap < 9 && ok; ++tap, ++it) {
-          const int sb = it % BSTAGES;
-          ok = c3_mbar_wait(&bfull[sb], (uint32_t)((it / BSTAGES) & 1), a.error);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const int sb = kResidentB ? tap : it % BSTAGES;
+          if (!kResidentB || it < 9) {                              // resident weights: each tap's tile is waited for once
+            ok = c3_mbar_wait(&bfull[sb], kResidentB ? 0u : (uint32_t)((it / BSTAGES) & 1), a.error);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          }
           if (lane == 0 && ok) {
             const int r = tap / 3, s = tap - 3 * r;
             const uint32_t off = (uint32_t)(r * a.P + s);             // window shift in patch rows
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(C3_THREADS, 2) conv3x3_tc_kernel(const __grid_
             const uint64_t bd = c3_desc(c3_smem(sB + sb * B_STAGE), 0u);
 #pragma unroll
             for (int k = 0; k < 4; ++k) c3_mma(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((cb | tap | k) != 0));
-            c3_commit(&bempty[sb]);
+            if (!kResidentB) c3_commit(&bempty[sb]);
           }
           __syncwarp();
         }
@@ -279,17 +283,24 @@ __global__ void __launch_bounds__(C3_THREADS, 2) conv3x3_tc_kernel(const __grid_
   } else {
     // ------------------------------- weight TMA issuer ----------------------------
     if (lane == 0) {
-      bool ok = true;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
-        const int n0 = (tile % n_tiles_n) * BN;
-        for (int cb = 0; cb < a.cblocks && ok; ++cb) {
-          for (int tap = 0; tap < 9 && ok; ++tap, ++it) {
-            const int sb = it % BSTAGES;
-            ok = c3_mbar_wait(&bempty[sb], (uint32_t)((it / BSTAGES) & 1) ^ 1u, a.error);
-            if (!ok) break;
-            c3_mbar_expect_tx(&bfull[sb], (uint32_t)B_STAGE);
-            c3_tma_2d(sB + sb * B_STAGE, &wmap, tap * a.Ci + cb * 64, n0, &bfull[sb]);
+      if (kResidentB) {
+        for (int tap = 0; tap < 9; ++tap) {                         // one-time load of the whole weight tensor
+          c3_mbar_expect_tx(&bfull[tap], (uint32_t)B_STAGE);
+          c3_tma_2d(sB + tap * B_STAGE, &wmap, tap * a.Ci, 0, &bfull[tap]);
+        }
+      } else {
+        bool ok = true;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
+          const int n0 = (tile % n_tiles_n) * BN;
+          for (int cb = 0; cb < a.cblocks && ok; ++cb) {
+            for (int tap = 0; tap < 9 && ok; ++tap, ++it) {
+              const int sb = it % BSTAGES;
+              ok = c3_mbar_wait(&bempty[sb], (uint32_t)((it / BSTAGES) & 1) ^ 1u, a.error);
+              if (!ok) break;
+              c3_mbar_expect_tx(&bfull[sb], (uint32_t)B_STAGE);
+              c3_tma_2d(sB + sb * B_STAGE, &wmap, tap * a.Ci + cb * 64, n0, &bfull[sb]);
+            }
           }
         }
       }
@@ -317,10 +328,10 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <class F, int BN, int BSTAGES, int PSTAGES>
+template <class F, int BN, int BSTAGES, int PSTAGES, bool kResidentB>
 static int launch_conv3(const CUtensorMap& map, const Conv3Args& a, cudaStream_t st) {
   const size_t smem = (size_t)PSTAGES * a.patch_bytes + (size_t)BSTAGES * BN * 128 + 1024 + 256;
-  auto kern = conv3x3_tc_kernel<F, BN, BSTAGES, PSTAGES>;
+  auto kern = conv3x3_tc_kernel<F, BN, BSTAGES, PSTAGES, kResidentB>;
   static size_t configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv3x3_tc)");
@@ -329,7 +340,8 @@ static int launch_conv3(const CUtensorMap& map, const Conv3Args& a, cudaStream_t
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const long long tiles = ((a.Q + 127) / 128) * (a.Co / BN);
-  const int grid = (int)(tiles < 2ll * sms ? tiles : 2ll * sms);          // persistent: 2 CTAs per SM walk the tile list
+  const long long slots = (kResidentB ? 1ll : 2ll) * sms;               // persistent CTAs per device
+  const int grid = (int)(tiles < slots ? tiles : slots);
   kern<<<grid, C3_THREADS, smem, st>>>(map, a);
   return check_launch("conv3x3_tc_kernel");
 }
@@ -363,6 +375,12 @@ extern "C" int serl_conv3x3s1_tc_h16(const serl_conv_tc_desc* d, int base_offset
   if (r != CUDA_SUCCESS) { set_last_error("serl_conv3x3s1_tc_h16: cuTensorMapEncodeTiled failed (%d)", (int)r); return SERL_ERR_CUDA; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // BN=64 (Ci=Co=64, 32x32 maps): 3 patches (25 KiB each) + 4 weight stages (8 KiB); BN=128: 2 patches + 3 weight stages (16 KiB)
-  if (d->fmt == SERL_FMT_FP16) return BN == 64 ? launch_conv3<C3Fp16, 64, 4, 3>(map, a, st) : launch_conv3<C3Fp16, 128, 3, 2>(map, a, st);
-  return BN == 64 ? launch_conv3<C3Bf16, 64, 4, 3>(map, a, st) : launch_conv3<C3Bf16, 128, 3, 2>(map, a, st);
+  //            with Ci == 64 as well the 72 KiB weight tensor stays resident (1 CTA / SM, 4 patches)
+  const bool resident = BN == 64 && d->Ci == 64;
+  if (d->fmt == SERL_FMT_FP16) {
+    if (resident) return launch_conv3<C3Fp16, 64, 9, 4, true>(map, a, st);
+    return BN == 64 ? launch_conv3<C3Fp16, 64, 4, 3, false>(map, a, st) : launch_conv3<C3Fp16, 128, 3, 2, false>(map, a, st);
+  }
+  if (resident) return launch_conv3<C3Bf16, 64, 9, 4, true>(map, a, st);
+  return BN == 64 ? launch_conv3<C3Bf16, 64, 4, 3, false>(map, a, st) : launch_conv3<C3Bf16, 128, 3, 2, false>(map, a, st);
 }

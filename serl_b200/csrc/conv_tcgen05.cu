@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     // by cp.async.mbarrier.arrive.noinc (one deferred arrival per producer thread).
     const int tid = threadIdx.x - 128;
     const int chunk = tid & 7, rsub = tid >> 3;
-    const int cpp = kStem ? 12 : a.Ci;                      // channels per input pixel
+    const int cpp = kStem ? 16 : a.Ci;                      // channels per input pixel (stem: 12 real + 4 zero-pad)
     bool ok = true;
     int it = 0;                                             // k-blocks produced so far (ring position)
     for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x) {
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
         const int s = it % STAGES;
         const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
         const int r = tap_r, sx = tap_s;
-        const int tap_off = kStem ? kb * a.Wi * 12 : (r * a.Wi + sx) * a.Ci + cblk * TC_BK;
+        const int tap_off = kStem ? kb * a.Wi * 16 : (r * a.Wi + sx) * a.Ci + cblk * TC_BK;
         if (!kStem) { if (++cblk == a.cblocks) { cblk = 0; if (++tap_s == a.kw) { tap_s = 0; ++tap_r; } } }
         ok = tc_mbar_wait(&empty[s], ph ^ 1u, a.error);
         const uint32_t As = smem_u32(sA + s * TC_A_STAGE);
@@ -192,12 +192,10 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
           const int row = rsub + 16 * i;
           const uint32_t dst = As + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4);
           if (kStem) {
-            // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 12 ch = 48 contiguous 16-bit values (96 B, 8 B aligned)
-            const bool inb = rh[i] > -100000 && chunk < 6;
+            // k-block = kernel row kb of the 4x4 space-to-depth kernel: 4 taps x 16 ch (12 real + 4 zero) = one aligned 128-byte row
+            const bool inb = rh[i] > -100000;
             const uint16_t* src = a.x + (inb ? (size_t)(uint32_t)(rbase[i] + tap_off + chunk * 8) : 0);
-            const uint32_t n = inb ? 8u : 0u;               // src-size 0 -> zero fill
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst + 8), "l"(src + 4), "r"(n) : "memory");
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(inb ? 16u : 0u) : "memory");
           } else {
             const int hi_ = rh[i] + r, wi_ = rw[i] + sx;
             const bool inb = hi_ >= 0 && hi_ < a.Hi && wi_ >= 0 && wi_ < a.Wi;
@@ -303,14 +301,14 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
   }
 }
 
-// ---- stem input: uint8 crops -> normalised bf16, 2x2 space-to-depth, zero padded: (N,67,67,12) ------------
+// ---- stem input: uint8 crops -> normalised 16-bit, 2x2 space-to-depth, zero padded: (N,67,67,16) [12 real + 4 zero ch] ----
 template <class F>
 __global__ void stem_prep_kernel(const uint8_t* __restrict__ x, uint16_t* __restrict__ xs, int N, int H, int W, int Hs, int Ws) {
   const size_t total = (size_t)N * Hs * Ws;
   const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int b = (int)(e % Ws); size_t r = e / Ws; const int aa = (int)(r % Hs); const int n = (int)(r / Hs);
-    uint32_t out[6];
+    uint32_t out[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                    // 16 channels: (p, q, c) at pq*3 + c, channels 12..15 zero
 #pragma unroll
     for (int pq = 0; pq < 4; ++pq) {
       const int p = pq >> 1, q = pq & 1;
@@ -321,17 +319,15 @@ __global__ void stem_prep_kernel(const uint8_t* __restrict__ x, uint16_t* __rest
 #pragma unroll
         for (int c = 0; c < 3; ++c) f[c] = ((float)px[c] / 255.0f - mean[c]) / stdv[c];
       }
-      // channel order (p, q, c): element index pq*3 + c
-      const int base = pq * 3;
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        const int ei = base + c;
+        const int ei = pq * 3 + c;
         const uint32_t h = F::pack(f[c], 0.f) & 0xFFFFu;
-        if (ei & 1) out[ei >> 1] |= h << 16; else out[ei >> 1] = h;
+        out[ei >> 1] |= (ei & 1) ? (h << 16) : h;
       }
     }
-    uint2* dst = reinterpret_cast<uint2*>(xs + e * 12);
-    dst[0] = make_uint2(out[0], out[1]); dst[1] = make_uint2(out[2], out[3]); dst[2] = make_uint2(out[4], out[5]);
+    uint4* dst = reinterpret_cast<uint4*>(xs + e * 16);
+    dst[0] = make_uint4(out[0], out[1], out[2], out[3]); dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
   }
 }
 

@@ -63,16 +63,28 @@ __global__ void sle_bwd_partial_kernel(const float* __restrict__ feat, const flo
   *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
-// ---- out[g][d] = sum_{r < rows} x[(g*rows + r) * ld + d] ; thread per (g, d) -----------------------
-__global__ void colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int groups, int rows, int D, long long ld,
-                              int accumulate) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= groups * D) return;
-  const int g = e / D, d = e - g * D;
-  const float* p = x + (size_t)g * rows * ld + d;
+// ---- out[g][d] = sum_{r < rows} x[(g*rows + r) * ld + d] --------------------------------------------------------
+// block = 32 columns x 8 row-slices (coalesced 128-byte row reads), fixed-order tree over the slices: deterministic.
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int groups, int rows, int D,
+                                                     long long ld, int accumulate) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int cblocks = ceil_div(D, 32);
+  const int g = blockIdx.x / cblocks, d = (blockIdx.x - g * cblocks) * 32 + cx;
   float s = 0.f;
-  for (int r = 0; r < rows; ++r) s += p[(size_t)r * ld];
-  out[e] = accumulate ? out[e] + s : s;
+  if (d < D) {
+    const float* p = x + (size_t)g * rows * ld + d;
+    for (int r = sl; r < rows; r += 8) s += p[(size_t)r * ld];
+  }
+  red[sl][cx] = s;
+  __syncthreads();
+  if (sl == 0 && d < D) {
+    float t = red[0][cx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) t += red[k][cx];
+    const size_t e = (size_t)g * D + d;
+    out[e] = accumulate ? out[e] + t : t;
+  }
 }
 
 // ---- LayerNorm + tanh forward: warp per row -------------------------------------------------------
@@ -128,19 +140,29 @@ __global__ void ln_tanh_bwd_kernel(const float* __restrict__ dt, int ld_dt, cons
   }
 }
 
-// ---- dscale[g][d] = sum_r dy*xhat ; dbias[g][d] = sum_r dy  (thread per (g, d)) ---------------------
-__global__ void ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ xhat, float* __restrict__ dscale,
-                                     float* __restrict__ dbias, int groups, int rows, int D) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= groups * D) return;
-  const int g = e / D, d = e - g * D;
+// ---- dscale[g][d] = sum_r dy*xhat ; dbias[g][d] = sum_r dy   (same 32 x 8 block shape as colsum) -----------------
+__global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ xhat,
+                                                            float* __restrict__ dscale, float* __restrict__ dbias, int groups, int rows, int D) {
+  __shared__ float ra[8][33], rb[8][33];
+  const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int cblocks = ceil_div(D, 32);
+  const int g = blockIdx.x / cblocks, d = (blockIdx.x - g * cblocks) * 32 + cx;
   float a = 0.f, b = 0.f;
-  for (int r = 0; r < rows; ++r) {
-    const size_t off = ((size_t)g * rows + r) * D + d;
-    const float v = dy[off];
-    a += v * xhat[off]; b += v;
+  if (d < D) {
+    for (int r = sl; r < rows; r += 8) {
+      const size_t off = ((size_t)g * rows + r) * D + d;
+      const float v = dy[off];
+      a += v * xhat[off]; b += v;
+    }
   }
-  dscale[e] = a; dbias[e] = b;
+  ra[sl][cx] = a; rb[sl][cx] = b;
+  __syncthreads();
+  if (sl == 0 && d < D) {
+    float ta = ra[0][cx], tb = rb[0][cx];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) { ta += ra[k][cx]; tb += rb[k][cx]; }
+    dscale[(size_t)g * D + d] = ta; dbias[(size_t)g * D + d] = tb;
+  }
 }
 
 // ---- strided 2-D copy (concat helper) -------------------------------------------------------------
@@ -175,12 +197,12 @@ extern "C" int serl_sle_bwd_kernel_grad(const float* feat, const float* dout, fl
   sle_bwd_partial_kernel<<<grid, 128, 0, ST(stream)>>>(feat, dout, workspace, N, P, C, ld_dout, chunks);
   if (int e = check_launch("sle_bwd_partial_kernel")) return e;
   const int D = P * C * F;
-  colsum_kernel<<<ceil_div(D, 256), 256, 0, ST(stream)>>>(workspace, dkernel, 1, chunks, D, D, 0);
+  colsum_kernel<<<ceil_div(D, 32), 256, 0, ST(stream)>>>(workspace, dkernel, 1, chunks, D, D, 0);
   return check_launch("colsum_kernel(sle)");
 }
 
 extern "C" int serl_colsum_f32(const float* x, float* out, int groups, int rows, int D, long long ld, int accumulate, void* stream) {
-  colsum_kernel<<<ceil_div(groups * D, 128), 128, 0, ST(stream)>>>(x, out, groups, rows, D, ld, accumulate);
+  colsum_kernel<<<groups * ceil_div(D, 32), 256, 0, ST(stream)>>>(x, out, groups, rows, D, ld, accumulate);
   return check_launch("colsum_kernel");
 }
 
@@ -200,7 +222,7 @@ extern "C" int serl_layernorm_tanh_bwd(const float* dt, int ld_dt, const float* 
   if (int e = check_launch("ln_tanh_bwd_kernel")) return e;
   if (dscale && dbias) {
     const int groups = R / rows_per_group;
-    ln_param_grad_kernel<<<ceil_div(groups * D, 128), 128, 0, ST(stream)>>>(dy, xhat, dscale, dbias, groups, rows_per_group, D);
+    ln_param_grad_kernel<<<groups * ceil_div(D, 32), 256, 0, ST(stream)>>>(dy, xhat, dscale, dbias, groups, rows_per_group, D);
     return check_launch("ln_param_grad_kernel");
   }
   return SERL_OK;

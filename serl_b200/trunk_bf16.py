@@ -34,15 +34,15 @@ def pack_conv_weight(w: torch.Tensor, dt=torch.bfloat16) -> torch.Tensor:
 
 
 def pack_stem_weight(w: torch.Tensor, dt=torch.bfloat16) -> torch.Tensor:
-    """conv_init (7,7,3,64) -> exact 4x4 space-to-depth kernel, bf16 [64][4 rows x 64] (48 valid K per row).
+    """conv_init (7,7,3,64) -> exact 4x4 space-to-depth kernel, 16-bit [64][4 rows x 64] (4 taps x (12 real + 4 zero) ch per row).
     ws[r', s', p, q, c, co] = w8[2r'+p, 2s'+q, c, co] with w8 = w zero-extended to 8x8."""
     co = w.shape[-1]
     w8 = torch.zeros(8, 8, 3, co, dtype=w.dtype, device=w.device)
     w8[:7, :7] = w
     ws = w8.view(4, 2, 4, 2, 3, co).permute(0, 2, 1, 3, 4, 5)            # (r', s', p, q, c, co)
-    rows = ws.reshape(4, 48, co)                                        # k within a row = s'*12 + (p*2+q)*3 + c
-    out = torch.zeros(co, 4, 64, dtype=torch.float32, device=w.device)
-    out[:, :, :48] = rows.permute(2, 0, 1)
+    rows = ws.reshape(4, 4, 12, co)                                     # (r', s', (p*2+q)*3 + c, co)
+    out = torch.zeros(co, 4, 4, 16, dtype=torch.float32, device=w.device)  # k within a row = s'*16 + (p*2+q)*3 + c; 4 zero channels per tap
+    out[:, :, :, :12] = rows.permute(3, 0, 1, 2)
     return out.reshape(co, 256).to(dt).contiguous()
 
 
@@ -54,7 +54,7 @@ class _Plan:
         bf = lambda *s: torch.empty(*s, dtype=self.dt, device=dev)
         s2 = hw // 2
         self.hs = s2 + 3
-        self.xs = bf(N, self.hs, self.hs, 12)
+        self.xs = bf(N, self.hs, self.hs, 16)
         self.y0 = bf(N, s2, s2, 64)
         self.buf = [bf(N * (s2 // 2) * (s2 // 2) * 64) for _ in range(5)]
         self.stats = torch.zeros(3, N, 4, 2, dtype=torch.float32, device=dev)
