@@ -243,42 +243,46 @@ __global__ void __launch_bounds__(C3_THREADS, kResidentB ? 1 : 2) conv3x3_tc_ker
     }
   } else if (warp == 8) {
     // ------------------------------- MMA issuer -----------------------------------
-    const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-    bool ok = true;
-    int it = 0, pc = 0, ac = 0;
-    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++ac) {
-      const int as = ac & 1;
-      ok = c3_mbar_wait(&aempty[as], (uint32_t)((ac >> 1) & 1) ^ 1u, a.error);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-      for (int cb = 0; cb < a.cblocks && ok; ++cb, ++pc) {
-        const int ps = pc % PSTAGES;
-        ok = c3_mbar_wait(&pfull[ps], (uint32_t)((pc / PSTAGES) & 1), a.error);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // cp.async (generic proxy) writes -> tensor-core reads
+    // ONE thread runs the whole issue loop (no per-iteration warp reconvergence): the loop body is a handful of integer
+    // ops per tcgen05.mma, which matters because a 128x64x16 MMA only occupies the tensor pipe for ~32 cycles.
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);     // LBO=1, SBO=1024 B, version 1, SWIZZLE_128B
+      const uint32_t p_lo = (c3_smem(sP) & 0x3FFFF) >> 4, b_lo = (c3_smem(sB) & 0x3FFFF) >> 4;  // start addresses in 16-byte units
+      const uint32_t p_step = (uint32_t)a.patch_bytes >> 4, b_step = (uint32_t)B_STAGE >> 4;
+      uint32_t tap_lo[9];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) tap_lo[t] = (uint32_t)((t / 3) * a.P + (t % 3)) * 8u;        // window shift: rows x 128 B / 16
+      bool ok = true;
+      int it = 0, pc = 0, ac = 0;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++ac) {
+        const int as = ac & 1;
+        ok = c3_mbar_wait(&aempty[as], (uint32_t)((ac >> 1) & 1) ^ 1u, a.error);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t pbase = c3_smem(sP + ps * a.patch_bytes);
-        for (int tap = 0; tap < 9 && ok; ++tap, ++it) {
-          const int sb = kResidentB ? tap : it % BSTAGES;
-          if (!kResidentB || it < 9) {                              // resident weights: each tap's tile is waited for once
-            ok = c3_mbar_wait(&bfull[sb], kResidentB ? 0u : (uint32_t)((it / BSTAGES) & 1), a.error);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          }
-          if (lane == 0 && ok) {
-            const int r = tap / 3, s = tap - 3 * r;
-            const uint32_t off = (uint32_t)(r * a.P + s);             // window shift in patch rows
-            const uint64_t ad = c3_desc(pbase + off * 128u, a.base_offset_mode ? off : 0u);
-            const uint64_t bd = c3_desc(c3_smem(sB + sb * B_STAGE), 0u);
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int cb = 0; cb < a.cblocks && ok; ++cb, ++pc) {
+          const int ps = pc % PSTAGES;
+          ok = c3_mbar_wait(&pfull[ps], (uint32_t)((pc / PSTAGES) & 1), a.error);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // cp.async (generic proxy) writes -> tensor-core reads
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t pbase = p_lo + (uint32_t)ps * p_step;
+#pragma unroll
+          for (int tap = 0; tap < 9; ++tap, ++it) {
+            const int sb = kResidentB ? tap : it % BSTAGES;
+            if (!kResidentB || it < 9) {                              // resident weights: each tap's tile is waited for once
+              ok = ok && c3_mbar_wait(&bfull[sb], kResidentB ? 0u : (uint32_t)((it / BSTAGES) & 1), a.error);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
+            const uint64_t ad = desc_hi | (uint64_t)(pbase + tap_lo[tap]);
+            const uint64_t bd = desc_hi | (uint64_t)(b_lo + (uint32_t)sb * b_step);
 #pragma unroll
             for (int k = 0; k < 4; ++k) c3_mma(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((cb | tap | k) != 0));
             if (!kResidentB) c3_commit(&bempty[sb]);
           }
-          __syncwarp();
+          c3_commit(&pempty[ps]);
         }
-        if (lane == 0 && ok) c3_commit(&pempty[ps]);
-        __syncwarp();
+        if (ok) c3_commit(&afull[as]); else c3_mbar_arrive(&afull[as]);
       }
-      if (lane == 0) { if (ok) c3_commit(&afull[as]); else c3_mbar_arrive(&afull[as]); }
-      __syncwarp();
     }
   } else {
     // ------------------------------- weight TMA issuer ----------------------------
@@ -376,7 +380,7 @@ extern "C" int serl_conv3x3s1_tc_h16(const serl_conv_tc_desc* d, int base_offset
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // BN=64 (Ci=Co=64, 32x32 maps): 3 patches (25 KiB each) + 4 weight stages (8 KiB); BN=128: 2 patches + 3 weight stages (16 KiB)
   //            with Ci == 64 as well the 72 KiB weight tensor stays resident (1 CTA / SM, 4 patches)
-  const bool resident = BN == 64 && d->Ci == 64;
+  const bool resident = false && BN == 64 && d->Ci == 64;   // measured slower than two streaming CTAs per SM (profiles/r01_trunk_kernels.md)
   if (d->fmt == SERL_FMT_FP16) {
     if (resident) return launch_conv3<C3Fp16, 64, 9, 4, true>(map, a, st);
     return BN == 64 ? launch_conv3<C3Fp16, 64, 4, 3, false>(map, a, st) : launch_conv3<C3Fp16, 128, 3, 2, false>(map, a, st);

@@ -250,32 +250,33 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 8) {
     // ------------------------------- MMA issuer ------------------------------
-    // instruction descriptor: D=F32 (bit 4), A/B format (bits 7, 10), K-major both, N>>3 at bit 17, M>>4 at bit 24
-    const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-    bool ok = true;
-    int it = 0, ac = 0;
-    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++ac) {
-      const int as = ac & 1;
-      ok = tc_mbar_wait(&aempty[as], (uint32_t)((ac >> 1) & 1) ^ 1u, a.error);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
-      for (int kb = 0; kb < a.num_kb && ok; ++kb, ++it) {
-        const int s = it % STAGES;
-        ok = tc_mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u, a.error);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+    // ONE thread runs the issue loop.  Instruction descriptor: D=F32 (bit 4), A/B format (bits 7, 10), K-major both,
+    // N>>3 at bit 17, M>>4 at bit 24.
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);     // LBO=1, SBO=1024 B, version 1, SWIZZLE_128B
+      const uint32_t a_lo = (smem_u32(sA) & 0x3FFFF) >> 4, b_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
+      bool ok = true;
+      int it = 0, ac = 0;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++ac) {
+        const int as = ac & 1;
+        ok = tc_mbar_wait(&aempty[as], (uint32_t)((ac >> 1) & 1) ^ 1u, a.error);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (lane == 0 && ok) {
-          const uint64_t ad = make_smem_desc(smem_u32(sA + s * TC_A_STAGE));
-          const uint64_t bd = make_smem_desc(smem_u32(sB + s * B_STAGE));
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < a.num_kb && ok; ++kb, ++it) {
+          const int s = it % STAGES;
+          ok = tc_mbar_wait(&full[s], (uint32_t)(it / STAGES) & 1u, a.error);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t ad = desc_hi | (uint64_t)(a_lo + (uint32_t)s * (TC_A_STAGE >> 4));
+          const uint64_t bd = desc_hi | (uint64_t)(b_lo + (uint32_t)s * (B_STAGE >> 4));
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)               // UMMA_K = 16 elements = 32 B: advance the start address by 2 (x16 B)
             tc_mma_bf16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
           tc_commit(&empty[s]);                              // stage reusable once these MMAs retire
         }
-        __syncwarp();
+        if (ok) tc_commit(&afull[as]); else tc_mbar_arrive(&afull[as]);
       }
-      if (lane == 0) { if (ok) tc_commit(&afull[as]); else tc_mbar_arrive(&afull[as]); }
-      __syncwarp();
     }
   } else {
     // ------------------------------- weight TMA issuer ------------------------
