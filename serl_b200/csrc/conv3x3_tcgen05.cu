@@ -378,13 +378,14 @@ extern "C" int serl_conv3x3s1_tc_h16(const serl_conv_tc_desc* d, int base_offset
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_last_error("serl_conv3x3s1_tc_h16: cuTensorMapEncodeTiled failed (%d)", (int)r); return SERL_ERR_CUDA; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // BN=64 (Ci=Co=64, 32x32 maps): 3 patches (25 KiB each) + 4 weight stages (8 KiB); BN=128: 2 patches + 3 weight stages (16 KiB)
+  // The weight ring is what bounds these kernels (TMA latency x ring depth vs 9 tiles per channel block), so it gets the
+  // shared memory: BN=64: 2 patches (25 KiB) + 7 weight stages (8 KiB); BN=128: 2 patches (<=21 KiB) + 4 weight stages (16 KiB).
   //            with Ci == 64 as well the 72 KiB weight tensor stays resident (1 CTA / SM, 4 patches)
   const bool resident = false && BN == 64 && d->Ci == 64;   // measured slower than two streaming CTAs per SM (profiles/r01_trunk_kernels.md)
   if (d->fmt == SERL_FMT_FP16) {
     if (resident) return launch_conv3<C3Fp16, 64, 9, 4, true>(map, a, st);
-    return BN == 64 ? launch_conv3<C3Fp16, 64, 4, 3, false>(map, a, st) : launch_conv3<C3Fp16, 128, 3, 2, false>(map, a, st);
+    return BN == 64 ? launch_conv3<C3Fp16, 64, 7, 2, false>(map, a, st) : launch_conv3<C3Fp16, 128, 4, 2, false>(map, a, st);
   }
   if (resident) return launch_conv3<C3Bf16, 64, 9, 4, true>(map, a, st);
-  return BN == 64 ? launch_conv3<C3Bf16, 64, 4, 3, false>(map, a, st) : launch_conv3<C3Bf16, 128, 3, 2, false>(map, a, st);
+  return BN == 64 ? launch_conv3<C3Bf16, 64, 7, 2, false>(map, a, st) : launch_conv3<C3Bf16, 128, 4, 2, false>(map, a, st);
 }
