@@ -279,6 +279,14 @@ def run_b200(args):
     h2d = (rb.h2d_bytes - h2d0) / args.steps
     assert np.isfinite(loss)
 
+    replicas_identical = None
+    if world > 1:                                   # data-parallel replicas must stay bit-identical (same reduced gradient everywhere)
+        mine = agent._store.params.clone()
+        ref = mine.clone()
+        dist.broadcast(ref, src=0)
+        same = torch.tensor([int(torch.equal(mine, ref))], device="cuda")
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        replicas_identical = bool(same.item())
     tmax = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -299,7 +307,7 @@ def run_b200(args):
             "config": workload_config(args),
             "clocks": clk,
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h / args.steps},
-            "gpu_launches": launches, "cuda_graph": True,
+            "gpu_launches": launches, "cuda_graph": True, "replicas_identical": replicas_identical,
             "roofline": {"kernel": "frozen ResNet-10 trunk (conv_igemm + groupnorm + maxpool kernels)", "bound": "tensor",
                          "achieved": trunk_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": trunk_tflops / pk["tensor"],
                          "traffic": None, "peak_source": pk["src"], "ms_per_step": trunk_ms,

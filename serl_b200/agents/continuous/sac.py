@@ -234,13 +234,19 @@ class SACAgent:
             for cam in self._cfg.cams:
                 eng.trunk_forward(cam, eng.pix[cam], eng.feats[cam])
 
+    def _world(self) -> int:
+        dist = _dist()
+        return dist.get_world_size() if (dist is not None and self.data_parallel) else 1
+
     def _allreduce(self, eng: Engine, lo: int, hi: int):
+        """jax.lax.pmean(grads_and_aux) (common.py:213-214): the loss kernels already scale their gradients by 1/world
+        (grad_scale), so a SUM all-reduce of the live gradient segment yields the mean; info scalars are averaged."""
         dist = _dist()
         if dist is None:
             return
-        g = self._store.grad[lo:hi]
-        dist.all_reduce(g, op=dist.ReduceOp.AVG)                 # jax.lax.pmean(grads_and_aux) (common.py:213-214)
-        dist.all_reduce(eng.info[:12], op=dist.ReduceOp.AVG)
+        dist.all_reduce(self._store.grad[lo:hi], op=dist.ReduceOp.SUM)
+        dist.all_reduce(eng.info[:12], op=dist.ReduceOp.SUM)
+        eng.info[:12].mul_(1.0 / dist.get_world_size())
 
     def _update_on_engine(self, eng: Engine, nets: FrozenSet[str], pmap_axis=None, schedule_keys: bool = True, want_info: bool = True):
         assert nets.issubset(ALL_NETS), f"Invalid gradient steps: {nets}"
@@ -249,12 +255,13 @@ class SACAgent:
             eng.launches += 1
         expl = self.explicit_randomness
         st = self._store
+        gscale = 1.0 / self._world() if (pmap_axis is not None or self.data_parallel) else 1.0
         if "critic" in nets:
-            eng.critic_loss_and_grads(self._keys, explicit=expl)
+            eng.critic_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl)
         if "actor" in nets or "temperature" in nets:
             if not ("actor" in nets and "temperature" in nets):
                 raise NotImplementedError("actor and temperature are updated together (update_high_utd, sac.py:586-590)")
-            eng.actor_temp_loss_and_grads(self._keys, explicit=expl)
+            eng.actor_temp_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl)
         if pmap_axis is not None or self.data_parallel:
             if "critic" in nets:
                 self._allreduce(eng, 0, st.seg_end[0])
