@@ -291,9 +291,17 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     ms, e2e_ms = tmax.tolist()
-    if rank != 0:
+    def shutdown():
+        # captured NCCL kernels inside live CUDA graphs can block process-group teardown: drop the graphs first, and never
+        # let a teardown problem turn into a hung bench (os._exit after the line is out)
+        agent._graphs.clear()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
         if world > 1:
-            dist.destroy_process_group()
+            os._exit(0)
+
+    if rank != 0:
+        shutdown()
         return
     pk = peaks()
     value = args.steps / (ms / 1e3)
@@ -325,8 +333,7 @@ def run_b200(args):
     except Exception as e:                      # noqa: BLE001
         line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":
