@@ -24,9 +24,13 @@ struct GemmArgs {
   int accumulate, to_ws;
 };
 
+constexpr int GSTAGES = 4;
+
+// 4-stage cp.async pipeline: these GEMMs are small (a few hundred CTAs of 64x64 tiles), so each CTA is bound by the
+// global->shared latency of its k-loop; with three k-blocks of loads in flight per CTA the loop runs at FMA speed.
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs g) {
-  __shared__ __align__(16) float As[2][GK][GM + 4];
-  __shared__ __align__(16) float Bs[2][GK][GN + 4];
+  __shared__ __align__(16) float As[GSTAGES][GK][GM + 4];
+  __shared__ __align__(16) float Bs[GSTAGES][GK][GN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int z = blockIdx.z / g.S, s = blockIdx.z - z * g.S;
   const int m0 = blockIdx.x * GM, n0 = blockIdx.y * GN;
@@ -38,29 +42,21 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs g) {
   // thread -> tile element mappings, chosen so the unit-stride dimension is fastest across threads
   const bool a_kfast = (g.sAk == 1);
   const bool b_nfast = (g.sBn == 1);
-  float ra[4], rb[4];
-  auto gload = [&](int k0) {
+  auto issue = [&](int k0, int buf) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       int m, k;
       if (a_kfast) { k = tid & 15; m = (tid >> 4) + 16 * e; } else { m = tid & 63; k = (tid >> 6) + 4 * e; }
       const int gm = m0 + m, gk = k0 + k;
-      ra[e] = (gm < g.M && gk < kend) ? A[gm * g.sAm + gk * g.sAk] : 0.f;
+      const bool va = gm < g.M && gk < kend;
+      const float* pa = va ? A + gm * g.sAm + gk * g.sAk : g.A;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(&As[buf][k][m])), "l"(pa), "r"(va ? 4u : 0u) : "memory");
       int n, kb;
       if (b_nfast) { n = tid & 63; kb = (tid >> 6) + 4 * e; } else { kb = tid & 15; n = (tid >> 4) + 16 * e; }
       const int gn = n0 + n, gkb = k0 + kb;
-      rb[e] = (gn < g.N && gkb < kend) ? B[gkb * g.sBk + gn * g.sBn] : 0.f;
-    }
-  };
-  auto sstore = [&](int buf) {
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      int m, k;
-      if (a_kfast) { k = tid & 15; m = (tid >> 4) + 16 * e; } else { m = tid & 63; k = (tid >> 6) + 4 * e; }
-      As[buf][k][m] = ra[e];
-      int n, kb;
-      if (b_nfast) { n = tid & 63; kb = (tid >> 6) + 4 * e; } else { kb = tid & 15; n = (tid >> 4) + 16 * e; }
-      Bs[buf][kb][n] = rb[e];
+      const bool vb = gn < g.N && gkb < kend;
+      const float* pb = vb ? B + gkb * g.sBk + gn * g.sBn : g.B;
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(&Bs[buf][kb][n])), "l"(pb), "r"(vb ? 4u : 0u) : "memory");
     }
   };
 
@@ -71,11 +67,17 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs g) {
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const int nk = kend > kbeg ? ceil_div(kend - kbeg, GK) : 0;
-  if (nk > 0) { gload(kbeg); sstore(0); }
-  __syncthreads();
+#pragma unroll
+  for (int st = 0; st < GSTAGES - 1; ++st) {
+    if (st < nk) issue(kbeg + st * GK, st);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   for (int kt = 0; kt < nk; ++kt) {
-    const int buf = kt & 1;
-    if (kt + 1 < nk) gload(kbeg + (kt + 1) * GK);
+    asm volatile("cp.async.wait_group %0;" ::"n"(GSTAGES - 2) : "memory");
+    __syncthreads();                                        // stage kt landed for everyone; stage (kt-1) fully consumed
+    if (kt + GSTAGES - 1 < nk) issue(kbeg + (kt + GSTAGES - 1) * GK, (kt + GSTAGES - 1) % GSTAGES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int buf = kt % GSTAGES;
 #pragma unroll
     for (int k = 0; k < GK; ++k) {
       float4 av = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
@@ -86,9 +88,8 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs g) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(aa[i], bb[j], acc[i][j]);
     }
-    if (kt + 1 < nk) sstore(buf ^ 1);
-    __syncthreads();
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
 
   if (g.to_ws) {
     float* P = g.ws + ((size_t)blockIdx.z * g.M) * g.N;        // part index = z*S + s
@@ -146,10 +147,11 @@ extern "C" int serl_gemm_f32(const serl_gemm_desc* d, void* stream) {
   g.sAz = d->sAz; g.sAm = d->sAm; g.sAk = d->sAk; g.sBz = d->sBz; g.sBk = d->sBk; g.sBn = d->sBn;
   g.sCz = d->sCz; g.sBiasZ = d->sBiasZ; g.ldc = d->ldc; g.accumulate = d->accumulate;
   const int tiles = ceil_div(d->M, GM) * ceil_div(d->N, GN) * d->Z;
+  // every CTA is latency-bound, so aim for ~4 CTAs per SM: split K (deterministic partial sums) until ~600 CTAs exist
   int S = 1;
-  if (tiles < 148 && d->K >= 256) {
-    S = ceil_div(2 * 148, tiles);
-    if (S > d->K / 128) S = d->K / 128;
+  if (tiles < 448 && d->K >= 128) {
+    S = ceil_div(600, tiles);
+    if (S > d->K / 64) S = d->K / 64;
     if (S < 1) S = 1;
   }
   const size_t part = (size_t)d->M * d->N * sizeof(float);
