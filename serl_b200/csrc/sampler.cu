@@ -204,6 +204,147 @@ __global__ void __launch_bounds__(kSamplerThreads) sample_gather_crop_kernel(con
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fast path (row_bytes % 16 == 0): ONE CTA per (row, camera, obs|next) streams its whole frame(s).
+// The serial preamble runs once per frame instead of once per band and is spread over two warps (warp 0: Philox index
+// draw; warp 1: the threefry crop-key chain, two lanes wide, three evaluations deep); the four 32-row bands are then
+// double-buffered: the TMA bulk copy of band k+1 is in flight while band k is shifted and written back.
+// ---------------------------------------------------------------------------------------------
+constexpr int kFrameThreads = 256;
+
+// crop offsets for frame g, computed cooperatively by lanes 0/1 of a full warp (all 32 lanes must call)
+__device__ inline void crop_offset_warp(const uint32_t* key, const int32_t* expl, int crop_total, int g, int span, int lane,
+                                        int* cy, int* cx) {
+  if (expl) { *cy = expl[2 * g]; *cx = expl[2 * g + 1]; return; }
+  const uint32_t n = (uint32_t)crop_total;
+  // level 1: key_g = split(key, n)[g] = (flat[2g], flat[2g+1])
+  const uint32_t pos = 2u * (uint32_t)g + (uint32_t)(lane & 1);
+  const uint32_t j = pos < n ? pos : pos - n;
+  const u32x2 y1 = threefry2x32(u32x2{key[0], key[1]}, j, n + j);
+  const uint32_t f = pos < n ? y1.x : y1.y;
+  const u32x2 k{__shfl_sync(0xffffffffu, f, 0), __shfl_sync(0xffffffffu, f, 1)};
+  // level 2: k1, k2 = split(key_g, 2): flat = [a0, a1, b0, b1] with (a_j, b_j) = TF(key_g, j, 2 + j)
+  const u32x2 y2 = threefry2x32(k, (uint32_t)(lane & 1), 2u + (uint32_t)(lane & 1));
+  const uint32_t a0 = __shfl_sync(0xffffffffu, y2.x, 0), a1 = __shfl_sync(0xffffffffu, y2.x, 1);
+  const uint32_t b0 = __shfl_sync(0xffffffffu, y2.y, 0), b1 = __shfl_sync(0xffffffffu, y2.y, 1);
+  // level 3: higher bits = random_bits(k1, (2,)), lower bits = random_bits(k2, (2,))
+  const u32x2 y3 = threefry2x32((lane & 1) ? u32x2{b0, b1} : u32x2{a0, a1}, 0u, 1u);
+  const uint32_t hb0 = __shfl_sync(0xffffffffu, y3.x, 0), hb1 = __shfl_sync(0xffffffffu, y3.y, 0);
+  const uint32_t lb0 = __shfl_sync(0xffffffffu, y3.x, 1), lb1 = __shfl_sync(0xffffffffu, y3.y, 1);
+  const uint32_t sp = (uint32_t)span;
+  uint32_t mult = 65536u % sp; mult = (mult * mult) % sp;
+  *cy = (int)(((hb0 % sp) * mult + (lb0 % sp)) % sp);
+  *cx = (int)(((hb1 % sp) * mult + (lb1 % sp)) % sp);
+}
+
+// grid: x = cam*2 + which, y = row i.
+__global__ void __launch_bounds__(kFrameThreads) sample_frames_kernel(const SamplerArgs a) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ uint64_t bar[2];
+  __shared__ int s_idx, s_cy[8], s_cx[8];
+
+  const serl_replay_view& rv = a.rv;
+  const int T = rv.num_stack, H = rv.height, W = rv.width, C = rv.channels;
+  const int row_bytes = W * C;
+  const int which = blockIdx.x & 1, cam = blockIdx.x >> 1;
+  const int i = blockIdx.y;
+  const int out_row = a.out_row_offset + i;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool leader = (cam == 0 && which == 0);
+  const int band_bytes = kBandRows * row_bytes + 32;
+
+  if (threadIdx.x == 0) {
+    const int idx = a.explicit_idx ? a.explicit_idx[i] : draw_index(a, a.lane_offset + (uint32_t)i);
+    s_idx = idx;
+    if (idx < 0) atomicOr(a.status, 1);
+    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    for (int t = 0; t < T; ++t) {
+      const int g = out_row * T + t;
+      int cy, cx;
+      crop_offset_warp(which ? a.key_next : a.key_obs, which ? a.explicit_off_next : a.explicit_off_obs, a.crop_total, g,
+                       2 * a.padding + 1, lane, &cy, &cx);
+      if (lane == 0) {
+        s_cy[t] = cy; s_cx[t] = cx;
+        if (cam == 0) { int32_t* o = which ? a.off_next_out : a.off_obs_out; if (o) { o[2 * g] = cy; o[2 * g + 1] = cx; } }
+      }
+    }
+  }
+  __syncthreads();
+  const int idx = s_idx;
+  if (idx < 0) return;
+
+  if (leader) {                                            // small fields: one CTA per row
+    const int ns = T * rv.state_dim;
+    for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+      a.obs_state[(size_t)out_row * ns + k] = rv.state[(size_t)idx * ns + k];
+      a.next_state[(size_t)out_row * ns + k] = rv.next_state[(size_t)idx * ns + k];
+    }
+    for (int k = threadIdx.x; k < rv.action_dim; k += blockDim.x)
+      a.actions[(size_t)out_row * rv.action_dim + k] = rv.actions[(size_t)idx * rv.action_dim + k];
+    if (threadIdx.x == 0) {
+      a.rewards[out_row] = rv.rewards[idx]; a.masks[out_row] = rv.masks[idx]; a.dones[out_row] = rv.dones[idx];
+      if (a.idx_out) a.idx_out[out_row] = idx;
+    }
+  }
+
+  const size_t frame_bytes = (size_t)H * row_bytes;
+  const int nb = ceil_div(H, kBandRows), total = T * nb;
+  const int cpr = row_bytes >> 4;
+  auto issue = [&](int it) {                               // thread 0: TMA bulk copy of band `it` into buffer it & 1
+    const int t = it / nb, band = it - t * nb;
+    const int y0 = band * kBandRows, rows = min(kBandRows, H - y0);
+    const int dy = s_cy[t] - a.padding;
+    const int r_lo = min(max(y0 + dy, 0), H - 1), r_hi = min(max(y0 + rows - 1 + dy, 0), H - 1);
+    const uint32_t nbytes = (uint32_t)(r_hi - r_lo + 1) * row_bytes;
+    const uint8_t* src = rv.frames[cam] + (size_t)(idx - T + t + which) * frame_bytes + (size_t)r_lo * row_bytes;
+    mbar_expect_tx(&bar[it & 1], nbytes);
+    bulk_g2s(smem + (it & 1) * band_bytes, src, nbytes, &bar[it & 1]);
+  };
+  if (threadIdx.x == 0) issue(0);
+  for (int it = 0; it < total; ++it) {
+    if (threadIdx.x == 0 && it + 1 < total) issue(it + 1);  // the other buffer was released by the barrier below
+    mbar_wait(&bar[it & 1], (uint32_t)(it >> 1) & 1u);
+    const int t = it / nb, band = it - t * nb;
+    const int y0 = band * kBandRows, rows = min(kBandRows, H - y0);
+    const int cy = s_cy[t], cx = s_cx[t];
+    const int dy = cy - a.padding, sh = (cx - a.padding) * C;
+    const int r_lo = min(max(y0 + dy, 0), H - 1);
+    const uint8_t* sb = smem + (it & 1) * band_bytes;
+    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sb);
+    const int g = out_row * T + t;
+    uint8_t* dst = (which ? a.next_pix[cam] : a.obs_pix[cam]) + ((size_t)g * H + y0) * row_bytes;
+    for (int q = threadIdx.x; q < rows * cpr; q += blockDim.x) {
+      const int yl = q / cpr, jj = q - yl * cpr;
+      const int r = min(max(y0 + yl + dy, 0), H - 1) - r_lo;
+      const int b0 = jj * 16, a0 = b0 + sh;
+      uint4 v;
+      if (a0 >= 0 && a0 + 16 <= row_bytes) {
+        const int base = r * row_bytes + a0;
+        const int wi = base >> 2, bs = (base & 3) * 8;
+        const uint32_t w0 = s32[wi], w1 = s32[wi + 1], w2 = s32[wi + 2], w3 = s32[wi + 3], w4 = s32[wi + 4];
+        v.x = __funnelshift_r(w0, w1, bs); v.y = __funnelshift_r(w1, w2, bs);
+        v.z = __funnelshift_r(w2, w3, bs); v.w = __funnelshift_r(w3, w4, bs);
+      } else {
+        uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int b = 0; b < 16; ++b) {
+          const int ob = b0 + b;
+          const int x = ob / C, ch = ob - x * C;
+          const int xs = min(max(x + cx - a.padding, 0), W - 1);
+          o[b >> 2] |= (uint32_t)sb[r * row_bytes + xs * C + ch] << ((b & 3) * 8);
+        }
+        v = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)yl * row_bytes + b0),
+                   "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    }
+    __syncthreads();                                       // buffer it & 1 may be refilled (by issue(it + 2)) after this
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Replay ring writes (insert path).  The ring bookkeeping (cursor, episode-start fillers, validity)
 // is host logic mirroring data/memory_efficient_replay_buffer.py:53-89; these kernels apply a batch
 // of slot writes staged in device memory.
@@ -307,7 +448,12 @@ extern "C" int serl_replay_sample_crop(const serl_replay_view* rv, const serl_sa
   dim3 grid(ceil_div(rv->height, kBandRows), rv->num_cams * 2 * rv->num_stack, rq->batch);
   if (rv->num_cams == 0) grid = dim3(1, 1, rq->batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (fast) {
+  if (fast && rv->num_stack <= 8) {
+    const size_t smem = 2 * ((size_t)kBandRows * row_bytes + 32);
+    dim3 fgrid(rv->num_cams * 2, rq->batch);
+    sample_frames_kernel<<<fgrid, kFrameThreads, smem, st>>>(a);
+    return check_launch("sample_frames_kernel");
+  } else if (fast) {
     size_t smem = (size_t)kBandRows * row_bytes + 32;
     sample_gather_crop_kernel<true><<<grid, kSamplerThreads, smem, st>>>(a);
   } else {

@@ -57,7 +57,7 @@ class _Plan:
         self.xs = bf(N, self.hs, self.hs, 16)
         self.y0 = bf(N, s2, s2, 64)
         self.buf = [bf(N * (s2 // 2) * (s2 // 2) * 64) for _ in range(5)]
-        self.stats = torch.zeros(3, N, 4, 2, dtype=torch.float32, device=dev)
+        self.stats = torch.zeros(16, N, 4, 2, dtype=torch.float32, device=dev)     # one slot per conv, zeroed by ONE memset per pass
         self.aff = torch.empty(3, 2, N, 512, dtype=torch.float32, device=dev)
         self.error = torch.zeros(1, dtype=torch.int32, device=dev)
 
@@ -103,8 +103,10 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
     s = hw // 2
     L.call("serl_trunk_stem_prep_h16", pix.data_ptr(), p.xs.data_ptr(), N, hw, hw, p.fmt, _s())
     p.stats.zero_()
-    _conv(p, p.xs, wp["conv_init/kernel"], p.y0, p.stats[0], N, p.hs, p.hs, 12, s, s, 64, 4, 1, 0, stem=True)
-    a0, b0 = _finalize(p.stats[0], w["norm_init/scale"], w["norm_init/bias"], p.aff[0], N, 64, s * s)
+    st = iter(p.stats)
+    st0 = next(st)
+    _conv(p, p.xs, wp["conv_init/kernel"], p.y0, st0, N, p.hs, p.hs, 12, s, s, 64, 4, 1, 0, stem=True)
+    a0, b0 = _finalize(st0, w["norm_init/scale"], w["norm_init/bias"], p.aff[0], N, 64, s * s)
     s //= 2
     x = p.buf[0][:N * s * s * 64].view(N, s, s, 64)
     L.call("serl_maxpool_affine_h16", p.y0.data_ptr(), a0.data_ptr(), b0.data_ptr(), x.data_ptr(), N, 2 * s, 2 * s, 64, p.fmt, _s())
@@ -116,19 +118,19 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
         iy, iy2, ir, io = free
         view = lambda j: p.buf[j][:N * so * so * f].view(N, so, so, f)
         yA, yB, yP, out = view(iy), view(iy2), view(ir), view(io)
-        p.stats.zero_()
+        sA, sB, sP = next(st), next(st), next(st)
         lo = 1 if stride == 1 else 0                                   # XLA SAME on even sizes: pad low 0 / high 1
-        _conv(p, x, wp[f"{b}/Conv_0/kernel"], yA, p.stats[0], N, s, s, cin, so, so, f, 3, stride, lo)
-        abA = _finalize(p.stats[0], w[f"{b}/MyGroupNorm_0/scale"], w[f"{b}/MyGroupNorm_0/bias"], p.aff[0], N, f, so * so)
+        _conv(p, x, wp[f"{b}/Conv_0/kernel"], yA, sA, N, s, s, cin, so, so, f, 3, stride, lo)
+        abA = _finalize(sA, w[f"{b}/MyGroupNorm_0/scale"], w[f"{b}/MyGroupNorm_0/bias"], p.aff[0], N, f, so * so)
         # materialise relu(GN(yA)) in place (one HBM-speed pass); the conv operands are then plain async copies
         L.call("serl_affine_relu_h16", yA.data_ptr(), abA[0].data_ptr(), abA[1].data_ptr(), N, so * so, f, p.fmt, _s())
-        _conv(p, yA, wp[f"{b}/Conv_1/kernel"], yB, p.stats[1], N, so, so, f, so, so, f, 3, 1, 1)
+        _conv(p, yA, wp[f"{b}/Conv_1/kernel"], yB, sB, N, so, so, f, so, so, f, 3, 1, 1)
         engine.launches += 1
-        abB = _finalize(p.stats[1], w[f"{b}/MyGroupNorm_1/scale"], w[f"{b}/MyGroupNorm_1/bias"], p.aff[1], N, f, so * so)
+        abB = _finalize(sB, w[f"{b}/MyGroupNorm_1/scale"], w[f"{b}/MyGroupNorm_1/bias"], p.aff[1], N, f, so * so)
         last = i == len(STAGES) - 1
         if stride != 1 or cin != f:
-            _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, p.stats[2], N, s, s, cin, so, so, f, 1, stride, 0)
-            abP = _finalize(p.stats[2], w[f"{b}/norm_proj/scale"], w[f"{b}/norm_proj/bias"], p.aff[2], N, f, so * so)
+            _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, sP, N, s, s, cin, so, so, f, 1, stride, 0)
+            abP = _finalize(sP, w[f"{b}/norm_proj/scale"], w[f"{b}/norm_proj/bias"], p.aff[2], N, f, so * so)
             res, ar, br = yP, abP[0].data_ptr(), abP[1].data_ptr()
             engine.launches += 2
         else:
