@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("SERL_PRECISION", "fp32"), choices=["fp32", "bf16", "fp16"])
+    ap.add_argument("--precision", default=os.environ.get("SERL_PRECISION", "fp16"), choices=["fp32", "bf16", "fp16"],
+                    help="trunk arithmetic: fp16 (default: tensor cores, fp32 accumulate, meets the 1e-2 bar), bf16, or fp32 (1e-5 parity build)")
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--cams", type=int, default=1)
     ap.add_argument("--capacity", type=int, default=100_000)
@@ -120,6 +121,8 @@ def workload_config(args):
     return {"workload": f"async_drq_sim: {args.cams}x 128x128x3 camera, batch {args.batch} (global), replay {args.capacity} in HBM, "
                         "critic grad step incl. sampling + DrQ shift", "global_batch": args.batch, "cams": args.cams,
             "replay_capacity": args.capacity, "parallelism": f"dp{args.gpus}", "precision": args.precision,
+            "arithmetic": ("frozen ResNet-10 trunk: 16-bit operands on tcgen05 tensor cores with fp32 accumulation; trainable heads, losses, "
+                           "Adam in fp32" if args.precision != "fp32" else "everything fp32 (CUDA cores): the 1e-5 parity build"),
             "l2": "inputs exceed L2: each step gathers fresh random frames from a multi-GB replay"}
 
 
