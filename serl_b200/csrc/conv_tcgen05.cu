@@ -302,6 +302,177 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stem (conv_init) kernel: two-level staging.  A tile = 2 output rows x 64 columns of one image; the 5 x 67 space-to-
+// depth pixels it needs (10.7 KB, contiguous in memory) arrive with ONE TMA bulk copy; the producers then build the four
+// im2col k-block tiles shared->shared (each operand row = 4 consecutive s2d pixels = 128 contiguous patch bytes), so the
+// 14.6x redundancy of the im2col view never touches L2.  The 32 KB weight tensor is loaded once and stays resident.
+//   warps 0-3 epilogue | 4-7 patch -> A-tile builders | 8 tcgen05.mma issuer | 9 TMA (weights once, one patch per tile)
+// ---------------------------------------------------------------------------------------------
+constexpr int ST_STAGES = 3;
+constexpr int ST_PATCH_ROWS = 5, ST_PITCH_PX = 67, ST_PX_BYTES = 32;
+constexpr int ST_PATCH_BYTES = ST_PATCH_ROWS * ST_PITCH_PX * ST_PX_BYTES;        // 10720
+constexpr int ST_PATCH_ALLOC = 11264;                                            // 1 KiB multiple
+
+__device__ inline void st_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <class F>
+__global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_constant__ CUtensorMap wmap, const ConvTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int BN = 64, W_TILE = BN * 128;                     // 8 KiB weight tile per k-block
+  uint8_t* sA = smem;                                           // ST_STAGES x 16 KiB
+  uint8_t* sW = sA + ST_STAGES * TC_A_STAGE;                    // 4 x 8 KiB resident weights
+  uint8_t* sP = sW + 4 * W_TILE;                                // 2 patches
+  uint64_t* full = reinterpret_cast<uint64_t*>(sP + 2 * ST_PATCH_ALLOC);
+  uint64_t* empty = full + ST_STAGES;
+  uint64_t* pfull = empty + ST_STAGES;
+  uint64_t* pempty = pfull + 2;
+  uint64_t* afull = pempty + 2;
+  uint64_t* aempty = afull + 2;
+  uint64_t* wfull = aempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = a.M / TC_BM;                              // N * 32 (M = N * 64 * 64)
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST_STAGES; ++s) { tc_mbar_init(&full[s], 4); tc_mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { tc_mbar_init(&pfull[s], 1); tc_mbar_init(&pempty[s], 4); tc_mbar_init(&afull[s], 1); tc_mbar_init(&aempty[s], 4); }
+    tc_mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(2 * BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 9 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // ------------------------------- A-tile builders (shared -> shared) -------------------------------
+    const int tid = threadIdx.x - 128, chunk = tid & 7, rsub = tid >> 3;
+    bool ok = true;
+    int it = 0, pc = 0;
+    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++pc) {
+      const int pb = pc & 1;
+      ok = tc_mbar_wait(&pfull[pb], (uint32_t)((pc >> 1) & 1), a.error);
+      const uint8_t* patch = sP + pb * ST_PATCH_ALLOC;
+      for (int kb = 0; kb < 4 && ok; ++kb, ++it) {
+        const int s = it % ST_STAGES;
+        uint4 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {                           // operand row = pixel (ho_l + kb, wo .. wo+3): 128 contiguous patch bytes
+          const int row = rsub + 16 * i, ho_l = row >> 6, wo = row & 63;
+          v[i] = *reinterpret_cast<const uint4*>(patch + ((ho_l + kb) * ST_PITCH_PX + wo) * ST_PX_BYTES + chunk * 16);
+        }
+        ok = tc_mbar_wait(&empty[s], ((uint32_t)(it / ST_STAGES) & 1u) ^ 1u, a.error);
+        uint8_t* As = sA + s * TC_A_STAGE;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = rsub + 16 * i;
+          *reinterpret_cast<uint4*>(As + (row >> 3) * 1024 + (row & 7) * 128 + ((chunk ^ (row & 7)) << 4)) = v[i];
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&full[s]);
+      }
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&pempty[pb]);               // this warp no longer reads the patch
+    }
+  } else if (warp < 4) {
+    // ------------------------------- epilogue (64 x 64 output maps: a warp's 32 rows share one image) -----------------
+    bool ok = true;
+    int ac = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ac) {
+      const int as = ac & 1;
+      ok = ok && tc_mbar_wait(&afull[as], (uint32_t)((ac >> 1) & 1), a.error);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int gm = tile * TC_BM + warp * 32 + lane;
+      const int n_img = gm >> 12;                                // / (64 * 64)
+#pragma unroll
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        float s = 0.f, ss = 0.f;
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
+          s += f0 + f1; ss += f0 * f0 + f1 * f1;
+          pk[j] = F::pack(f0, f1);
+        }
+        if (!ok) { s = 0.f; ss = 0.f; }
+        s = warp_sum(s); ss = warp_sum(ss);
+        if (ok) {
+          if (lane == 0) { float* st = a.stats + ((size_t)n_img * 4 + c0 / 16) * 2; atomicAdd(st, s); atomicAdd(st + 1, ss); }
+          uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)gm * BN + c0);
+          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) tc_mbar_arrive(&aempty[as]);
+    }
+  } else if (warp == 8) {
+    // ------------------------------- MMA issuer (one thread) ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t a_lo = (smem_u32(sA) & 0x3FFFF) >> 4, w_lo = (smem_u32(sW) & 0x3FFFF) >> 4;
+      bool ok = tc_mbar_wait(wfull, 0u, a.error);
+      int it = 0, ac = 0;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++ac) {
+        const int as = ac & 1;
+        ok = tc_mbar_wait(&aempty[as], (uint32_t)((ac >> 1) & 1) ^ 1u, a.error);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb, ++it) {
+          const int s = it % ST_STAGES;
+          ok = ok && tc_mbar_wait(&full[s], (uint32_t)(it / ST_STAGES) & 1u, a.error);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint64_t ad = desc_hi | (uint64_t)(a_lo + (uint32_t)s * (TC_A_STAGE >> 4));
+          const uint64_t bd = desc_hi | (uint64_t)(w_lo + (uint32_t)kb * (W_TILE >> 4));
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k) tc_mma_bf16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          tc_commit(&empty[s]);
+        }
+        if (ok) tc_commit(&afull[as]); else tc_mbar_arrive(&afull[as]);
+      }
+    }
+  } else {
+    // ------------------------------- TMA: resident weights + one patch per tile ------------------------
+    if (lane == 0) {
+      tc_mbar_expect_tx(wfull, 4u * W_TILE);
+      for (int kb = 0; kb < 4; ++kb) tc_tma_2d(sW + kb * W_TILE, &wmap, kb * TC_BK, 0, wfull);
+      bool ok = true;
+      int pc = 0;
+      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++pc) {
+        const int pb = pc & 1;
+        ok = tc_mbar_wait(&pempty[pb], (uint32_t)((pc >> 1) & 1) ^ 1u, a.error);
+        if (!ok) break;
+        const int n = tile >> 5, ho0 = (tile & 31) * 2;            // 32 tiles per image, 2 output rows each
+        const uint16_t* src = a.x + ((size_t)n * a.Hi + ho0) * a.Wi * 16;
+        tc_mbar_expect_tx(&pfull[pb], (uint32_t)ST_PATCH_BYTES);
+        st_bulk_g2s(sP + pb * ST_PATCH_ALLOC, src, (uint32_t)ST_PATCH_BYTES, &pfull[pb]);
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(2 * BN)) : "memory");
+  }
+}
+
 // ---- stem input: uint8 crops -> normalised 16-bit, 2x2 space-to-depth, zero padded: (N,67,67,16) [12 real + 4 zero ch] ----
 template <class F>
 __global__ void stem_prep_kernel(const uint8_t* __restrict__ x, uint16_t* __restrict__ xs, int N, int H, int W, int Hs, int Ws) {
@@ -494,9 +665,39 @@ using namespace serl;
 #define ST(s) static_cast<cudaStream_t>(s)
 
 template <class F>
+static int launch_stem_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
+  constexpr size_t smem = (size_t)ST_STAGES * TC_A_STAGE + 4 * 64 * 128 + 2 * ST_PATCH_ALLOC + 1024 + 256;
+  auto kern = stem_tc_kernel<F>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(stem_tc)");
+    configured = true;
+  }
+  TcEncodeTiledFn enc = tc_get_encode();
+  if (!enc) { set_last_error("serl_conv2d_tc_h16: cuTensorMapEncodeTiled unavailable"); return SERL_ERR_CUDA; }
+  CUtensorMap map;
+  const cuuint64_t gdim[2] = {256, 64};
+  const cuuint64_t gstr[1] = {512};
+  const cuuint32_t box[2] = {64u, 64u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(&map, fmt == SERL_FMT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                   const_cast<uint16_t*>(a.w), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_last_error("serl_conv2d_tc_h16: cuTensorMapEncodeTiled failed (%d)", (int)r); return SERL_ERR_CUDA; }
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int tiles = a.M / TC_BM;
+  const int grid = tiles < 2 * sms ? tiles : 2 * sms;
+  kern<<<grid, TC_THREADS, smem, st>>>(map, a);
+  return check_launch("stem_tc_kernel");
+}
+
+template <class F>
 static int conv_tc_dispatch(const serl_conv_tc_desc* d, ConvTcArgs& a, cudaStream_t st) {
   if (d->stem) {
     a.num_kb = 4; a.cblocks = 1;
+    // the two-level kernel is specialised for the 128x128 input of every SERL camera (s2d image 67x67, output 64x64)
+    if (d->Hi == 67 && d->Wi == 67 && d->Ho == 64 && d->Wo == 64) return launch_stem_tc<F>(a, d->fmt, st);
     return launch_conv_tc<F, 64, 4, true, false>(a, d->fmt, st);
   }
   a.cblocks = d->Ci / 64; a.num_kb = d->kh * d->kw * a.cblocks;
