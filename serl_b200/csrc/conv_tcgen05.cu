@@ -14,6 +14,8 @@
 // The 7x7/2 stem on 3 channels is rewritten exactly as a 4x4/1 convolution over a 2x2 space-to-depth image with
 // 12 channels (zero-extended 8x8 kernel), which gives K = 4 kernel rows x (4 taps x 12 ch = 48, padded to 64).
 // bf16 operands, fp32 accumulation: the 1e-2 tolerance build (north_star); the fp32 build is trunk_fp32.cu.
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -38,6 +40,7 @@ struct ConvTcArgs {
   int N, Hi, Wi, Ci, Ho, Wo, Co, kh, kw, stride, pad;
   int M, num_kb, cblocks, Cg;
   int32_t* error;
+  int debug;                     // profiling knobs (SERL_TC_DEBUG): 1 = skip output stores, 2 = skip statistics, 4 = skip tcgen05.ld
 };
 
 __device__ inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -399,7 +402,11 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t v[16];
-        tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        if (!(a.debug & 4)) tc_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(as * BN + c0), v);
+        else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0x3f800000u;
+        }
         float s = 0.f, ss = 0.f;
         uint32_t pk[8];
 #pragma unroll
@@ -409,13 +416,15 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
           pk[j] = F::pack(f0, f1);
         }
         if (!ok) { s = 0.f; ss = 0.f; }
-        s = warp_sum(s); ss = warp_sum(ss);
-        if (ok) {
-          if (lane == 0) { float* st = a.stats + ((size_t)n_img * 4 + c0 / 16) * 2; atomicAdd(st, s); atomicAdd(st + 1, ss); }
+        if (!(a.debug & 2)) {
+          s = warp_sum(s); ss = warp_sum(ss);
+          if (ok && lane == 0) { float* st = a.stats + ((size_t)n_img * 4 + c0 / 16) * 2; atomicAdd(st, s); atomicAdd(st + 1, ss); }
+        }
+        if (ok && !(a.debug & 1)) {
           uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)gm * BN + c0);
           dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        } else if (ok && pk[0] == 0x12345678u) { a.y[gm] = (uint16_t)pk[1]; }     // keep the values live
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -722,6 +731,7 @@ extern "C" int serl_conv2d_tc_h16(const serl_conv_tc_desc* d, void* stream) {
   a.stats = d->stats; a.in_a = d->in_a; a.in_b = d->in_b; a.error = d->error;
   a.N = d->N; a.Hi = d->Hi; a.Wi = d->Wi; a.Ci = d->Ci; a.Co = d->Co; a.kh = d->kh; a.kw = d->kw; a.stride = d->stride; a.pad = d->pad_lo;
   a.Ho = d->Ho; a.Wo = d->Wo; a.M = d->N * d->Ho * d->Wo; a.Cg = d->Co / 4;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SERL_TC_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
   const int HoWo = d->Ho * d->Wo;
   if (d->Co % 64 != 0 || (HoWo & (HoWo - 1)) != 0 || HoWo < 16) {
     set_last_error("serl_conv2d_tc_h16: unsupported shape (Co=%d Ho*Wo=%d)", d->Co, HoWo); return SERL_ERR_UNSUPPORTED;
