@@ -206,10 +206,12 @@ __global__ void __launch_bounds__(kSamplerThreads) sample_gather_crop_kernel(con
 // ---------------------------------------------------------------------------------------------
 // Fast path (row_bytes % 16 == 0): ONE CTA per (row, camera, obs|next) streams its whole frame(s).
 // The serial preamble runs once per frame instead of once per band and is spread over two warps (warp 0: Philox index
-// draw; warp 1: the threefry crop-key chain, two lanes wide, three evaluations deep); the four 32-row bands are then
-// double-buffered: the TMA bulk copy of band k+1 is in flight while band k is shifted and written back.
+// draw; warp 1: the threefry crop-key chain, two lanes wide, three evaluations deep); the 32-row bands of a frame are then
+// all fetched at once (one TMA bulk copy + mbarrier per band, 48 KiB of shared memory per CTA) and shifted / written back
+// in arrival order, so a CTA pays one memory round trip per frame instead of one per band.
 // ---------------------------------------------------------------------------------------------
 constexpr int kFrameThreads = 256;
+constexpr int kMaxBands = 8;             // frames up to 256 rows
 
 // crop offsets for frame g, computed cooperatively by lanes 0/1 of a full warp (all 32 lanes must call)
 __device__ inline void crop_offset_warp(const uint32_t* key, const int32_t* expl, int crop_total, int g, int span, int lane,
@@ -239,7 +241,7 @@ __device__ inline void crop_offset_warp(const uint32_t* key, const int32_t* expl
 // grid: x = cam*2 + which, y = row i.
 __global__ void __launch_bounds__(kFrameThreads) sample_frames_kernel(const SamplerArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ uint64_t bar[2];
+  __shared__ uint64_t bar[kMaxBands];
   __shared__ int s_idx, s_cy[8], s_cx[8];
 
   const serl_replay_view& rv = a.rv;
@@ -256,7 +258,7 @@ __global__ void __launch_bounds__(kFrameThreads) sample_frames_kernel(const Samp
     const int idx = a.explicit_idx ? a.explicit_idx[i] : draw_index(a, a.lane_offset + (uint32_t)i);
     s_idx = idx;
     if (idx < 0) atomicOr(a.status, 1);
-    mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+    for (int b = 0; b < kMaxBands; ++b) mbar_init(&bar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -290,57 +292,56 @@ __global__ void __launch_bounds__(kFrameThreads) sample_frames_kernel(const Samp
   }
 
   const size_t frame_bytes = (size_t)H * row_bytes;
-  const int nb = ceil_div(H, kBandRows), total = T * nb;
+  const int nb = ceil_div(H, kBandRows);                   // <= kMaxBands, all in flight at once
   const int cpr = row_bytes >> 4;
-  auto issue = [&](int it) {                               // thread 0: TMA bulk copy of band `it` into buffer it & 1
-    const int t = it / nb, band = it - t * nb;
-    const int y0 = band * kBandRows, rows = min(kBandRows, H - y0);
-    const int dy = s_cy[t] - a.padding;
-    const int r_lo = min(max(y0 + dy, 0), H - 1), r_hi = min(max(y0 + rows - 1 + dy, 0), H - 1);
-    const uint32_t nbytes = (uint32_t)(r_hi - r_lo + 1) * row_bytes;
-    const uint8_t* src = rv.frames[cam] + (size_t)(idx - T + t + which) * frame_bytes + (size_t)r_lo * row_bytes;
-    mbar_expect_tx(&bar[it & 1], nbytes);
-    bulk_g2s(smem + (it & 1) * band_bytes, src, nbytes, &bar[it & 1]);
-  };
-  if (threadIdx.x == 0) issue(0);
-  for (int it = 0; it < total; ++it) {
-    if (threadIdx.x == 0 && it + 1 < total) issue(it + 1);  // the other buffer was released by the barrier below
-    mbar_wait(&bar[it & 1], (uint32_t)(it >> 1) & 1u);
-    const int t = it / nb, band = it - t * nb;
-    const int y0 = band * kBandRows, rows = min(kBandRows, H - y0);
+  for (int t = 0; t < T; ++t) {
     const int cy = s_cy[t], cx = s_cx[t];
     const int dy = cy - a.padding, sh = (cx - a.padding) * C;
-    const int r_lo = min(max(y0 + dy, 0), H - 1);
-    const uint8_t* sb = smem + (it & 1) * band_bytes;
-    const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sb);
-    const int g = out_row * T + t;
-    uint8_t* dst = (which ? a.next_pix[cam] : a.obs_pix[cam]) + ((size_t)g * H + y0) * row_bytes;
-    for (int q = threadIdx.x; q < rows * cpr; q += blockDim.x) {
-      const int yl = q / cpr, jj = q - yl * cpr;
-      const int r = min(max(y0 + yl + dy, 0), H - 1) - r_lo;
-      const int b0 = jj * 16, a0 = b0 + sh;
-      uint4 v;
-      if (a0 >= 0 && a0 + 16 <= row_bytes) {
-        const int base = r * row_bytes + a0;
-        const int wi = base >> 2, bs = (base & 3) * 8;
-        const uint32_t w0 = s32[wi], w1 = s32[wi + 1], w2 = s32[wi + 2], w3 = s32[wi + 3], w4 = s32[wi + 4];
-        v.x = __funnelshift_r(w0, w1, bs); v.y = __funnelshift_r(w1, w2, bs);
-        v.z = __funnelshift_r(w2, w3, bs); v.w = __funnelshift_r(w3, w4, bs);
-      } else {
-        uint32_t o[4] = {0, 0, 0, 0};
-#pragma unroll
-        for (int b = 0; b < 16; ++b) {
-          const int ob = b0 + b;
-          const int x = ob / C, ch = ob - x * C;
-          const int xs = min(max(x + cx - a.padding, 0), W - 1);
-          o[b >> 2] |= (uint32_t)sb[r * row_bytes + xs * C + ch] << ((b & 3) * 8);
-        }
-        v = make_uint4(o[0], o[1], o[2], o[3]);
+    if (threadIdx.x == 0) {                                // one TMA bulk copy per band, each with its own mbarrier
+      const uint8_t* fsrc = rv.frames[cam] + (size_t)(idx - T + t + which) * frame_bytes;
+      for (int band = 0; band < nb; ++band) {
+        const int y0 = band * kBandRows, rows = min(kBandRows, H - y0);
+        const int r_lo = min(max(y0 + dy, 0), H - 1), r_hi = min(max(y0 + rows - 1 + dy, 0), H - 1);
+        const uint32_t nbytes = (uint32_t)(r_hi - r_lo + 1) * row_bytes;
+        mbar_expect_tx(&bar[band], nbytes);
+        bulk_g2s(smem + band * band_bytes, fsrc + (size_t)r_lo * row_bytes, nbytes, &bar[band]);
       }
-      asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)yl * row_bytes + b0),
-                   "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
     }
-    __syncthreads();                                       // buffer it & 1 may be refilled (by issue(it + 2)) after this
+    const int g = out_row * T + t;
+    for (int band = 0; band < nb; ++band) {
+      mbar_wait(&bar[band], (uint32_t)t & 1u);
+      const int y0 = band * kBandRows, rows = min(kBandRows, H - y0);
+      const int r_lo = min(max(y0 + dy, 0), H - 1);
+      const uint8_t* sb = smem + band * band_bytes;
+      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sb);
+      uint8_t* dst = (which ? a.next_pix[cam] : a.obs_pix[cam]) + ((size_t)g * H + y0) * row_bytes;
+      for (int q = threadIdx.x; q < rows * cpr; q += blockDim.x) {
+        const int yl = q / cpr, jj = q - yl * cpr;
+        const int r = min(max(y0 + yl + dy, 0), H - 1) - r_lo;
+        const int b0 = jj * 16, a0 = b0 + sh;
+        uint4 v;
+        if (a0 >= 0 && a0 + 16 <= row_bytes) {
+          const int base = r * row_bytes + a0;
+          const int wi = base >> 2, bs = (base & 3) * 8;
+          const uint32_t w0 = s32[wi], w1 = s32[wi + 1], w2 = s32[wi + 2], w3 = s32[wi + 3], w4 = s32[wi + 4];
+          v.x = __funnelshift_r(w0, w1, bs); v.y = __funnelshift_r(w1, w2, bs);
+          v.z = __funnelshift_r(w2, w3, bs); v.w = __funnelshift_r(w3, w4, bs);
+        } else {
+          uint32_t o[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int b = 0; b < 16; ++b) {
+            const int ob = b0 + b;
+            const int x = ob / C, ch = ob - x * C;
+            const int xs = min(max(x + cx - a.padding, 0), W - 1);
+            o[b >> 2] |= (uint32_t)sb[r * row_bytes + xs * C + ch] << ((b & 3) * 8);
+          }
+          v = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)yl * row_bytes + b0),
+                     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+      }
+    }
+    __syncthreads();                                       // every band buffer is free again for the next stacked frame
   }
 }
 
@@ -448,8 +449,14 @@ extern "C" int serl_replay_sample_crop(const serl_replay_view* rv, const serl_sa
   dim3 grid(ceil_div(rv->height, kBandRows), rv->num_cams * 2 * rv->num_stack, rq->batch);
   if (rv->num_cams == 0) grid = dim3(1, 1, rq->batch);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (fast && rv->num_stack <= 8) {
-    const size_t smem = 2 * ((size_t)kBandRows * row_bytes + 32);
+  if (fast && rv->num_stack <= 8 && ceil_div(rv->height, kBandRows) <= kMaxBands &&
+      (size_t)ceil_div(rv->height, kBandRows) * ((size_t)kBandRows * row_bytes + 32) <= 96 * 1024) {
+    const size_t smem = (size_t)ceil_div(rv->height, kBandRows) * ((size_t)kBandRows * row_bytes + 32);
+    static size_t configured = 0;
+    if (smem > configured) {
+      if (cudaFuncSetAttribute(sample_frames_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(sample_frames)");
+      configured = smem;
+    }
     dim3 fgrid(rv->num_cams * 2, rq->batch);
     sample_frames_kernel<<<fgrid, kFrameThreads, smem, st>>>(a);
     return check_launch("sample_frames_kernel");
