@@ -315,30 +315,39 @@ __global__ void __launch_bounds__(kFrameThreads) sample_frames_kernel(const Samp
       const uint8_t* sb = smem + band * band_bytes;
       const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sb);
       uint8_t* dst = (which ? a.next_pix[cam] : a.obs_pix[cam]) + ((size_t)g * H + y0) * row_bytes;
+      // interior chunks: pure funnel-shift copies (no divergence); the <= 1-2 chunks per row that touch the clamped edge
+      // are handled by a second, compact loop so that no warp pays the per-byte path for its 31 interior lanes
       for (int q = threadIdx.x; q < rows * cpr; q += blockDim.x) {
         const int yl = q / cpr, jj = q - yl * cpr;
-        const int r = min(max(y0 + yl + dy, 0), H - 1) - r_lo;
         const int b0 = jj * 16, a0 = b0 + sh;
-        uint4 v;
         if (a0 >= 0 && a0 + 16 <= row_bytes) {
+          const int r = min(max(y0 + yl + dy, 0), H - 1) - r_lo;
           const int base = r * row_bytes + a0;
           const int wi = base >> 2, bs = (base & 3) * 8;
           const uint32_t w0 = s32[wi], w1 = s32[wi + 1], w2 = s32[wi + 2], w3 = s32[wi + 3], w4 = s32[wi + 4];
-          v.x = __funnelshift_r(w0, w1, bs); v.y = __funnelshift_r(w1, w2, bs);
-          v.z = __funnelshift_r(w2, w3, bs); v.w = __funnelshift_r(w3, w4, bs);
-        } else {
-          uint32_t o[4] = {0, 0, 0, 0};
+          asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)yl * row_bytes + b0),
+                       "r"(__funnelshift_r(w0, w1, bs)), "r"(__funnelshift_r(w1, w2, bs)), "r"(__funnelshift_r(w2, w3, bs)),
+                       "r"(__funnelshift_r(w3, w4, bs)) : "memory");
+        }
+      }
+      const int ne_l = sh < 0 ? min(cpr, (-sh + 15) >> 4) : 0, ne_r = sh > 0 ? min(cpr - ne_l, (sh + 15) >> 4) : 0;
+      const int ne = ne_l + ne_r;
+      for (int e = threadIdx.x; e < rows * ne; e += blockDim.x) {
+        const int yl = e / ne, k = e - yl * ne;
+        const int jj = k < ne_l ? k : cpr - ne_r + (k - ne_l);
+        const int r = min(max(y0 + yl + dy, 0), H - 1) - r_lo;
+        const int b0 = jj * 16;
+        uint32_t o[4] = {0, 0, 0, 0};
 #pragma unroll
-          for (int b = 0; b < 16; ++b) {
-            const int ob = b0 + b;
-            const int x = ob / C, ch = ob - x * C;
-            const int xs = min(max(x + cx - a.padding, 0), W - 1);
-            o[b >> 2] |= (uint32_t)sb[r * row_bytes + xs * C + ch] << ((b & 3) * 8);
-          }
-          v = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int b = 0; b < 16; ++b) {
+          const int ob = b0 + b;
+          const int x = (C == 3 && ob < 65536) ? (int)(((uint32_t)ob * 43691u) >> 17) : ob / C;
+          const int ch = ob - x * C;
+          const int xs = min(max(x + cx - a.padding, 0), W - 1);
+          o[b >> 2] |= (uint32_t)sb[r * row_bytes + xs * C + ch] << ((b & 3) * 8);
         }
         asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)yl * row_bytes + b0),
-                     "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+                     "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
       }
     }
     __syncthreads();                                       // every band buffer is free again for the next stacked frame
