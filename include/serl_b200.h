@@ -162,6 +162,9 @@ typedef struct serl_gemm_desc {
   int32_t reduce_z;                             /* single C = sum over z                           */
 } serl_gemm_desc;
 int serl_gemm_f32(const serl_gemm_desc* d, void* stream);
+/* Same contract on the tensor cores: fp32 operands split into TF32 hi + lo parts, three tcgen05.mma (kind::tf32) products
+ * per k-step accumulated in fp32 TMEM ("3xTF32": fp32-class accuracy, ~2^-22 per product).  Heads of the 16-bit builds. */
+int serl_gemm_tf32x3(const serl_gemm_desc* d, void* stream);
 
 /* SpatialLearnedEmbeddings (vision/resnet_v1.py:81-116) + Dropout (resnet_v1.py:352) */
 int serl_sle_fwd(const float* feat, const float* kernel, const uint8_t* keep_mask, float keep, float* out,

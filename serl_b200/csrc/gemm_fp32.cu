@@ -9,20 +9,12 @@
 //   C[z](m, n) = sum_k A[z](m, k) * B[z](k, n) (+ bias[z](n)) (+ C[z](m, n) if accumulate)
 // with element addresses A + z*sAz + m*sAm + k*sAk, B + z*sBz + k*sBk + n*sBn, C + z*sCz + m*ldc + n.
 // reduce_z: a single C = sum_z (...)  (used for dX = sum_e dZ_e W_e^T of the broadcast ensemble input).
-#include "common.cuh"
+#include "gemm_common.cuh"
 #include "serl_b200.h"
 
 namespace serl {
 
 constexpr int GM = 64, GN = 64, GK = 16;
-
-struct GemmArgs {
-  const float* A; const float* B; float* C; const float* bias; float* ws;
-  int M, N, K, Z, S;                 // S = k-splits
-  long long sAz, sAm, sAk, sBz, sBk, sBn, sCz, sBiasZ;
-  int ldc;
-  int accumulate, to_ws;
-};
 
 constexpr int GSTAGES = 4;
 
@@ -116,22 +108,6 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs g) {
   }
 }
 
-// C[zc](m,n) = sum_{parts} ws[part](m,n) + bias + (accumulate ? C : 0); parts of zc: reduce_z ? all Z*S : S.
-__global__ void gemm_reduce_kernel(const GemmArgs g, int reduce_z) {
-  const int ZC = reduce_z ? 1 : g.Z;
-  const size_t MN = (size_t)g.M * g.N, total = MN * ZC;
-  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-    const int zc = (int)(e / MN); const size_t mn = e - (size_t)zc * MN;
-    const int m = (int)(mn / g.N), n = (int)(mn - (size_t)m * g.N);
-    const int p0 = reduce_z ? 0 : zc * g.S, np = reduce_z ? g.Z * g.S : g.S;
-    float v = 0.f;
-    for (int p = 0; p < np; ++p) v += g.ws[(size_t)(p0 + p) * MN + mn];
-    if (g.bias) v += (g.bias + zc * g.sBiasZ)[n];
-    float* c = g.C + zc * g.sCz + (size_t)m * g.ldc + n;
-    *c = g.accumulate ? (*c + v) : v;
-  }
-}
-
 }  // namespace serl
 
 using namespace serl;
@@ -169,10 +145,7 @@ extern "C" int serl_gemm_f32(const serl_gemm_desc* d, void* stream) {
   gemm_f32_kernel<<<grid, 256, 0, st>>>(g);
   if (int e = check_launch("gemm_f32_kernel")) return e;
   if (g.to_ws) {
-    size_t total = (size_t)d->M * d->N * (d->reduce_z ? 1 : d->Z);
-    int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-    gemm_reduce_kernel<<<blocks, 256, 0, st>>>(g, d->reduce_z);
-    return check_launch("gemm_reduce_kernel");
+    return launch_gemm_reduce(g, d->reduce_z, st);
   }
   return SERL_OK;
 }

@@ -13,6 +13,8 @@ common/common.py:124-221 (see oracle/drq.py for the restatement this is tested a
 """
 from __future__ import annotations
 
+import os
+
 from dataclasses import dataclass
 from typing import Dict, Optional, Sequence
 
@@ -65,7 +67,9 @@ class Engine:
         B, E, A, F = batch, cfg.ensemble, cfg.action_dim, cfg.enc_dim
         self.F, self.FA = F, F + A
         e = lambda *s: torch.empty(*s, dtype=f32, device=device)
-        self.ws = ops.Workspace(max(48 << 20, 2 * 4 * E * B * self.FA), device)
+        # heads GEMMs: CUDA-core SGEMM in the 1e-5 build, tensor-core 3xTF32 (fp32-class accuracy) next to the 16-bit trunk
+        gemm_impl = os.environ.get("SERL_HEADS_GEMM") or ("f32" if cfg.precision == "fp32" else "tf32x3")
+        self.ws = ops.Workspace(max(48 << 20, 2 * 4 * E * B * self.FA), device, gemm_impl)
         # batch tensors
         self.state_o, self.state_n = e(B, cfg.state_in), e(B, cfg.state_in)
         self.actions, self.rewards, self.masks = e(B, A), e(B), e(B)

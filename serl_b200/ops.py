@@ -55,9 +55,12 @@ def maxpool3x3s2_nhwc(x, y):
 class Workspace:
     """Caller-owned scratch for split-K / batch-reduce partials."""
 
-    def __init__(self, nbytes: int, device):
+    GEMM_IMPLS = {"f32": "serl_gemm_f32", "tf32x3": "serl_gemm_tf32x3"}
+
+    def __init__(self, nbytes: int, device, gemm_impl: str = "f32"):
         self.buf = torch.empty(nbytes // 4, dtype=torch.float32, device=device)
         self.nbytes = self.buf.numel() * 4
+        self.gemm_fn = self.GEMM_IMPLS[gemm_impl]      # CUDA-core SGEMM (1e-5 build) or tensor-core 3xTF32 (speed builds)
 
 
 def gemm(ws: Workspace, A_ptr, B_ptr, C_ptr, M, N, K, *, sAm, sAk, sBk, sBn, ldc, Z=1, sAz=0, sBz=0, sCz=0,
@@ -68,7 +71,7 @@ def gemm(ws: Workspace, A_ptr, B_ptr, C_ptr, M, N, K, *, sAm, sAk, sBk, sBn, ldc
     d.M, d.N, d.K, d.Z = M, N, K, Z
     d.sAz, d.sAm, d.sAk, d.sBz, d.sBk, d.sBn, d.sCz, d.sBiasZ = sAz, sAm, sAk, sBz, sBk, sBn, sCz, sBiasZ
     d.ldc, d.accumulate, d.reduce_z = ldc, int(accumulate), int(reduce_z)
-    L.call("serl_gemm_f32", C.byref(d), _s())
+    L.call(ws.gemm_fn, C.byref(d), _s())
 
 
 def at(t: torch.Tensor, elem_offset: int = 0) -> int:

@@ -62,11 +62,14 @@ def test_maxpool():
     np.testing.assert_array_equal(y.cpu().numpy(), max_pool_3x3_s2_same(torch.as_tensor(x)).numpy())
 
 
-@pytest.mark.parametrize("M,K,N,Z", [(37, 4096, 256, 1), (256, 580, 256, 10), (256, 256, 1, 1), (19, 7, 64, 1), (64, 256, 4, 1)])
-def test_dense_fwd_bwd(M, K, N, Z):
+@pytest.mark.parametrize("impl", ["f32", "tf32x3"])
+@pytest.mark.parametrize("M,K,N,Z", [(37, 4096, 256, 1), (256, 580, 256, 10), (256, 256, 1, 1), (19, 7, 64, 1), (64, 256, 4, 1),
+                                     (512, 4096, 256, 1), (256, 327, 256, 2), (130, 100, 70, 3)])
+def test_dense_fwd_bwd(M, K, N, Z, impl):
+    """Both GEMM carriers (CUDA-core SGEMM, tensor-core 3xTF32) against an fp64 einsum: same 1e-5 bar."""
     from serl_b200 import ops
     rng = np.random.default_rng(3)
-    ws = ops.Workspace(64 << 20, "cuda")
+    ws = ops.Workspace(64 << 20, "cuda", impl)
     x = rng.standard_normal((Z, M, K)).astype(np.float32)
     w = (rng.standard_normal((Z, K, N)) / np.sqrt(K)).astype(np.float32)
     b = rng.standard_normal((Z, N)).astype(np.float32)
@@ -86,6 +89,38 @@ def test_dense_fwd_bwd(M, K, N, Z):
     dxs = torch.empty(M, K, device="cuda")                                   # broadcast input: sum over the ensemble
     ops.dense_bwd_input(ws, dzd.data_ptr(), N, wd.data_ptr(), dxs.data_ptr(), K, M, K, N, Z=Z, dz_z=M * N, reduce_z=True)
     assert rel_err(dxs.cpu().numpy(), refdx.sum(0)) < TOL
+
+
+def test_gemm_tf32x3_misaligned_and_accumulate():
+    """4-byte staging modes (operands at odd float offsets / odd leading dimensions), bias, accumulate and bit-exact
+    agreement of repeated launches (deterministic split-K)."""
+    from serl_b200 import ops
+    rng = np.random.default_rng(13)
+    ws = ops.Workspace(64 << 20, "cuda", "tf32x3")
+    M, K, N = 200, 1000, 90
+    lda, ldb, ldc = K + 3, N + 1, N + 5
+    a = rng.standard_normal((M, lda)).astype(np.float32)
+    b = rng.standard_normal((K, ldb)).astype(np.float32)
+    bias = rng.standard_normal(N).astype(np.float32)
+    c0 = rng.standard_normal((M, ldc)).astype(np.float32)
+    buf_a, buf_b = cu(np.concatenate([[0.0], a.ravel()]).astype(np.float32)), cu(np.concatenate([[0.0], b.ravel()]).astype(np.float32))
+    bd = cu(bias)
+    ref = a[:, :K].astype(np.float64) @ b[:, :N].astype(np.float64) + bias
+    outs = []
+    for _ in range(2):
+        c = cu(c0)
+        ops.gemm(ws, buf_a.data_ptr() + 4, buf_b.data_ptr() + 4, c.data_ptr(), M, N, K, sAm=lda, sAk=1, sBk=ldb, sBn=1, ldc=ldc,
+                 bias_ptr=bd.data_ptr(), accumulate=True)
+        outs.append(c.cpu().numpy())
+    np.testing.assert_array_equal(outs[0], outs[1])
+    assert rel_err(outs[0][:, :N], ref + c0[:, :N]) < TOL
+    np.testing.assert_array_equal(outs[0][:, N:], c0[:, N:])                 # nothing written past column N
+    # transposed operands at odd offsets: C = A^T B with A (K,M) and B^T (N,K) storage
+    at_, bt_ = np.ascontiguousarray(a[:, :K].T), np.ascontiguousarray(b[:, :N].T)
+    buf_at, buf_bt = cu(np.concatenate([[0.0], at_.ravel()]).astype(np.float32)), cu(np.concatenate([[0.0], bt_.ravel()]).astype(np.float32))
+    c = torch.empty(M, N, device="cuda")
+    ops.gemm(ws, buf_at.data_ptr() + 4, buf_bt.data_ptr() + 4, c.data_ptr(), M, N, K, sAm=1, sAk=M, sBk=1, sBn=K, ldc=N)
+    assert rel_err(c.cpu().numpy(), ref - bias) < TOL
 
 
 def test_sle_fwd_bwd_and_dropout():
