@@ -141,6 +141,19 @@ int serl_conv2d_tc_h16(const serl_conv_tc_desc* d, void* stream);
  * in shared memory and the nine taps are shifted UMMA descriptors over it; weights arrive by TMA.  Same descriptor as
  * above (kh=kw=3, stride=1, pad_lo=1, no operand transform).  base_offset_mode: 0 = descriptor base_offset field left 0. */
 int serl_conv3x3s1_tc_h16(const serl_conv_tc_desc* d, int base_offset_mode, void* stream);
+/* conv_init (7x7/2 as a 4x4/1 conv over the space-to-depth image) FUSED with the 3x3/2 SAME max-pool that follows its
+ * GroupNorm + ReLU (vision/resnet_v1.py:247-261).  relu(a*x+b) is monotone in x with the sign of the frozen GroupNorm
+ * scale, so the pool runs on the raw sign-adjusted conv output inside the epilogue and the 64x64 map never reaches HBM.
+ * xs (N,67,67,16) from serl_trunk_stem_prep_h16; w = packed stem weights; pooled (N,32,32,64); side (N,4,32,64);
+ * stats (N,4,2) GroupNorm sums of the raw conv output; neg_mask bit c = (scale[c] < 0).
+ * serl_pool_finish_h16 then writes y = relu(|a| * pooled' + b) with (a, b) from serl_gn_finalize. */
+typedef struct serl_stem_pool_desc {
+  const void* xs; const void* w; void* pooled; void* side; float* stats; int32_t* error;
+  uint64_t neg_mask;
+  int32_t N, fmt;
+} serl_stem_pool_desc;
+int serl_stem_conv_pool_tc_h16(const serl_stem_pool_desc* d, void* stream);
+int serl_pool_finish_h16(const void* pooled, const void* side, const float* a, const float* b, void* y, int N, int fmt, void* stream);
 /* (N,4,2) sums -> per-(image, channel) affine a = rstd*gamma, b = beta - mean*a (flax GroupNorm statistics) */
 int serl_gn_finalize(const float* stats, const float* gamma, const float* beta, float* out_a, float* out_b, int N, int C,
                      int HW, float eps, void* stream);

@@ -57,6 +57,11 @@ class ConvTcDesc(C.Structure):
                 ("kw", i32), ("stride", i32), ("pad_lo", i32), ("stem", i32), ("fmt", i32)]
 
 
+class StemPoolDesc(C.Structure):
+    _fields_ = [("xs", vp), ("w", vp), ("pooled", vp), ("side", vp), ("stats", vp), ("error", vp), ("neg_mask", C.c_uint64),
+                ("N", i32), ("fmt", i32)]
+
+
 class AdamDesc(C.Structure):
     _fields_ = [("params", vp), ("target", vp), ("m", vp), ("v", vp), ("grad", vp), ("n", i32), ("seg_end", i32 * 3),
                 ("live", i32 * 3), ("counts", vp), ("lr", f32 * 3), ("warmup", i32 * 3), ("b1", f32), ("b2", f32),
@@ -85,6 +90,8 @@ _PROTOS = {
     "serl_conv3x3s1_tc_h16": [C.POINTER(ConvTcDesc), C.c_int, vp],
     "serl_gn_finalize": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp],
     "serl_affine_relu_h16": [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "serl_stem_conv_pool_tc_h16": [C.POINTER(StemPoolDesc), vp],
+    "serl_pool_finish_h16": [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp],
     "serl_maxpool_affine_h16": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_block_combine_h16": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_gemm_f32": [C.POINTER(GemmDesc), vp],

@@ -41,6 +41,8 @@ struct ConvTcArgs {
   int M, num_kb, cblocks, Cg;
   int32_t* error;
   int debug;                     // profiling knobs (SERL_TC_DEBUG): 1 = skip output stores, 2 = skip statistics, 4 = skip tcgen05.ld
+  uint16_t* pool_side;           // fused stem + max-pool: (N,4,32,64) first-row column maxima of every 8-tile unit
+  unsigned long long neg_mask;   // fused stem + max-pool: bit c set <=> GroupNorm scale of channel c is negative
 };
 
 __device__ inline uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -92,6 +94,9 @@ struct Bf16 {
   static constexpr uint32_t kUmmaFormat = 1;
   __device__ static inline uint32_t pack(float lo, float hi) { __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&v); }
   __device__ static inline float2 unpack(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u)); }
+  __device__ static inline uint32_t max2(uint32_t a, uint32_t b) {
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b)); return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 struct Fp16 {
   static constexpr uint32_t kUmmaFormat = 0;
@@ -100,6 +105,9 @@ struct Fp16 {
     return *reinterpret_cast<uint32_t*>(&v);
   }
   __device__ static inline float2 unpack(uint32_t u) { return __half22float2(*reinterpret_cast<__half2*>(&u)); }
+  __device__ static inline uint32_t max2(uint32_t a, uint32_t b) {
+    __half2 r = __hmax2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b)); return *reinterpret_cast<uint32_t*>(&r);
+  }
 };
 template <class F>
 __device__ inline uint32_t affine_relu_x2(uint32_t u, float a0, float b0, float a1, float b1) {
@@ -311,7 +319,19 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
 // im2col k-block tiles shared->shared (each operand row = 4 consecutive s2d pixels = 128 contiguous patch bytes), so the
 // 14.6x redundancy of the im2col view never touches L2.  The 32 KB weight tensor is loaded once and stays resident.
 //   warps 0-3 epilogue | 4-7 patch -> A-tile builders | 8 tcgen05.mma issuer | 9 TMA (weights once, one patch per tile)
+//
+// kPool fuses the 3x3/2 max-pool that follows GroupNorm+ReLU (resnet_v1.py:253-261) into the epilogue, BEFORE the
+// statistics are known: relu(a*x+b) is monotone in x with the sign of a = rstd*gamma = the sign of gamma, a frozen
+// weight, so max_window relu(a*x+b) = relu(|a| * max_window(sgn*x) + b).  The epilogue flips the sign of the channels with
+// negative gamma (neg_mask), packs to 16 bits, and pools through an 8 KB shared staging tile (two 32-channel halves).
+// A tile holds conv rows (2t, 2t+1); pooled row t also needs row 2t+2, the first row of the NEXT tile, so a CTA walks
+// units of 8 consecutive tiles and carries A_t = colpool(max(row 2t, row 2t+1)) in registers:
+//   pooled[t-1] = max(A_{t-1}, B_t),  B_t = colpool(row 2t).
+// At unit boundaries B_t goes to the small side buffer and A_{t-1} is stored as is; serl_pool_finish_h16 joins the two
+// while it applies the affine + ReLU.  The raw 64x64x64 map (268 MB at N=512) is never written: HBM traffic of
+// stem + pool drops from 268 w + 268 r + 67 w to 67 w + 67 r + 67 w.
 // ---------------------------------------------------------------------------------------------
+constexpr int ST_POOL_STAGE = 128 * 64;                                          // 128 positions x 32 channels x 2 B
 constexpr int ST_STAGES = 3;
 constexpr int ST_PATCH_ROWS = 5, ST_PITCH_PX = 67, ST_PX_BYTES = 32;
 constexpr int ST_PATCH_BYTES = ST_PATCH_ROWS * ST_PITCH_PX * ST_PX_BYTES;        // 10720
@@ -322,7 +342,7 @@ __device__ inline void st_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t by
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <class F>
+template <class F, bool kPool>
 __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_constant__ CUtensorMap wmap, const ConvTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -330,7 +350,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
   uint8_t* sA = smem;                                           // ST_STAGES x 16 KiB
   uint8_t* sW = sA + ST_STAGES * TC_A_STAGE;                    // 4 x 8 KiB resident weights
   uint8_t* sP = sW + 4 * W_TILE;                                // 2 patches
-  uint64_t* full = reinterpret_cast<uint64_t*>(sP + 2 * ST_PATCH_ALLOC);
+  uint8_t* sStage = sP + 2 * ST_PATCH_ALLOC;                    // kPool: epilogue staging tile
+  uint64_t* full = reinterpret_cast<uint64_t*>(sStage + (kPool ? ST_POOL_STAGE : 0));
   uint64_t* empty = full + ST_STAGES;
   uint64_t* pfull = empty + ST_STAGES;
   uint64_t* pempty = pfull + 2;
@@ -341,6 +362,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = a.M / TC_BM;                              // N * 32 (M = N * 64 * 64)
+  // q-th tile of this CTA: round-robin over tiles, or over units of 8 consecutive tiles (kPool)
+  auto tile_of = [&](int q) { return kPool ? (((int)blockIdx.x + (q >> 3) * (int)gridDim.x) * 8 + (q & 7)) : ((int)blockIdx.x + q * (int)gridDim.x); };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < ST_STAGES; ++s) { tc_mbar_init(&full[s], 4); tc_mbar_init(&empty[s], 1); }
@@ -363,7 +386,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
     const int tid = threadIdx.x - 128, chunk = tid & 7, rsub = tid >> 3;
     bool ok = true;
     int it = 0, pc = 0;
-    for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++pc) {
+    for (int tile = tile_of(0); tile < n_tiles && ok; tile = tile_of(++pc)) {
       const int pb = pc & 1;
       ok = tc_mbar_wait(&pfull[pb], (uint32_t)((pc >> 1) & 1), a.error);
       const uint8_t* patch = sP + pb * ST_PATCH_ALLOC;
@@ -393,11 +416,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
     // ------------------------------- epilogue (64 x 64 output maps: a warp's 32 rows share one image) -----------------
     bool ok = true;
     int ac = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ac) {
+    uint32_t prevA[2][4];                                        // kPool: A_{t-1} of this thread's (pooled column, 8-channel chunk), per half
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) prevA[h][j] = 0u;
+    const int tid = threadIdx.x;                                 // 0..127
+    for (int tile = tile_of(0); tile < n_tiles; tile = tile_of(++ac)) {
       const int as = ac & 1;
       ok = ok && tc_mbar_wait(&afull[as], (uint32_t)((ac >> 1) & 1), a.error);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int gm = tile * TC_BM + warp * 32 + lane;
+      const int pos = warp * 32 + lane;
+      const int gm = tile * TC_BM + pos;
       const int n_img = gm >> 12;                                // / (64 * 64)
 #pragma unroll
       for (int c0 = 0; c0 < BN; c0 += 16) {
@@ -407,28 +437,80 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = 0x3f800000u;
         }
-        float s = 0.f, ss = 0.f;
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float f0 = __uint_as_float(v[2 * j]), f1 = __uint_as_float(v[2 * j + 1]);
-          s += f0 + f1; ss += f0 * f0 + f1 * f1;
-          pk[j] = F::pack(f0, f1);
+        if (kPool && c0 == BN - 16) {                            // accumulator drained: hand the TMEM stage back early
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(&aempty[as]);
         }
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float f = __uint_as_float(v[j]); s += f; ss += f * f; }
         if (!ok) { s = 0.f; ss = 0.f; }
         if (!(a.debug & 2)) {
           s = warp_sum(s); ss = warp_sum(ss);
           if (ok && lane == 0) { float* st = a.stats + ((size_t)n_img * 4 + c0 / 16) * 2; atomicAdd(st, s); atomicAdd(st + 1, ss); }
         }
-        if (ok && !(a.debug & 1)) {
-          uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)gm * BN + c0);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        } else if (ok && pk[0] == 0x12345678u) { a.y[gm] = (uint16_t)pk[1]; }     // keep the values live
+        uint32_t pk[8];
+        if (kPool) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] ^= (uint32_t)((a.neg_mask >> (c0 + j)) & 1ull) << 31;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pk[j] = F::pack(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+        if (!kPool) {
+          if (ok && !(a.debug & 1)) {
+            uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)gm * BN + c0);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          } else if (ok && pk[0] == 0x12345678u) { a.y[gm] = (uint16_t)pk[1]; }     // keep the values live
+        } else {
+          // staging tile of one 32-channel half: [pos][4 x 16 B], chunk index swizzled by (pos >> 1) & 3
+          const int ch = (c0 & 16) >> 3, sw = (pos >> 1) & 3;
+          uint8_t* row = sStage + pos * 64;
+          *reinterpret_cast<uint4*>(row + ((ch ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(row + (((ch + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (c0 & 16) {                                         // half complete: pool it
+            const int half = c0 >> 5;
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const int j = tid >> 2, qd = tid & 3;                // pooled column, 8-channel chunk of the half
+            uint32_t B[4] = {0u, 0u, 0u, 0u}, R1[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+#pragma unroll
+              for (int dc = 0; dc < 3; ++dc) {
+                const int col = 2 * j + dc;
+                if (col < 64) {
+                  const int p2 = r * 64 + col;
+                  const uint4 u = *reinterpret_cast<const uint4*>(sStage + p2 * 64 + ((qd ^ ((p2 >> 1) & 3)) << 4));
+                  uint32_t* acc = r == 0 ? B : R1;
+                  if (dc == 0) { acc[0] = u.x; acc[1] = u.y; acc[2] = u.z; acc[3] = u.w; }
+                  else { acc[0] = F::max2(acc[0], u.x); acc[1] = F::max2(acc[1], u.y); acc[2] = F::max2(acc[2], u.z); acc[3] = F::max2(acc[3], u.w); }
+                }
+              }
+            }
+            const int t = tile & 31, tt = tile & 7;
+            const size_t cofs = (size_t)j * 64 + half * 32 + qd * 8;
+            if (ok && !(a.debug & 1)) {
+              if (tt != 0) {
+                *reinterpret_cast<uint4*>(a.y + ((size_t)n_img * 32 + (t - 1)) * 2048 + cofs) =
+                    make_uint4(F::max2(prevA[half][0], B[0]), F::max2(prevA[half][1], B[1]), F::max2(prevA[half][2], B[2]), F::max2(prevA[half][3], B[3]));
+              } else if (t != 0) {
+                *reinterpret_cast<uint4*>(a.pool_side + ((size_t)n_img * 4 + (t >> 3)) * 2048 + cofs) = make_uint4(B[0], B[1], B[2], B[3]);
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) prevA[half][i] = F::max2(B[i], R1[i]);
+            if (ok && tt == 7 && !(a.debug & 1))
+              *reinterpret_cast<uint4*>(a.y + ((size_t)n_img * 32 + t) * 2048 + cofs) = make_uint4(prevA[half][0], prevA[half][1], prevA[half][2], prevA[half][3]);
+            asm volatile("bar.sync 1, 128;" ::: "memory");      // staging tile free for the next half
+          }
+        }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      __syncwarp();
-      if (lane == 0) tc_mbar_arrive(&aempty[as]);
+      if (!kPool) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) tc_mbar_arrive(&aempty[as]);
+      }
     }
   } else if (warp == 8) {
     // ------------------------------- MMA issuer (one thread) ------------------------------
@@ -438,7 +520,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
       const uint32_t a_lo = (smem_u32(sA) & 0x3FFFF) >> 4, w_lo = (smem_u32(sW) & 0x3FFFF) >> 4;
       bool ok = tc_mbar_wait(wfull, 0u, a.error);
       int it = 0, ac = 0;
-      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++ac) {
+      for (int tile = tile_of(0); tile < n_tiles && ok; tile = tile_of(++ac)) {
         const int as = ac & 1;
         ok = tc_mbar_wait(&aempty[as], (uint32_t)((ac >> 1) & 1) ^ 1u, a.error);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -464,7 +546,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
       for (int kb = 0; kb < 4; ++kb) tc_tma_2d(sW + kb * W_TILE, &wmap, kb * TC_BK, 0, wfull);
       bool ok = true;
       int pc = 0;
-      for (int tile = blockIdx.x; tile < n_tiles && ok; tile += gridDim.x, ++pc) {
+      for (int tile = tile_of(0); tile < n_tiles && ok; tile = tile_of(++pc)) {
         const int pb = pc & 1;
         ok = tc_mbar_wait(&pempty[pb], (uint32_t)((pc >> 1) & 1) ^ 1u, a.error);
         if (!ok) break;
@@ -582,6 +664,28 @@ __global__ void maxpool_affine_kernel(const uint16_t* __restrict__ x, const floa
   }
 }
 
+// ---- second half of the fused stem max-pool: join unit-boundary rows with the side buffer, then relu(|a|*x' + b) ----
+template <class F>
+__global__ void pool_finish_kernel(const uint16_t* __restrict__ pooled, const uint16_t* __restrict__ side, const float* __restrict__ ga,
+                                   const float* __restrict__ gb, uint16_t* __restrict__ y, int N) {
+  const size_t total = (size_t)N * 32 * 32 * 8;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(e & 7); size_t r = e >> 3;
+    const int j = (int)(r & 31); r >>= 5; const int p = (int)(r & 31); const int n = (int)(r >> 5);
+    uint4 v = *reinterpret_cast<const uint4*>(pooled + e * 8);
+    if ((p & 7) == 7 && p != 31) {
+      const uint4 u = *reinterpret_cast<const uint4*>(side + (((size_t)n * 4 + ((p + 1) >> 3)) * 32 + j) * 64 + c8 * 8);
+      v.x = F::max2(v.x, u.x); v.y = F::max2(v.y, u.y); v.z = F::max2(v.z, u.z); v.w = F::max2(v.w, u.w);
+    }
+    const size_t co = (size_t)n * 64 + c8 * 8;
+    const float4 a0 = *reinterpret_cast<const float4*>(ga + co), a1 = *reinterpret_cast<const float4*>(ga + co + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(gb + co), b1 = *reinterpret_cast<const float4*>(gb + co + 4);
+    v.x = affine_relu_x2<F>(v.x, fabsf(a0.x), b0.x, fabsf(a0.y), b0.y); v.y = affine_relu_x2<F>(v.y, fabsf(a0.z), b0.z, fabsf(a0.w), b0.w);
+    v.z = affine_relu_x2<F>(v.z, fabsf(a1.x), b1.x, fabsf(a1.y), b1.y); v.w = affine_relu_x2<F>(v.w, fabsf(a1.z), b1.z, fabsf(a1.w), b1.w);
+    *reinterpret_cast<uint4*>(y + e * 8) = v;
+  }
+}
+
 // ---- block output: relu( (a2*y2 + b2) + residual ), residual = res (identity) or ar*res + br (projection) ----
 template <class F>
 __global__ void block_combine_kernel(const uint16_t* __restrict__ y2, const float* __restrict__ a2, const float* __restrict__ b2,
@@ -673,10 +777,10 @@ static int launch_conv_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
 using namespace serl;
 #define ST(s) static_cast<cudaStream_t>(s)
 
-template <class F>
+template <class F, bool kPool>
 static int launch_stem_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
-  constexpr size_t smem = (size_t)ST_STAGES * TC_A_STAGE + 4 * 64 * 128 + 2 * ST_PATCH_ALLOC + 1024 + 256;
-  auto kern = stem_tc_kernel<F>;
+  constexpr size_t smem = (size_t)ST_STAGES * TC_A_STAGE + 4 * 64 * 128 + 2 * ST_PATCH_ALLOC + (kPool ? ST_POOL_STAGE : 0) + 1024 + 256;
+  auto kern = stem_tc_kernel<F, kPool>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(stem_tc)");
@@ -695,8 +799,8 @@ static int launch_stem_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
   if (r != CUDA_SUCCESS) { set_last_error("serl_conv2d_tc_h16: cuTensorMapEncodeTiled failed (%d)", (int)r); return SERL_ERR_CUDA; }
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  const int tiles = a.M / TC_BM;
-  const int grid = tiles < 2 * sms ? tiles : 2 * sms;
+  const int work = kPool ? a.M / TC_BM / 8 : a.M / TC_BM;      // units of 8 tiles when the pool is fused
+  const int grid = work < 2 * sms ? work : 2 * sms;
   kern<<<grid, TC_THREADS, smem, st>>>(map, a);
   return check_launch("stem_tc_kernel");
 }
@@ -706,7 +810,7 @@ static int conv_tc_dispatch(const serl_conv_tc_desc* d, ConvTcArgs& a, cudaStrea
   if (d->stem) {
     a.num_kb = 4; a.cblocks = 1;
     // the two-level kernel is specialised for the 128x128 input of every SERL camera (s2d image 67x67, output 64x64)
-    if (d->Hi == 67 && d->Wi == 67 && d->Ho == 64 && d->Wo == 64) return launch_stem_tc<F>(a, d->fmt, st);
+    if (d->Hi == 67 && d->Wi == 67 && d->Ho == 64 && d->Wo == 64) return launch_stem_tc<F, false>(a, d->fmt, st);
     return launch_conv_tc<F, 64, 4, true, false>(a, d->fmt, st);
   }
   a.cblocks = d->Ci / 64; a.num_kb = d->kh * d->kw * a.cblocks;
@@ -739,6 +843,30 @@ extern "C" int serl_conv2d_tc_h16(const serl_conv_tc_desc* d, void* stream) {
   if (d->stem && d->Co != 64) { set_last_error("serl_conv2d_tc_h16: stem expects Co=64"); return SERL_ERR_UNSUPPORTED; }
   if (!d->stem && d->Ci % 64 != 0) { set_last_error("serl_conv2d_tc_h16: Ci %% 64 != 0"); return SERL_ERR_UNSUPPORTED; }
   return d->fmt == SERL_FMT_FP16 ? conv_tc_dispatch<Fp16>(d, a, ST(stream)) : conv_tc_dispatch<Bf16>(d, a, ST(stream));
+}
+
+extern "C" int serl_stem_conv_pool_tc_h16(const serl_stem_pool_desc* d, void* stream) {
+  if (!d || !d->xs || !d->w || !d->pooled || !d->side || !d->stats || !d->error || d->N < 1) {
+    set_last_error("serl_stem_conv_pool_tc_h16: invalid descriptor"); return SERL_ERR_INVALID;
+  }
+  ConvTcArgs a{};
+  a.x = static_cast<const uint16_t*>(d->xs); a.w = static_cast<const uint16_t*>(d->w); a.y = static_cast<uint16_t*>(d->pooled);
+  a.pool_side = static_cast<uint16_t*>(d->side); a.neg_mask = d->neg_mask;
+  a.stats = d->stats; a.error = d->error;
+  a.N = d->N; a.Hi = 67; a.Wi = 67; a.Ci = 12; a.Co = 64; a.kh = 4; a.kw = 4; a.stride = 1; a.pad = 0;
+  a.Ho = 64; a.Wo = 64; a.M = d->N * 64 * 64; a.Cg = 16; a.num_kb = 4; a.cblocks = 1;
+  { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SERL_TC_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
+  return d->fmt == SERL_FMT_FP16 ? launch_stem_tc<Fp16, true>(a, d->fmt, ST(stream)) : launch_stem_tc<Bf16, true>(a, d->fmt, ST(stream));
+}
+
+extern "C" int serl_pool_finish_h16(const void* pooled, const void* side, const float* a, const float* b, void* y, int N, int fmt, void* stream) {
+  const size_t total = (size_t)N * 32 * 32 * 8;
+  int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
+  if (fmt == SERL_FMT_FP16)
+    pool_finish_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(static_cast<const uint16_t*>(pooled), static_cast<const uint16_t*>(side), a, b, static_cast<uint16_t*>(y), N);
+  else
+    pool_finish_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(static_cast<const uint16_t*>(pooled), static_cast<const uint16_t*>(side), a, b, static_cast<uint16_t*>(y), N);
+  return check_launch("pool_finish_kernel");
 }
 
 extern "C" int serl_gn_finalize(const float* stats, const float* gamma, const float* beta, float* out_a, float* out_b, int N, int C,

@@ -177,9 +177,11 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tf32x3_kernel(const GemmArg
     if (kt >= 2) t_mbar_wait(&empty[os], (uint32_t)(((kt >> 1) - 1) & 1));   // MMAs of k-block kt-2 have read this stage
     uint8_t* op = sOp + os * OP_STAGE;
     const float* raw = reinterpret_cast<const float*>(sRaw + (kt % T_RS) * RAW_STAGE);
-    t_convert<TM>(raw, op, op + OP_A, (g.a_mode & 1) != 0, tid);
-    t_convert<TN>(raw + TM * TK, op + 2 * OP_A, op + 2 * OP_A + OP_B, (g.b_mode & 1) != 0, tid);
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic-proxy stores -> tensor-core reads
+    if (!(g.debug & 2)) {
+      t_convert<TM>(raw, op, op + OP_A, (g.a_mode & 1) != 0, tid);
+      t_convert<TN>(raw + TM * TK, op + 2 * OP_A, op + 2 * OP_A + OP_B, (g.b_mode & 1) != 0, tid);
+    }
+    if (!(g.debug & 4)) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");            // generic-proxy stores -> tensor-core reads
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (tid == 0) {
@@ -188,12 +190,16 @@ __global__ void __launch_bounds__(T_THREADS, 1) gemm_tf32x3_kernel(const GemmArg
       const uint64_t a_lo = desc_hi | (uint64_t)((t_smem(op + OP_A) & 0x3FFFF) >> 4);
       const uint64_t b_hi = desc_hi | (uint64_t)((t_smem(op + 2 * OP_A) & 0x3FFFF) >> 4);
       const uint64_t b_lo = desc_hi | (uint64_t)((t_smem(op + 2 * OP_A + OP_B) & 0x3FFFF) >> 4);
+      if (!(g.debug & 8)) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) t_mma(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, (uint32_t)((kt | k) != 0));
+        for (int k = 0; k < 4; ++k) t_mma(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, (uint32_t)((kt | k) != 0));
+        if (!(g.debug & 1)) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) t_mma(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) t_mma(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) t_mma(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+          for (int k = 0; k < 4; ++k) t_mma(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+        }
+      }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_smem(&empty[os])) : "memory");
       if (kt == nk - 1)
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(t_smem(done)) : "memory");
@@ -283,6 +289,7 @@ extern "C" int serl_gemm_tf32x3(const serl_gemm_desc* d, void* stream) {
   g.M = d->M; g.N = d->N; g.K = d->K; g.Z = d->Z;
   g.sAz = d->sAz; g.sAm = d->sAm; g.sAk = d->sAk; g.sBz = d->sBz; g.sBk = d->sBk; g.sBn = d->sBn;
   g.sCz = d->sCz; g.sBiasZ = d->sBiasZ; g.ldc = d->ldc; g.accumulate = d->accumulate;
+  { const char* e = getenv("SERL_GEMM_DEBUG"); g.debug = e ? atoi(e) : 0; }      // profiling knobs (results are wrong when set)
   g.a_mode = pick_mode(d->A, d->sAz, d->sAm, d->sAk, d->Z);
   g.b_mode = pick_mode(d->B, d->sBz, d->sBn, d->sBk, d->Z);
   const int tiles = ceil_div(d->M, TM) * ceil_div(d->N, TN) * d->Z;

@@ -24,6 +24,9 @@ def _s():
 USE_SHIFTED_WINDOW = True
 BASE_OFFSET_MODE = 0
 
+# conv_init + GroupNorm + ReLU + max-pool: pool inside the stem epilogue (the 64x64x64 map never reaches HBM).
+USE_FUSED_STEM_POOL = True
+
 FMT = {"bf16": (L.FMT_BF16, torch.bfloat16), "fp16": (L.FMT_FP16, torch.float16)}
 
 
@@ -55,7 +58,11 @@ class _Plan:
         s2 = hw // 2
         self.hs = s2 + 3
         self.xs = bf(N, self.hs, self.hs, 16)
-        self.y0 = bf(N, s2, s2, 64)
+        self.fused_pool = USE_FUSED_STEM_POOL and hw == 128
+        if self.fused_pool:
+            self.pooled, self.side = bf(N, 32, 32, 64), bf(N, 4, 32, 64)
+        else:
+            self.y0 = bf(N, s2, s2, 64)
         self.buf = [bf(N * (s2 // 2) * (s2 // 2) * 64) for _ in range(5)]
         self.stats = torch.zeros(16, N, 4, 2, dtype=torch.float32, device=dev)     # one slot per conv, zeroed by ONE memset per pass
         self.aff = torch.empty(3, 2, N, 512, dtype=torch.float32, device=dev)
@@ -88,6 +95,8 @@ def packed_weights(engine, cam):
     ver = tuple(t._version for t in w.values())
     if cam not in cache or cache[cam][0] != ver:
         packed = {k: (pack_stem_weight(v, dt) if k == "conv_init/kernel" else pack_conv_weight(v, dt)) for k, v in w.items() if k.endswith("kernel")}
+        # sign of the frozen norm_init scale per channel: which way relu(a*x+b) is monotone (fused stem max-pool)
+        packed["_stem_neg_mask"] = sum(1 << c for c, g in enumerate(w["norm_init/scale"].detach().cpu().tolist()) if g < 0)
         cache[cam] = (ver, packed)
     return cache[cam][1]
 
@@ -105,11 +114,20 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
     p.stats.zero_()
     st = iter(p.stats)
     st0 = next(st)
-    _conv(p, p.xs, wp["conv_init/kernel"], p.y0, st0, N, p.hs, p.hs, 12, s, s, 64, 4, 1, 0, stem=True)
+    if p.fused_pool:
+        d = L.StemPoolDesc()
+        d.xs, d.w, d.pooled, d.side = p.xs.data_ptr(), wp["conv_init/kernel"].data_ptr(), p.pooled.data_ptr(), p.side.data_ptr()
+        d.stats, d.error, d.neg_mask, d.N, d.fmt = st0.data_ptr(), p.error.data_ptr(), wp["_stem_neg_mask"], N, p.fmt
+        L.call("serl_stem_conv_pool_tc_h16", C.byref(d), _s())
+    else:
+        _conv(p, p.xs, wp["conv_init/kernel"], p.y0, st0, N, p.hs, p.hs, 12, s, s, 64, 4, 1, 0, stem=True)
     a0, b0 = _finalize(st0, w["norm_init/scale"], w["norm_init/bias"], p.aff[0], N, 64, s * s)
     s //= 2
     x = p.buf[0][:N * s * s * 64].view(N, s, s, 64)
-    L.call("serl_maxpool_affine_h16", p.y0.data_ptr(), a0.data_ptr(), b0.data_ptr(), x.data_ptr(), N, 2 * s, 2 * s, 64, p.fmt, _s())
+    if p.fused_pool:
+        L.call("serl_pool_finish_h16", p.pooled.data_ptr(), p.side.data_ptr(), a0.data_ptr(), b0.data_ptr(), x.data_ptr(), N, p.fmt, _s())
+    else:
+        L.call("serl_maxpool_affine_h16", p.y0.data_ptr(), a0.data_ptr(), b0.data_ptr(), x.data_ptr(), N, 2 * s, 2 * s, 64, p.fmt, _s())
     engine.launches += 5
     free, cur, cin = [1, 2, 3, 4], 0, 64
     for i, (f, stride) in enumerate(STAGES):

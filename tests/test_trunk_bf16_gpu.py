@@ -91,10 +91,54 @@ def test_stem_space_to_depth_is_the_7x7_conv(prec):
     plan = T._Plan(N, 128, "cuda", prec)
     L.call("serl_trunk_stem_prep_h16", torch.as_tensor(pix).cuda().data_ptr(), plan.xs.data_ptr(), N, 128, 128, plan.fmt, L.stream_ptr())
     stats = torch.zeros(N, 4, 2, device="cuda")
-    T._conv(plan, plan.xs, T.pack_stem_weight(torch.as_tensor(w).cuda(), DT[prec]), plan.y0, stats, N, plan.hs, plan.hs, 12, 64, 64, 64, 4, 1, 0, stem=True)
+    y0 = torch.empty(N, 64, 64, 64, dtype=DT[prec], device="cuda")
+    T._conv(plan, plan.xs, T.pack_stem_weight(torch.as_tensor(w).cuda(), DT[prec]), y0, stats, N, plan.hs, plan.hs, 12, 64, 64, 64, 4, 1, 0, stem=True)
     torch.cuda.synchronize()
     assert int(plan.error.item()) == 0
-    assert rel_err(plan.y0.float().cpu().numpy(), ref.numpy()) < OUT_TOL[prec]
+    assert rel_err(y0.float().cpu().numpy(), ref.numpy()) < OUT_TOL[prec]
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("N", [1, 3, 80])
+def test_fused_stem_pool_equals_conv_then_pool(N, prec):
+    """conv_init with the max-pool folded into its epilogue (sign-adjusted raw maxima + pool_finish) must give the SAME
+    bits as conv -> maxpool(relu(a*x+b)) for the same (a, b): max commutes exactly with a monotone affine + ReLU.
+    Mixed-sign GroupNorm scales exercise both monotonicity directions; N=80 makes CTAs walk several 8-tile units."""
+    from serl_b200 import _lib as L
+    from serl_b200 import trunk_bf16 as T
+    rng = np.random.default_rng(12)
+    pix = torch.as_tensor(rng.integers(0, 256, (N, 128, 128, 3), dtype=np.uint8)).cuda()
+    w = torch.as_tensor((rng.standard_normal((7, 7, 3, 64)) * np.sqrt(2.0 / 147)).astype(np.float32)).cuda()
+    gamma = torch.as_tensor((rng.standard_normal(64) + 0.3).astype(np.float32)).cuda()
+    gamma[5] = 0.0
+    beta = torch.as_tensor((0.2 * rng.standard_normal(64)).astype(np.float32)).cuda()
+    wp = T.pack_stem_weight(w, DT[prec])
+    plan = T._Plan(N, 128, "cuda", prec)
+    s = L.stream_ptr()
+    L.call("serl_trunk_stem_prep_h16", pix.data_ptr(), plan.xs.data_ptr(), N, 128, 128, plan.fmt, s)
+    # separate path: raw conv -> finalize -> pool(relu(affine))
+    st_ref = torch.zeros(N, 4, 2, device="cuda")
+    y0 = torch.empty(N, 64, 64, 64, dtype=DT[prec], device="cuda")
+    T._conv(plan, plan.xs, wp, y0, st_ref, N, plan.hs, plan.hs, 12, 64, 64, 64, 4, 1, 0, stem=True)
+    aff = torch.empty(2, N, 64, device="cuda")
+    a, b = T._finalize(st_ref, gamma, beta, aff, N, 64, 64 * 64)
+    ref = torch.empty(N, 32, 32, 64, dtype=DT[prec], device="cuda")
+    L.call("serl_maxpool_affine_h16", y0.data_ptr(), a.data_ptr(), b.data_ptr(), ref.data_ptr(), N, 64, 64, 64, plan.fmt, s)
+    # fused path
+    st = torch.zeros(N, 4, 2, device="cuda")
+    pooled = torch.full((N, 32, 32, 64), float("nan"), dtype=DT[prec], device="cuda")
+    side = torch.full((N, 4, 32, 64), float("nan"), dtype=DT[prec], device="cuda")
+    d = L.StemPoolDesc()
+    d.xs, d.w, d.pooled, d.side, d.stats, d.error = plan.xs.data_ptr(), wp.data_ptr(), pooled.data_ptr(), side.data_ptr(), st.data_ptr(), plan.error.data_ptr()
+    d.neg_mask = sum(1 << c for c, g in enumerate(gamma.cpu().tolist()) if g < 0)
+    d.N, d.fmt = N, plan.fmt
+    L.call("serl_stem_conv_pool_tc_h16", C.byref(d), s)
+    out = torch.empty(N, 32, 32, 64, dtype=DT[prec], device="cuda")
+    L.call("serl_pool_finish_h16", pooled.data_ptr(), side.data_ptr(), a.data_ptr(), b.data_ptr(), out.data_ptr(), N, plan.fmt, s)
+    torch.cuda.synchronize()
+    assert int(plan.error.item()) == 0
+    np.testing.assert_allclose(st.cpu().numpy(), st_ref.cpu().numpy(), rtol=1e-4, atol=1e-2)   # atomics: order differs
+    assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
 
 
 @pytest.mark.parametrize("prec,feat_tol,q_tol", [("fp16", 5e-3, 1e-2), ("bf16", 3e-2, 3e-2)])
