@@ -181,5 +181,50 @@ def new_event():
     return _Event()
 
 
+class _Side:
+    """A side stream with fork / join against the CURRENT stream (works eagerly and under CUDA-graph capture, where the
+    event dependencies become fork / join edges of the captured graph).  Entering it makes it the current stream."""
+
+    def __init__(self, device):
+        import torch
+        self.s = torch.cuda.Stream(device)
+        self._ctx = None
+
+    def fork(self):                 # side stream waits for everything enqueued on the current stream so far
+        import torch
+        e = torch.cuda.Event()
+        e.record()
+        self.s.wait_event(e)
+
+    def join(self):                 # current stream waits for everything enqueued on the side stream so far
+        import torch
+        e = torch.cuda.Event()
+        e.record(self.s)
+        torch.cuda.current_stream().wait_event(e)
+
+    def __enter__(self):
+        import torch
+        self._ctx = torch.cuda.stream(self.s)
+        self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        ctx, self._ctx = self._ctx, None
+        return ctx.__exit__(*a)
+
+
+class _NoSide:
+    """Serial stand-in (dry runs on a CPU device, or SERL_STREAMS=0): same call sites, everything stays on one stream."""
+
+    def fork(self): pass
+    def join(self): pass
+    def __enter__(self): return self
+    def __exit__(self, *a): return False
+
+
+def new_side_stream(device, enabled=True):
+    return _Side(device) if enabled and device.type == "cuda" else _NoSide()
+
+
 def pin(t):
     return t.pin_memory()

@@ -61,6 +61,17 @@ class _MlpActs:
         self.h2, self.xhat2, self.rstd2 = e(R, H), e(R, H), e(R)
 
 
+class _EncScratch:
+    """Scratch of one encoder-heads pass; each concurrently running branch of the step owns one."""
+
+    def __init__(self, cfg, B, device, ws):
+        e = lambda *s: torch.empty(*s, dtype=f32, device=device)
+        self.ws = ws
+        if cfg.pixel:
+            self.sle = {c: e(B, 4096) for c in cfg.cams}
+            self.enc_z, self.enc_zp = e(B, 256), e(B, 64)
+
+
 class Engine:
     def __init__(self, cfg: AgentConfig, store: ParamStore, trunk: Dict[str, Dict[str, torch.Tensor]], batch: int, device):
         self.cfg, self.store, self.trunk, self.B, self.dev = cfg, store, trunk, batch, device
@@ -69,7 +80,15 @@ class Engine:
         e = lambda *s: torch.empty(*s, dtype=f32, device=device)
         # heads GEMMs: CUDA-core SGEMM in the 1e-5 build, tensor-core 3xTF32 (fp32-class accuracy) next to the 16-bit trunk
         gemm_impl = os.environ.get("SERL_HEADS_GEMM") or ("f32" if cfg.precision == "fp32" else "tf32x3")
-        self.ws = ops.Workspace(max(48 << 20, 2 * 4 * E * B * self.FA), device, gemm_impl)
+        ws_bytes = max(48 << 20, 2 * 4 * E * B * self.FA)
+        self.ws = ops.Workspace(ws_bytes, device, gemm_impl)
+        # Branch-level concurrency: the heads are ~100 short, latency-bound launches, and several chains of them are
+        # independent (online critic / target encoder / policy in the forward pass; weight gradients vs the dX chain in
+        # the backward pass).  They run on two side streams; under CUDA-graph capture the fork / join events become graph
+        # edges.  Every branch owns its scratch (split-K workspace included).
+        dev = torch.device(device)
+        self.side = [L.new_side_stream(dev, os.environ.get("SERL_STREAMS", "1") != "0") for _ in range(2)]
+        self.ws_side = [ops.Workspace(ws_bytes, device, gemm_impl) for _ in range(2)]
         # batch tensors
         self.state_o, self.state_n = e(B, cfg.state_in), e(B, cfg.state_in)
         self.actions, self.rewards, self.masks = e(B, A), e(B), e(B)
@@ -85,15 +104,16 @@ class Engine:
             s2 = hw // 2
             self.t_a0 = e(N, s2, s2, 64)
             self.t_buf = [e(N * (s2 // 2) * (s2 // 2) * 64) for _ in range(4)]
-            self.sle = {c: e(B, 4096) for c in cfg.cams}
             self.sle_saved = {c: e(B, 4096) for c in cfg.cams}
-            self.enc_z = e(B, 256)
             self.enc_xhat = {c: e(B, 256) for c in cfg.cams}
             self.enc_rstd = {c: e(B) for c in cfg.cams}
-            self.enc_zp, self.enc_xhat_p, self.enc_rstd_p = e(B, 64), e(B, 64), e(B)
+            self.enc_xhat_p, self.enc_rstd_p = e(B, 64), e(B)
             self.masks_u8 = {c: torch.empty(B, 4096, dtype=torch.uint8, device=device) for c in cfg.cams}
-            self.d_enc_z, self.d_enc_y, self.d_sle = e(B, 256), e(B, 256), e(B, 4096)
+            self.d_enc_z = {c: e(B, 256) for c in cfg.cams}          # per camera: the side stream reads it while the next one is written
+            self.d_enc_y, self.d_sle = e(B, 256), e(B, 4096)
             self.d_enc_zp, self.d_enc_yp = e(B, 64), e(B, 64)
+        self.sc_main = _EncScratch(cfg, B, device, self.ws)
+        self.sc_side = [_EncScratch(cfg, B, device, w) for w in self.ws_side]
         # critic / policy activations
         self.Xc, self.Xt, self.Xp = e(B, self.FA), e(B, self.FA), e(B, F)
         self.c_main, self.c_tgt = _MlpActs(E * B, device), _MlpActs(E * B, device)
@@ -105,6 +125,7 @@ class Engine:
         self.sub = torch.zeros(2, dtype=torch.int32, device=device)
         # gradient scratch
         self.dh, self.dz, self.dy = e(E * B, 256), e(E * B, 256), e(E * B, 256)
+        self.dz0 = e(E * B, 256)                                    # layer-0 dz: layer-1's is still read by the side stream
         self.dX = e(B, self.FA)
         self.dmu, self.dls = e(B, A), e(B, A)
         self.pdh, self.pdz, self.pdy = e(B, 256), e(B, 256), e(B, 256)
@@ -162,44 +183,50 @@ class Engine:
 
     # ---- trainable encoder heads (common/encoding.py:26-72, vision/resnet_v1.py:340-374) -------
     def encode(self, buf, feats_rows: slice, state: torch.Tensor, out: torch.Tensor, ld_out: int,
-               masks: Optional[Dict[str, torch.Tensor]], save: bool):
-        cfg, B, ws = self.cfg, self.B, self.ws
+               masks: Optional[Dict[str, torch.Tensor]], save: bool, sc: Optional[_EncScratch] = None):
+        sc = sc or self.sc_main
+        cfg, B, ws = self.cfg, self.B, sc.ws
         if not cfg.pixel:
             ops.copy2d(state.data_ptr(), cfg.state_in, out.data_ptr(), ld_out, B, cfg.state_in)
             self.launches += 1
             return
         for j, cam in enumerate(cfg.cams):
             p = f"{ENC}/encoder_{cam}"
-            sle = self.sle_saved[cam] if save else self.sle[cam]
+            sle = self.sle_saved[cam] if save else sc.sle[cam]
             ops.sle_fwd(self.feats[cam][feats_rows], self.store.view(buf, f"{p}/SpatialLearnedEmbeddings_0/kernel"),
                         None if masks is None else masks[cam], 0.9, sle.data_ptr(), 4096)
             ops.dense_fwd(ws, sle.data_ptr(), 4096, self.P(buf, f"{p}/Dense_0/kernel"), self.P(buf, f"{p}/Dense_0/bias"),
-                          self.enc_z.data_ptr(), 256, B, 4096, 256)
-            ops.ln_tanh_fwd(self.enc_z.data_ptr(), 256, self.P(buf, f"{p}/LayerNorm_0/scale"), self.P(buf, f"{p}/LayerNorm_0/bias"),
+                          sc.enc_z.data_ptr(), 256, B, 4096, 256)
+            ops.ln_tanh_fwd(sc.enc_z.data_ptr(), 256, self.P(buf, f"{p}/LayerNorm_0/scale"), self.P(buf, f"{p}/LayerNorm_0/bias"),
                             B, 0, ops.at(out, 256 * j), ld_out, self.enc_xhat[cam].data_ptr() if save else None,
                             self.enc_rstd[cam].data_ptr() if save else None, B, 256)
             self.launches += 4
         ops.dense_fwd(ws, state.data_ptr(), cfg.state_in, self.P(buf, f"{ENC}/Dense_0/kernel"), self.P(buf, f"{ENC}/Dense_0/bias"),
-                      self.enc_zp.data_ptr(), 64, B, cfg.state_in, 64)
-        ops.ln_tanh_fwd(self.enc_zp.data_ptr(), 64, self.P(buf, f"{ENC}/LayerNorm_0/scale"), self.P(buf, f"{ENC}/LayerNorm_0/bias"),
+                      sc.enc_zp.data_ptr(), 64, B, cfg.state_in, 64)
+        ops.ln_tanh_fwd(sc.enc_zp.data_ptr(), 64, self.P(buf, f"{ENC}/LayerNorm_0/scale"), self.P(buf, f"{ENC}/LayerNorm_0/bias"),
                         B, 0, ops.at(out, 256 * len(cfg.cams)), ld_out, self.enc_xhat_p.data_ptr() if save else None,
                         self.enc_rstd_p.data_ptr() if save else None, B, 64)
         self.launches += 2
 
     def encode_backward(self, dX: torch.Tensor, X: torch.Tensor, feats_rows: slice, state: torch.Tensor):
-        """Gradients of the trainable heads given d(enc) = dX[:, :F]; trunk is stop-gradient."""
+        """Gradients of the trainable heads given d(enc) = dX[:, :F]; trunk is stop-gradient.
+        Weight / bias gradients run on side stream 0, the d_enc_z -> d_sle -> SLE-kernel chain stays on the main stream."""
         cfg, B, ws, st = self.cfg, self.B, self.ws, self.store
         G = st.grad
         ld = self.FA
+        side, wss = self.side[0], self.ws_side[0]
         for j, cam in enumerate(cfg.cams):
             p = f"{ENC}/encoder_{cam}"
+            dez = self.d_enc_z[cam]
             ops.ln_tanh_bwd(ops.at(dX, 256 * j), ld, ops.at(X, 256 * j), ld, self.enc_xhat[cam].data_ptr(), self.enc_rstd[cam].data_ptr(),
-                            self.P(st.params, f"{p}/LayerNorm_0/scale"), B, 0, self.d_enc_z.data_ptr(), self.d_enc_y.data_ptr(),
+                            self.P(st.params, f"{p}/LayerNorm_0/scale"), B, 0, dez.data_ptr(), self.d_enc_y.data_ptr(),
                             self.P(G, f"{p}/LayerNorm_0/scale"), self.P(G, f"{p}/LayerNorm_0/bias"), B, 256)
-            ops.dense_bwd_weight(ws, self.sle_saved[cam].data_ptr(), 4096, self.d_enc_z.data_ptr(), 256, self.P(G, f"{p}/Dense_0/kernel"),
-                                 B, 4096, 256)
-            ops.colsum(self.d_enc_z.data_ptr(), self.P(G, f"{p}/Dense_0/bias"), 1, B, 256, 256)
-            ops.dense_bwd_input(ws, self.d_enc_z.data_ptr(), 256, self.P(st.params, f"{p}/Dense_0/kernel"), self.d_sle.data_ptr(), 4096,
+            side.fork()
+            with side:
+                ops.dense_bwd_weight(wss, self.sle_saved[cam].data_ptr(), 4096, dez.data_ptr(), 256, self.P(G, f"{p}/Dense_0/kernel"),
+                                     B, 4096, 256)
+                ops.colsum(dez.data_ptr(), self.P(G, f"{p}/Dense_0/bias"), 1, B, 256, 256)
+            ops.dense_bwd_input(ws, dez.data_ptr(), 256, self.P(st.params, f"{p}/Dense_0/kernel"), self.d_sle.data_ptr(), 4096,
                                 B, 4096, 256)
             ops.sle_bwd_kernel_grad(ws, self.feats[cam][feats_rows], self.d_sle.data_ptr(), 4096,
                                     self.P(G, f"{p}/SpatialLearnedEmbeddings_0/kernel"))
@@ -208,14 +235,16 @@ class Engine:
         ops.ln_tanh_bwd(ops.at(dX, off), ld, ops.at(X, off), ld, self.enc_xhat_p.data_ptr(), self.enc_rstd_p.data_ptr(),
                         self.P(st.params, f"{ENC}/LayerNorm_0/scale"), B, 0, self.d_enc_zp.data_ptr(), self.d_enc_yp.data_ptr(),
                         self.P(G, f"{ENC}/LayerNorm_0/scale"), self.P(G, f"{ENC}/LayerNorm_0/bias"), B, 64)
-        ops.dense_bwd_weight(ws, state.data_ptr(), cfg.state_in, self.d_enc_zp.data_ptr(), 64, self.P(G, f"{ENC}/Dense_0/kernel"),
-                             B, cfg.state_in, 64)
-        ops.colsum(self.d_enc_zp.data_ptr(), self.P(G, f"{ENC}/Dense_0/bias"), 1, B, 64, 64)
+        side.fork()
+        with side:
+            ops.dense_bwd_weight(wss, state.data_ptr(), cfg.state_in, self.d_enc_zp.data_ptr(), 64, self.P(G, f"{ENC}/Dense_0/kernel"),
+                                 B, cfg.state_in, 64)
+            ops.colsum(self.d_enc_zp.data_ptr(), self.P(G, f"{ENC}/Dense_0/bias"), 1, B, 64, 64)
         self.launches += 4
 
     # ---- critic ensemble (networks/actor_critic_nets.py:57-73, networks/mlp.py:22-31) ----------
-    def critic_forward(self, buf, X: torch.Tensor, acts: _MlpActs, q: torch.Tensor, save: bool):
-        cfg, B, E, ws = self.cfg, self.B, self.cfg.ensemble, self.ws
+    def critic_forward(self, buf, X: torch.Tensor, acts: _MlpActs, q: torch.Tensor, save: bool, ws: Optional[ops.Workspace] = None):
+        cfg, B, E, ws = self.cfg, self.B, self.cfg.ensemble, ws or self.ws
         c = "modules_critic/network"
         FA = self.FA
         ops.dense_fwd(ws, X.data_ptr(), FA, self.P(buf, f"{c}/Dense_0/kernel"), self.P(buf, f"{c}/Dense_0/bias"), acts.z.data_ptr(), 256,
@@ -234,38 +263,48 @@ class Engine:
         self.launches += 7
 
     def critic_backward(self, X: torch.Tensor, acts: _MlpActs, dq: torch.Tensor, param_grads: bool, need_dx: bool):
+        """The dq -> dh -> dz -> ... -> dX chain runs on the main stream; each layer's weight / bias gradient only needs that
+        layer's (input, dz) pair, so it is forked to side stream 0 as soon as dz exists (joined by the caller)."""
         cfg, B, E, ws, st = self.cfg, self.B, self.cfg.ensemble, self.ws, self.store
         G, Pm = st.grad, st.params
         c = "modules_critic/network"
         FA, R = self.FA, E * B
-        dh, dz, dy = self.dh.data_ptr(), self.dz.data_ptr(), self.dy.data_ptr()
+        dh, dz, dz0, dy = self.dh.data_ptr(), self.dz.data_ptr(), self.dz0.data_ptr(), self.dy.data_ptr()
+        side, wss = self.side[0], self.ws_side[0]
         wk = self.P(Pm, "modules_critic/Dense_0/kernel")
+        if param_grads:
+            side.fork()
+            with side:
+                if cfg.pixel:
+                    ops.dense_bwd_weight(wss, acts.h2.data_ptr(), 256, dq.data_ptr(), 1, self.P(G, "modules_critic/Dense_0/kernel"), R, 256, 1)
+                    ops.colsum(dq.data_ptr(), self.P(G, "modules_critic/Dense_0/bias"), 1, R, 1, 1)
+                else:
+                    ops.dense_bwd_weight(wss, acts.h2.data_ptr(), 256, dq.data_ptr(), 1, self.P(G, "modules_critic/Dense_0/kernel"), B, 256, 1,
+                                         Z=E, x_z=B * 256, dz_z=B, dw_z=256)
+                    ops.colsum(dq.data_ptr(), self.P(G, "modules_critic/Dense_0/bias"), E, B, 1, 1)
         if cfg.pixel:
             ops.dense_bwd_input(ws, dq.data_ptr(), 1, wk, dh, 256, R, 256, 1)
-            if param_grads:
-                ops.dense_bwd_weight(ws, acts.h2.data_ptr(), 256, dq.data_ptr(), 1, self.P(G, "modules_critic/Dense_0/kernel"), R, 256, 1)
-                ops.colsum(dq.data_ptr(), self.P(G, "modules_critic/Dense_0/bias"), 1, R, 1, 1)
         else:
             ops.dense_bwd_input(ws, dq.data_ptr(), 1, wk, dh, 256, B, 256, 1, Z=E, dz_z=B, w_z=256, dx_z=B * 256)
-            if param_grads:
-                ops.dense_bwd_weight(ws, acts.h2.data_ptr(), 256, dq.data_ptr(), 1, self.P(G, "modules_critic/Dense_0/kernel"), B, 256, 1,
-                                     Z=E, x_z=B * 256, dz_z=B, dw_z=256)
-                ops.colsum(dq.data_ptr(), self.P(G, "modules_critic/Dense_0/bias"), E, B, 1, 1)
         ops.ln_tanh_bwd(dh, 256, acts.h2.data_ptr(), 256, acts.xhat2.data_ptr(), acts.rstd2.data_ptr(), self.P(Pm, f"{c}/LayerNorm_1/scale"), B, 256,
                         dz, dy, self.P(G, f"{c}/LayerNorm_1/scale") if param_grads else None,
                         self.P(G, f"{c}/LayerNorm_1/bias") if param_grads else None, R, 256)
         if param_grads:
-            ops.dense_bwd_weight(ws, acts.h1.data_ptr(), 256, dz, 256, self.P(G, f"{c}/Dense_1/kernel"), B, 256, 256, Z=E, x_z=B * 256, dz_z=B * 256)
-            ops.colsum(dz, self.P(G, f"{c}/Dense_1/bias"), E, B, 256, 256)
+            side.fork()
+            with side:
+                ops.dense_bwd_weight(wss, acts.h1.data_ptr(), 256, dz, 256, self.P(G, f"{c}/Dense_1/kernel"), B, 256, 256, Z=E, x_z=B * 256, dz_z=B * 256)
+                ops.colsum(dz, self.P(G, f"{c}/Dense_1/bias"), E, B, 256, 256)
         ops.dense_bwd_input(ws, dz, 256, self.P(Pm, f"{c}/Dense_1/kernel"), dh, 256, B, 256, 256, Z=E, dz_z=B * 256, dx_z=B * 256)
         ops.ln_tanh_bwd(dh, 256, acts.h1.data_ptr(), 256, acts.xhat1.data_ptr(), acts.rstd1.data_ptr(), self.P(Pm, f"{c}/LayerNorm_0/scale"), B, 256,
-                        dz, dy, self.P(G, f"{c}/LayerNorm_0/scale") if param_grads else None,
+                        dz0, dy, self.P(G, f"{c}/LayerNorm_0/scale") if param_grads else None,
                         self.P(G, f"{c}/LayerNorm_0/bias") if param_grads else None, R, 256)
         if param_grads:
-            ops.dense_bwd_weight(ws, X.data_ptr(), FA, dz, 256, self.P(G, f"{c}/Dense_0/kernel"), B, FA, 256, Z=E, x_z=0, dz_z=B * 256)
-            ops.colsum(dz, self.P(G, f"{c}/Dense_0/bias"), E, B, 256, 256)
+            side.fork()
+            with side:
+                ops.dense_bwd_weight(wss, X.data_ptr(), FA, dz0, 256, self.P(G, f"{c}/Dense_0/kernel"), B, FA, 256, Z=E, x_z=0, dz_z=B * 256)
+                ops.colsum(dz0, self.P(G, f"{c}/Dense_0/bias"), E, B, 256, 256)
         if need_dx:       # input is broadcast over the ensemble: dX = sum_e dZ1_e W1_e^T
-            ops.dense_bwd_input(ws, dz, 256, self.P(Pm, f"{c}/Dense_0/kernel"), self.dX.data_ptr(), FA, B, FA, 256, Z=E, dz_z=B * 256,
+            ops.dense_bwd_input(ws, dz0, 256, self.P(Pm, f"{c}/Dense_0/kernel"), self.dX.data_ptr(), FA, B, FA, 256, Z=E, dz_z=B * 256,
                                 reduce_z=True)
         self.launches += 8 + (7 if param_grads else 0) + (2 if need_dx else 0)
 
@@ -334,7 +373,18 @@ class Engine:
         """sac.py:134-191 + its gradient w.r.t. group-0 parameters (written to store.grad)."""
         cfg, B, E, st = self.cfg, self.B, self.cfg.ensemble, self.store
         obs_rows, next_rows = slice(0, B), slice(B, 2 * B)
-        # a', logp' ~ pi(s')  (params, train=True)
+        # three independent forward branches:
+        #   side 0: Q(s, a) with params, saved for backward      side 1: target-encoder heads on s'
+        #   main:   a', logp' ~ pi(s') (params, train=True), then Q'(s', a') with target params once side 1 has delivered enc(s')
+        s0, s1 = self.side
+        s0.fork()
+        s1.fork()
+        with s0:
+            self.encode(st.params, obs_rows, self.state_o, self.Xc, self.FA, None, save=True, sc=self.sc_side[0])
+            ops.copy2d(self.actions.data_ptr(), cfg.action_dim, ops.at(self.Xc, self.F), self.FA, B, cfg.action_dim)
+            self.critic_forward(st.params, self.Xc, self.c_main, self.q, save=True, ws=self.ws_side[0])
+        with s1:
+            self.encode(st.target, next_rows, self.state_n, self.Xt, self.FA, None, save=False, sc=self.sc_side[1])
         self._policy_pass(next_rows, self.state_n, L.KEY_CRITIC_NEXT, L.KEY_CRITIC_NEXT, keys, ops.at(self.Xt, self.F), self.FA, save=False,
                           explicit=None if explicit is None else explicit["critic"])
         n_sub = 0
@@ -345,18 +395,15 @@ class Engine:
             else:
                 self.sub.copy_(explicit["critic"]["subsample"])
             n_sub = cfg.subsample
-        # Q'(s', a') with target params
-        self.encode(st.target, next_rows, self.state_n, self.Xt, self.FA, None, save=False)
+        s1.join()
         self.critic_forward(st.target, self.Xt, self.c_tgt, self.q_next, save=False)
-        # Q(s, a) with params, saved for backward
-        self.encode(st.params, obs_rows, self.state_o, self.Xc, self.FA, None, save=True)
-        ops.copy2d(self.actions.data_ptr(), cfg.action_dim, ops.at(self.Xc, self.F), self.FA, B, cfg.action_dim)
-        self.critic_forward(st.params, self.Xc, self.c_main, self.q, save=True)
+        s0.join()
         ops.critic_loss(self.q, self.q_next, self.sub, n_sub, self.rewards, self.masks, self.logp, self.P(st.params, "modules_temperature/lagrange"),
                         cfg.backup_entropy, cfg.discount, grad_scale, self.target_q, self.dq, self.info.data_ptr(), E, B)
         self.critic_backward(self.Xc, self.c_main, self.dq, param_grads=True, need_dx=cfg.pixel)
         if cfg.pixel:
             self.encode_backward(self.dX, self.Xc, obs_rows, self.state_o)
+        s0.join()                                               # weight / bias gradients
         self.launches += 2
 
     def actor_temp_loss_and_grads(self, keys, grad_scale=1.0, explicit=None):
