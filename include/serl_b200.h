@@ -154,6 +154,15 @@ typedef struct serl_stem_pool_desc {
 } serl_stem_pool_desc;
 int serl_stem_conv_pool_tc_h16(const serl_stem_pool_desc* d, void* stream);
 int serl_pool_finish_h16(const void* pooled, const void* side, const float* a, const float* b, void* y, int N, int fmt, void* stream);
+/* "_gn" consumers: take the conv epilogue's GroupNorm sums (N,4,2) + the frozen scale / bias instead of a finalized (a, b)
+ * table and derive the affine in registers (same arithmetic as serl_gn_finalize) - no finalize launch in the chain. */
+int serl_pool_finish_gn_h16(const void* pooled, const void* side, const float* stats, const float* gamma, const float* beta, void* y,
+                            int N, float eps, int fmt, void* stream);
+int serl_affine_relu_gn_h16(void* x, const float* stats, const float* gamma, const float* beta, int N, int HW, int C, float eps, int fmt,
+                            void* stream);
+int serl_block_combine_gn_h16(const void* y2, const float* stats2, const float* gamma2, const float* beta2, const void* res,
+                              const float* stats_r, const float* gamma_r, const float* beta_r, void* out_h16, float* out_f32,
+                              int N, int HW, int C, float eps, int fmt, void* stream);
 /* (N,4,2) sums -> per-(image, channel) affine a = rstd*gamma, b = beta - mean*a (flax GroupNorm statistics) */
 int serl_gn_finalize(const float* stats, const float* gamma, const float* beta, float* out_a, float* out_b, int N, int C,
                      int HW, float eps, void* stream);

@@ -92,6 +92,9 @@ _PROTOS = {
     "serl_affine_relu_h16": [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_stem_conv_pool_tc_h16": [C.POINTER(StemPoolDesc), vp],
     "serl_pool_finish_h16": [vp, vp, vp, vp, vp, C.c_int, C.c_int, vp],
+    "serl_pool_finish_gn_h16": [vp, vp, vp, vp, vp, vp, C.c_int, C.c_float, C.c_int, vp],
+    "serl_affine_relu_gn_h16": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp],
+    "serl_block_combine_gn_h16": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, vp],
     "serl_maxpool_affine_h16": [vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_block_combine_h16": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_gemm_f32": [C.POINTER(GemmDesc), vp],

@@ -567,8 +567,18 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
 // ---- stem input: uint8 crops -> normalised 16-bit, 2x2 space-to-depth, zero padded: (N,67,67,16) [12 real + 4 zero ch] ----
 template <class F>
 __global__ void stem_prep_kernel(const uint8_t* __restrict__ x, uint16_t* __restrict__ xs, int N, int H, int W, int Hs, int Ws) {
+  // a byte has 256 values: normalise each (channel, value) pair once per block (true fp32 divisions, as the fp32 build and
+  // the oracle do) and look the 16-bit result up afterwards
+  __shared__ uint16_t lut[3][256];
+  {
+    const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
+    for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+      const int c = i >> 8, v = i & 255;
+      lut[c][v] = (uint16_t)(F::pack(((float)v / 255.0f - mean[c]) / stdv[c], 0.f) & 0xFFFFu);
+    }
+  }
+  __syncthreads();
   const size_t total = (size_t)N * Hs * Ws;
-  const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int b = (int)(e % Ws); size_t r = e / Ws; const int aa = (int)(r % Hs); const int n = (int)(r / Hs);
     uint32_t out[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};                    // 16 channels: (p, q, c) at pq*3 + c, channels 12..15 zero
@@ -576,21 +586,47 @@ __global__ void stem_prep_kernel(const uint8_t* __restrict__ x, uint16_t* __rest
     for (int pq = 0; pq < 4; ++pq) {
       const int p = pq >> 1, q = pq & 1;
       const int hi = 2 * aa + p - 3, wi = 2 * b + q - 3;          // explicit padding (3,3) of conv_init (resnet_v1.py:247)
-      float f[3] = {0.f, 0.f, 0.f};
       if (hi >= 0 && hi < H && wi >= 0 && wi < W) {
         const uint8_t* px = x + (((size_t)n * H + hi) * W + wi) * 3;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) f[c] = ((float)px[c] / 255.0f - mean[c]) / stdv[c];
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const int ei = pq * 3 + c;
-        const uint32_t h = F::pack(f[c], 0.f) & 0xFFFFu;
-        out[ei >> 1] |= (ei & 1) ? (h << 16) : h;
+        for (int c = 0; c < 3; ++c) {
+          const int ei = pq * 3 + c;
+          const uint32_t h = lut[c][px[c]];
+          out[ei >> 1] |= (ei & 1) ? (h << 16) : h;
+        }
       }
     }
     uint4* dst = reinterpret_cast<uint4*>(xs + e * 16);
     dst[0] = make_uint4(out[0], out[1], out[2], out[3]); dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+  }
+}
+
+// ---- where a consumer gets its GroupNorm affine from: a precomputed (N, C) table (serl_gn_finalize), or straight from the
+// conv epilogue's sums + the frozen scale / bias (same arithmetic as gn_finalize_kernel, bit for bit) - the "_gn" entry
+// points, which take the 12 finalize launches out of the trunk's dependency chain.
+struct GnSrc {
+  const float* a; const float* b;
+  const float* stats; const float* gamma; const float* beta;
+  float count, eps; int Cg;
+};
+__device__ inline void gn_load8(const GnSrc& g, int n, int C, int c0, float (&a)[8], float (&b)[8]) {
+  if (g.stats) {
+    const int grp = c0 / g.Cg;                                 // 8 consecutive channels never straddle a group (Cg >= 16)
+    const float s = g.stats[((size_t)n * 4 + grp) * 2], ss = g.stats[((size_t)n * 4 + grp) * 2 + 1];
+    const float mean = s / g.count;
+    const float var = fmaxf(ss / g.count - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + g.eps);
+    const float4 g0 = *reinterpret_cast<const float4*>(g.gamma + c0), g1 = *reinterpret_cast<const float4*>(g.gamma + c0 + 4);
+    const float4 e0 = *reinterpret_cast<const float4*>(g.beta + c0), e1 = *reinterpret_cast<const float4*>(g.beta + c0 + 4);
+    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = rstd * gm[j]; b[j] = bt[j] - mean * a[j]; }
+  } else {
+    const size_t co = (size_t)n * C + c0;
+    const float4 a0 = *reinterpret_cast<const float4*>(g.a + co), a1 = *reinterpret_cast<const float4*>(g.a + co + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(g.b + co), b1 = *reinterpret_cast<const float4*>(g.b + co + 4);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
   }
 }
 
@@ -609,17 +645,17 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, const float*
 
 // ---- GroupNorm + ReLU applied in place on the raw 16-bit conv output: x <- relu(a*x + b); thread per 8 channels ----
 template <class F>
-__global__ void affine_relu_kernel(uint16_t* __restrict__ x, const float* __restrict__ ga, const float* __restrict__ gb, int N, int HW, int C) {
+__global__ void affine_relu_kernel(uint16_t* __restrict__ x, const GnSrc g, int N, int HW, int C) {
   const int c8n = C >> 3;
   const size_t total = (size_t)N * HW * c8n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(e % c8n); const size_t pix = e / c8n; const int n = (int)(pix / HW);
-    const size_t off = pix * C + c8 * 8, co = (size_t)n * C + c8 * 8;
+    const size_t off = pix * C + c8 * 8;
     uint4 v = *reinterpret_cast<const uint4*>(x + off);
-    const float4 a0 = *reinterpret_cast<const float4*>(ga + co), a1 = *reinterpret_cast<const float4*>(ga + co + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(gb + co), b1 = *reinterpret_cast<const float4*>(gb + co + 4);
-    v.x = affine_relu_x2<F>(v.x, a0.x, b0.x, a0.y, b0.y); v.y = affine_relu_x2<F>(v.y, a0.z, b0.z, a0.w, b0.w);
-    v.z = affine_relu_x2<F>(v.z, a1.x, b1.x, a1.y, b1.y); v.w = affine_relu_x2<F>(v.w, a1.z, b1.z, a1.w, b1.w);
+    float a[8], b[8];
+    gn_load8(g, n, C, c8 * 8, a, b);
+    v.x = affine_relu_x2<F>(v.x, a[0], b[0], a[1], b[1]); v.y = affine_relu_x2<F>(v.y, a[2], b[2], a[3], b[3]);
+    v.z = affine_relu_x2<F>(v.z, a[4], b[4], a[5], b[5]); v.w = affine_relu_x2<F>(v.w, a[6], b[6], a[7], b[7]);
     *reinterpret_cast<uint4*>(x + off) = v;
   }
 }
@@ -666,8 +702,8 @@ __global__ void maxpool_affine_kernel(const uint16_t* __restrict__ x, const floa
 
 // ---- second half of the fused stem max-pool: join unit-boundary rows with the side buffer, then relu(|a|*x' + b) ----
 template <class F>
-__global__ void pool_finish_kernel(const uint16_t* __restrict__ pooled, const uint16_t* __restrict__ side, const float* __restrict__ ga,
-                                   const float* __restrict__ gb, uint16_t* __restrict__ y, int N) {
+__global__ void pool_finish_kernel(const uint16_t* __restrict__ pooled, const uint16_t* __restrict__ side, const GnSrc g,
+                                   uint16_t* __restrict__ y, int N) {
   const size_t total = (size_t)N * 32 * 32 * 8;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(e & 7); size_t r = e >> 3;
@@ -677,37 +713,29 @@ __global__ void pool_finish_kernel(const uint16_t* __restrict__ pooled, const ui
       const uint4 u = *reinterpret_cast<const uint4*>(side + (((size_t)n * 4 + ((p + 1) >> 3)) * 32 + j) * 64 + c8 * 8);
       v.x = F::max2(v.x, u.x); v.y = F::max2(v.y, u.y); v.z = F::max2(v.z, u.z); v.w = F::max2(v.w, u.w);
     }
-    const size_t co = (size_t)n * 64 + c8 * 8;
-    const float4 a0 = *reinterpret_cast<const float4*>(ga + co), a1 = *reinterpret_cast<const float4*>(ga + co + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(gb + co), b1 = *reinterpret_cast<const float4*>(gb + co + 4);
-    v.x = affine_relu_x2<F>(v.x, fabsf(a0.x), b0.x, fabsf(a0.y), b0.y); v.y = affine_relu_x2<F>(v.y, fabsf(a0.z), b0.z, fabsf(a0.w), b0.w);
-    v.z = affine_relu_x2<F>(v.z, fabsf(a1.x), b1.x, fabsf(a1.y), b1.y); v.w = affine_relu_x2<F>(v.w, fabsf(a1.z), b1.z, fabsf(a1.w), b1.w);
+    float a[8], b[8];
+    gn_load8(g, n, 64, c8 * 8, a, b);
+    v.x = affine_relu_x2<F>(v.x, fabsf(a[0]), b[0], fabsf(a[1]), b[1]); v.y = affine_relu_x2<F>(v.y, fabsf(a[2]), b[2], fabsf(a[3]), b[3]);
+    v.z = affine_relu_x2<F>(v.z, fabsf(a[4]), b[4], fabsf(a[5]), b[5]); v.w = affine_relu_x2<F>(v.w, fabsf(a[6]), b[6], fabsf(a[7]), b[7]);
     *reinterpret_cast<uint4*>(y + e * 8) = v;
   }
 }
 
 // ---- block output: relu( (a2*y2 + b2) + residual ), residual = res (identity) or ar*res + br (projection) ----
 template <class F>
-__global__ void block_combine_kernel(const uint16_t* __restrict__ y2, const float* __restrict__ a2, const float* __restrict__ b2,
-                                     const uint16_t* __restrict__ res, const float* __restrict__ ar, const float* __restrict__ br,
+__global__ void block_combine_kernel(const uint16_t* __restrict__ y2, const GnSrc g2, const uint16_t* __restrict__ res, const GnSrc gr, int ar,
                                      uint16_t* __restrict__ out_bf16, float* __restrict__ out_f32, int N, int HW, int C) {
   const int c8n = C >> 3;
   const size_t total = (size_t)N * HW * c8n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(e % c8n); const size_t pix = e / c8n; const int n = (int)(pix / HW);
-    const size_t off = pix * C + c8 * 8, co = (size_t)n * C + c8 * 8;
+    const size_t off = pix * C + c8 * 8;
     const uint4 yv = *reinterpret_cast<const uint4*>(y2 + off), rv = *reinterpret_cast<const uint4*>(res + off);
     const uint32_t yu[4] = {yv.x, yv.y, yv.z, yv.w}, ru[4] = {rv.x, rv.y, rv.z, rv.w};
-    const float4 p0 = *reinterpret_cast<const float4*>(a2 + co), p1 = *reinterpret_cast<const float4*>(a2 + co + 4);
-    const float4 q0 = *reinterpret_cast<const float4*>(b2 + co), q1 = *reinterpret_cast<const float4*>(b2 + co + 4);
-    const float ya[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w}, yb[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-    float ra[8], rb[8];
-    if (ar) {
-      const float4 r0 = *reinterpret_cast<const float4*>(ar + co), r1 = *reinterpret_cast<const float4*>(ar + co + 4);
-      const float4 s0 = *reinterpret_cast<const float4*>(br + co), s1 = *reinterpret_cast<const float4*>(br + co + 4);
-      ra[0] = r0.x; ra[1] = r0.y; ra[2] = r0.z; ra[3] = r0.w; ra[4] = r1.x; ra[5] = r1.y; ra[6] = r1.z; ra[7] = r1.w;
-      rb[0] = s0.x; rb[1] = s0.y; rb[2] = s0.z; rb[3] = s0.w; rb[4] = s1.x; rb[5] = s1.y; rb[6] = s1.z; rb[7] = s1.w;
-    } else {
+    float ya[8], yb[8], ra[8], rb[8];
+    gn_load8(g2, n, C, c8 * 8, ya, yb);
+    if (ar) gn_load8(gr, n, C, c8 * 8, ra, rb);
+    else {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { ra[j] = 1.f; rb[j] = 0.f; }
     }
@@ -859,14 +887,26 @@ extern "C" int serl_stem_conv_pool_tc_h16(const serl_stem_pool_desc* d, void* st
   return d->fmt == SERL_FMT_FP16 ? launch_stem_tc<Fp16, true>(a, d->fmt, ST(stream)) : launch_stem_tc<Bf16, true>(a, d->fmt, ST(stream));
 }
 
-extern "C" int serl_pool_finish_h16(const void* pooled, const void* side, const float* a, const float* b, void* y, int N, int fmt, void* stream) {
+static GnSrc gn_table(const float* a, const float* b) { GnSrc g{}; g.a = a; g.b = b; return g; }
+static GnSrc gn_sums(const float* stats, const float* gamma, const float* beta, int C, int HW, float eps) {
+  GnSrc g{}; g.stats = stats; g.gamma = gamma; g.beta = beta; g.Cg = C / 4; g.count = (float)HW * (float)(C / 4); g.eps = eps; return g;
+}
+
+static int launch_pool_finish(const void* pooled, const void* side, const GnSrc& g, void* y, int N, int fmt, void* stream) {
   const size_t total = (size_t)N * 32 * 32 * 8;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
   if (fmt == SERL_FMT_FP16)
-    pool_finish_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(static_cast<const uint16_t*>(pooled), static_cast<const uint16_t*>(side), a, b, static_cast<uint16_t*>(y), N);
+    pool_finish_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(static_cast<const uint16_t*>(pooled), static_cast<const uint16_t*>(side), g, static_cast<uint16_t*>(y), N);
   else
-    pool_finish_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(static_cast<const uint16_t*>(pooled), static_cast<const uint16_t*>(side), a, b, static_cast<uint16_t*>(y), N);
+    pool_finish_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(static_cast<const uint16_t*>(pooled), static_cast<const uint16_t*>(side), g, static_cast<uint16_t*>(y), N);
   return check_launch("pool_finish_kernel");
+}
+extern "C" int serl_pool_finish_h16(const void* pooled, const void* side, const float* a, const float* b, void* y, int N, int fmt, void* stream) {
+  return launch_pool_finish(pooled, side, gn_table(a, b), y, N, fmt, stream);
+}
+extern "C" int serl_pool_finish_gn_h16(const void* pooled, const void* side, const float* stats, const float* gamma, const float* beta, void* y,
+                                       int N, float eps, int fmt, void* stream) {
+  return launch_pool_finish(pooled, side, gn_sums(stats, gamma, beta, 64, 64 * 64, eps), y, N, fmt, stream);
 }
 
 extern "C" int serl_gn_finalize(const float* stats, const float* gamma, const float* beta, float* out_a, float* out_b, int N, int C,
@@ -876,12 +916,19 @@ extern "C" int serl_gn_finalize(const float* stats, const float* gamma, const fl
   return check_launch("gn_finalize_kernel");
 }
 
-extern "C" int serl_affine_relu_h16(void* x, const float* a, const float* b, int N, int HW, int C, int fmt, void* stream) {
+static int launch_affine_relu(void* x, const GnSrc& g, int N, int HW, int C, int fmt, void* stream) {
   size_t total = (size_t)N * HW * (C / 8);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  if (fmt == SERL_FMT_FP16) affine_relu_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(static_cast<uint16_t*>(x), a, b, N, HW, C);
-  else affine_relu_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(static_cast<uint16_t*>(x), a, b, N, HW, C);
+  if (fmt == SERL_FMT_FP16) affine_relu_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(static_cast<uint16_t*>(x), g, N, HW, C);
+  else affine_relu_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(static_cast<uint16_t*>(x), g, N, HW, C);
   return check_launch("affine_relu_kernel");
+}
+extern "C" int serl_affine_relu_h16(void* x, const float* a, const float* b, int N, int HW, int C, int fmt, void* stream) {
+  return launch_affine_relu(x, gn_table(a, b), N, HW, C, fmt, stream);
+}
+extern "C" int serl_affine_relu_gn_h16(void* x, const float* stats, const float* gamma, const float* beta, int N, int HW, int C, float eps,
+                                       int fmt, void* stream) {
+  return launch_affine_relu(x, gn_sums(stats, gamma, beta, C, HW, eps), N, HW, C, fmt, stream);
 }
 
 extern "C" int serl_maxpool_affine_h16(const void* x, const float* a, const float* b, void* y, int N, int Hi, int Wi, int C, int fmt, void* stream) {
@@ -894,12 +941,22 @@ extern "C" int serl_maxpool_affine_h16(const void* x, const float* a, const floa
   return check_launch("maxpool_affine_kernel");
 }
 
-extern "C" int serl_block_combine_h16(const void* y2, const float* a2, const float* b2, const void* res, const float* ar, const float* br,
-                                      void* out_h16, float* out_f32, int N, int HW, int C, int fmt, void* stream) {
+static int launch_block_combine(const void* y2, const GnSrc& g2, const void* res, const GnSrc& gr, int ar, void* out_h16, float* out_f32,
+                                int N, int HW, int C, int fmt, void* stream) {
   size_t total = (size_t)N * HW * (C / 8);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
   auto yi = static_cast<const uint16_t*>(y2); auto ri = static_cast<const uint16_t*>(res); auto oo = static_cast<uint16_t*>(out_h16);
-  if (fmt == SERL_FMT_FP16) block_combine_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(yi, a2, b2, ri, ar, br, oo, out_f32, N, HW, C);
-  else block_combine_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(yi, a2, b2, ri, ar, br, oo, out_f32, N, HW, C);
+  if (fmt == SERL_FMT_FP16) block_combine_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(yi, g2, ri, gr, ar, oo, out_f32, N, HW, C);
+  else block_combine_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(yi, g2, ri, gr, ar, oo, out_f32, N, HW, C);
   return check_launch("block_combine_kernel");
+}
+extern "C" int serl_block_combine_h16(const void* y2, const float* a2, const float* b2, const void* res, const float* ar, const float* br,
+                                      void* out_h16, float* out_f32, int N, int HW, int C, int fmt, void* stream) {
+  return launch_block_combine(y2, gn_table(a2, b2), res, gn_table(ar, br), ar != nullptr, out_h16, out_f32, N, HW, C, fmt, stream);
+}
+extern "C" int serl_block_combine_gn_h16(const void* y2, const float* stats2, const float* gamma2, const float* beta2, const void* res,
+                                         const float* stats_r, const float* gamma_r, const float* beta_r, void* out_h16, float* out_f32,
+                                         int N, int HW, int C, float eps, int fmt, void* stream) {
+  return launch_block_combine(y2, gn_sums(stats2, gamma2, beta2, C, HW, eps), res, gn_sums(stats_r, gamma_r, beta_r, C, HW, eps),
+                              stats_r != nullptr, out_h16, out_f32, N, HW, C, fmt, stream);
 }

@@ -27,6 +27,10 @@ BASE_OFFSET_MODE = 0
 # conv_init + GroupNorm + ReLU + max-pool: pool inside the stem epilogue (the 64x64x64 map never reaches HBM).
 USE_FUSED_STEM_POOL = True
 
+# GroupNorm affines derived inside the consumers from the conv epilogue sums (no serl_gn_finalize launches in the chain).
+USE_FUSED_GN = True
+GN_EPS = 1e-5
+
 FMT = {"bf16": (L.FMT_BF16, torch.bfloat16), "fp16": (L.FMT_FP16, torch.float16)}
 
 
@@ -121,14 +125,20 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
         L.call("serl_stem_conv_pool_tc_h16", C.byref(d), _s())
     else:
         _conv(p, p.xs, wp["conv_init/kernel"], p.y0, st0, N, p.hs, p.hs, 12, s, s, 64, 4, 1, 0, stem=True)
-    a0, b0 = _finalize(st0, w["norm_init/scale"], w["norm_init/bias"], p.aff[0], N, 64, s * s)
+    g0, be0 = w["norm_init/scale"], w["norm_init/bias"]
+    if not (USE_FUSED_GN and p.fused_pool):
+        a0, b0 = _finalize(st0, g0, be0, p.aff[0], N, 64, s * s)
+        engine.launches += 1
     s //= 2
     x = p.buf[0][:N * s * s * 64].view(N, s, s, 64)
-    if p.fused_pool:
+    if p.fused_pool and USE_FUSED_GN:
+        L.call("serl_pool_finish_gn_h16", p.pooled.data_ptr(), p.side.data_ptr(), st0.data_ptr(), g0.data_ptr(), be0.data_ptr(), x.data_ptr(),
+               N, GN_EPS, p.fmt, _s())
+    elif p.fused_pool:
         L.call("serl_pool_finish_h16", p.pooled.data_ptr(), p.side.data_ptr(), a0.data_ptr(), b0.data_ptr(), x.data_ptr(), N, p.fmt, _s())
     else:
         L.call("serl_maxpool_affine_h16", p.y0.data_ptr(), a0.data_ptr(), b0.data_ptr(), x.data_ptr(), N, 2 * s, 2 * s, 64, p.fmt, _s())
-    engine.launches += 5
+    engine.launches += 4                                            # stem_prep, stats memset, stem conv, pool
     free, cur, cin = [1, 2, 3, 4], 0, 64
     for i, (f, stride) in enumerate(STAGES):
         b = f"ResNetBlock_{i}"
@@ -138,24 +148,37 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
         yA, yB, yP, out = view(iy), view(iy2), view(ir), view(io)
         sA, sB, sP = next(st), next(st), next(st)
         lo = 1 if stride == 1 else 0                                   # XLA SAME on even sizes: pad low 0 / high 1
-        _conv(p, x, wp[f"{b}/Conv_0/kernel"], yA, sA, N, s, s, cin, so, so, f, 3, stride, lo)
-        abA = _finalize(sA, w[f"{b}/MyGroupNorm_0/scale"], w[f"{b}/MyGroupNorm_0/bias"], p.aff[0], N, f, so * so)
-        # materialise relu(GN(yA)) in place (one HBM-speed pass); the conv operands are then plain async copies
-        L.call("serl_affine_relu_h16", yA.data_ptr(), abA[0].data_ptr(), abA[1].data_ptr(), N, so * so, f, p.fmt, _s())
-        _conv(p, yA, wp[f"{b}/Conv_1/kernel"], yB, sB, N, so, so, f, so, so, f, 3, 1, 1)
-        engine.launches += 1
-        abB = _finalize(sB, w[f"{b}/MyGroupNorm_1/scale"], w[f"{b}/MyGroupNorm_1/bias"], p.aff[1], N, f, so * so)
+        gA, bA = w[f"{b}/MyGroupNorm_0/scale"], w[f"{b}/MyGroupNorm_0/bias"]
+        gB, bB = w[f"{b}/MyGroupNorm_1/scale"], w[f"{b}/MyGroupNorm_1/bias"]
+        proj = stride != 1 or cin != f
         last = i == len(STAGES) - 1
-        if stride != 1 or cin != f:
-            _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, sP, N, s, s, cin, so, so, f, 1, stride, 0)
-            abP = _finalize(sP, w[f"{b}/norm_proj/scale"], w[f"{b}/norm_proj/bias"], p.aff[2], N, f, so * so)
-            res, ar, br = yP, abP[0].data_ptr(), abP[1].data_ptr()
-            engine.launches += 2
+        _conv(p, x, wp[f"{b}/Conv_0/kernel"], yA, sA, N, s, s, cin, so, so, f, 3, stride, lo)
+        # materialise relu(GN(yA)) in place (one HBM-speed pass); the conv operands are then plain async copies
+        if USE_FUSED_GN:
+            L.call("serl_affine_relu_gn_h16", yA.data_ptr(), sA.data_ptr(), gA.data_ptr(), bA.data_ptr(), N, so * so, f, GN_EPS, p.fmt, _s())
         else:
-            res, ar, br = x, None, None
-        L.call("serl_block_combine_h16", yB.data_ptr(), abB[0].data_ptr(), abB[1].data_ptr(), res.data_ptr(), ar, br,
-               None if last else out.data_ptr(), feats.data_ptr() if last else None, N, so * so, f, p.fmt, _s())
-        engine.launches += 6
+            abA = _finalize(sA, gA, bA, p.aff[0], N, f, so * so)
+            L.call("serl_affine_relu_h16", yA.data_ptr(), abA[0].data_ptr(), abA[1].data_ptr(), N, so * so, f, p.fmt, _s())
+        _conv(p, yA, wp[f"{b}/Conv_1/kernel"], yB, sB, N, so, so, f, so, so, f, 3, 1, 1)
+        if proj:
+            _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, sP, N, s, s, cin, so, so, f, 1, stride, 0)
+            gP, bP = w[f"{b}/norm_proj/scale"], w[f"{b}/norm_proj/bias"]
+        o16, o32 = (None if last else out.data_ptr()), (feats.data_ptr() if last else None)
+        if USE_FUSED_GN:
+            L.call("serl_block_combine_gn_h16", yB.data_ptr(), sB.data_ptr(), gB.data_ptr(), bB.data_ptr(), yP.data_ptr() if proj else x.data_ptr(),
+                   sP.data_ptr() if proj else None, gP.data_ptr() if proj else None, bP.data_ptr() if proj else None, o16, o32,
+                   N, so * so, f, GN_EPS, p.fmt, _s())
+        else:
+            abB = _finalize(sB, gB, bB, p.aff[1], N, f, so * so)
+            if proj:
+                abP = _finalize(sP, gP, bP, p.aff[2], N, f, so * so)
+                res, ar, br = yP, abP[0].data_ptr(), abP[1].data_ptr()
+            else:
+                res, ar, br = x, None, None
+            L.call("serl_block_combine_h16", yB.data_ptr(), abB[0].data_ptr(), abB[1].data_ptr(), res.data_ptr(), ar, br, o16, o32,
+                   N, so * so, f, p.fmt, _s())
+            engine.launches += 2 + int(proj)
+        engine.launches += 4 + int(proj)
         free, cur = [cur, iy, iy2, ir], io
         x, s, cin = out, so, f
     return feats

@@ -141,6 +141,58 @@ def test_fused_stem_pool_equals_conv_then_pool(N, prec):
     assert torch.equal(out.view(torch.int16), ref.view(torch.int16))
 
 
+@pytest.mark.parametrize("prec", ["bf16", "fp16"])
+@pytest.mark.parametrize("N,HW,Cc", [(3, 1024, 64), (5, 64, 256), (2, 16, 512)])
+def test_gn_consumers_from_sums_equal_finalize_then_consume(N, HW, Cc, prec):
+    """The "_gn" consumers (affine derived in registers from the conv sums) give the same bits as serl_gn_finalize followed
+    by the table-driven consumers."""
+    from serl_b200 import _lib as L
+    rng = np.random.default_rng(21)
+    dt, fmt = DT[prec], {"bf16": L.FMT_BF16, "fp16": L.FMT_FP16}[prec]
+    s = L.stream_ptr()
+    cnt = HW * (Cc // 4)
+    mean = rng.standard_normal((N, 4)) * 0.5
+    var = rng.random((N, 4)) + 0.2
+    stats = torch.as_tensor(np.stack([mean * cnt, (var + mean ** 2) * cnt], -1).astype(np.float32)).cuda()
+    stats_r = torch.as_tensor(np.stack([var * cnt * 0.3, (var + (0.3 * var) ** 2) * cnt], -1).astype(np.float32)).cuda()
+    gamma, beta = [torch.as_tensor(rng.standard_normal(Cc).astype(np.float32)).cuda() for _ in range(2)]
+    gamma_r, beta_r = [torch.as_tensor(rng.standard_normal(Cc).astype(np.float32)).cuda() for _ in range(2)]
+    y = torch.as_tensor(rng.standard_normal((N, HW, Cc)).astype(np.float32)).to(dt).cuda()
+    res = torch.as_tensor(rng.standard_normal((N, HW, Cc)).astype(np.float32)).to(dt).cuda()
+    ab, abr = torch.empty(2, N, Cc, device="cuda"), torch.empty(2, N, Cc, device="cuda")
+    L.call("serl_gn_finalize", stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ab[0].data_ptr(), ab[1].data_ptr(), N, Cc, HW, 1e-5, s)
+    L.call("serl_gn_finalize", stats_r.data_ptr(), gamma_r.data_ptr(), beta_r.data_ptr(), abr[0].data_ptr(), abr[1].data_ptr(), N, Cc, HW, 1e-5, s)
+    # affine + relu in place
+    x1, x2 = y.clone(), y.clone()
+    L.call("serl_affine_relu_h16", x1.data_ptr(), ab[0].data_ptr(), ab[1].data_ptr(), N, HW, Cc, fmt, s)
+    L.call("serl_affine_relu_gn_h16", x2.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), N, HW, Cc, 1e-5, fmt, s)
+    assert torch.equal(x1.view(torch.int16), x2.view(torch.int16))
+    # block output, identity and projected residual, 16-bit and fp32 outputs
+    for proj in (False, True):
+        o1, o2 = torch.empty_like(y), torch.empty_like(y)
+        f1, f2 = torch.empty(N, HW, Cc, device="cuda"), torch.empty(N, HW, Cc, device="cuda")
+        for o16a, o32a, o16b, o32b in ((o1, None, o2, None), (None, f1, None, f2)):
+            L.call("serl_block_combine_h16", y.data_ptr(), ab[0].data_ptr(), ab[1].data_ptr(), res.data_ptr(),
+                   abr[0].data_ptr() if proj else None, abr[1].data_ptr() if proj else None,
+                   None if o16a is None else o16a.data_ptr(), None if o32a is None else o32a.data_ptr(), N, HW, Cc, fmt, s)
+            L.call("serl_block_combine_gn_h16", y.data_ptr(), stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), res.data_ptr(),
+                   stats_r.data_ptr() if proj else None, gamma_r.data_ptr() if proj else None, beta_r.data_ptr() if proj else None,
+                   None if o16b is None else o16b.data_ptr(), None if o32b is None else o32b.data_ptr(), N, HW, Cc, 1e-5, fmt, s)
+        assert torch.equal(o1.view(torch.int16), o2.view(torch.int16)) and torch.equal(f1, f2)
+    if Cc == 64:   # pool_finish: (N,32,32,64) maps, statistics of the 64x64 conv output
+        pooled = torch.as_tensor(rng.standard_normal((N, 32, 32, 64)).astype(np.float32)).to(dt).cuda()
+        side = torch.as_tensor(rng.standard_normal((N, 4, 32, 64)).astype(np.float32)).to(dt).cuda()
+        st0 = stats * 4.0                                        # any sums do: count is 64*64*16 here
+        ab0 = torch.empty(2, N, 64, device="cuda")
+        L.call("serl_gn_finalize", st0.data_ptr(), gamma.data_ptr(), beta.data_ptr(), ab0[0].data_ptr(), ab0[1].data_ptr(), N, 64, 4096, 1e-5, s)
+        p1, p2 = torch.empty_like(pooled), torch.empty_like(pooled)
+        L.call("serl_pool_finish_h16", pooled.data_ptr(), side.data_ptr(), ab0[0].data_ptr(), ab0[1].data_ptr(), p1.data_ptr(), N, fmt, s)
+        L.call("serl_pool_finish_gn_h16", pooled.data_ptr(), side.data_ptr(), st0.data_ptr(), gamma.data_ptr(), beta.data_ptr(), p2.data_ptr(),
+               N, 1e-5, fmt, s)
+        assert torch.equal(p1.view(torch.int16), p2.view(torch.int16))
+    torch.cuda.synchronize()
+
+
 @pytest.mark.parametrize("prec,feat_tol,q_tol", [("fp16", 5e-3, 1e-2), ("bf16", 3e-2, 3e-2)])
 def test_16bit_trunk_vs_fp64_oracle_and_downstream_q(prec, feat_tol, q_tol):
     """Whole trunk on tensor cores vs the float64 oracle, then the bar on what north_star names (Q-values, losses).
