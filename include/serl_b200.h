@@ -82,6 +82,9 @@ typedef struct serl_scatter_request {
   const float* state; const float* next_state; const float* actions;
   const float* rewards; const float* masks; const uint8_t* dones;
   const uint8_t* valid;              /* (n) validity byte to store                                     */
+  int64_t row_stride;                /* 0: the fields above are packed (n, ...) arrays; else they point into row 0 of an
+                                      * interleaved staging record and row k lies k*row_stride BYTES further (the whole
+                                      * staged batch then moves host->device as ONE copy)                          */
 } serl_scatter_request;
 
 /* Device side of MemoryEfficientReplayBuffer.insert (memory_efficient_replay_buffer.py:53-89,
@@ -89,6 +92,8 @@ typedef struct serl_scatter_request {
 int serl_replay_scatter(const serl_replay_view* rv, const serl_scatter_request* rq, void* stream);
 int serl_counter_add(uint64_t* counter, uint64_t inc, void* stream);   /* device-resident step counters */
 int serl_replay_set_valid(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n, void* stream);
+/* same + publishes the ring's new size to its device-resident copy (read by graph-replayed sampling launches) */
+int serl_replay_commit(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n, int32_t* size_dev, int32_t size, void* stream);
 
 /* ---- JAX-compatible key schedule and random fills ---------------------------------------------
  * Key slots written by serl_rng_schedule (uint32[2] each), following SACAgent.update's split order

@@ -41,7 +41,8 @@ class BatchOut(C.Structure):
 
 class ScatterRequest(C.Structure):
     _fields_ = [("n", i32), ("dst_slot", vp), ("src_slot", vp), ("frames", vp * MAX_CAMS), ("state", vp),
-                ("next_state", vp), ("actions", vp), ("rewards", vp), ("masks", vp), ("dones", vp), ("valid", vp)]
+                ("next_state", vp), ("actions", vp), ("rewards", vp), ("masks", vp), ("dones", vp), ("valid", vp),
+                ("row_stride", i64)]
 
 
 class GemmDesc(C.Structure):
@@ -72,6 +73,7 @@ _PROTOS = {
     "serl_replay_sample_crop": [C.POINTER(ReplayView), C.POINTER(SampleRequest), C.POINTER(BatchOut), vp],
     "serl_replay_scatter": [C.POINTER(ReplayView), C.POINTER(ScatterRequest), vp],
     "serl_replay_set_valid": [vp, vp, vp, C.c_int, vp],
+    "serl_replay_commit": [vp, vp, vp, C.c_int, vp, C.c_int, vp],
     "serl_counter_add": [vp, u64, vp],
     "serl_rng_schedule": [vp, vp, C.c_int, C.c_int, vp],
     "serl_normal_fill": [vp, vp, C.c_int, vp],
@@ -159,9 +161,30 @@ def require_cuda(device):
         raise SerlError("serl_b200 runs on a CUDA device only (HBM-resident replay and sm_100a kernels; no CPU fallback)")
 
 
-def stream_ptr():
+_stream_objs = {}
+
+
+def _raw_stream():
+    """Raw cudaStream_t of the CURRENT stream.  torch.cuda.current_stream() costs ~15 us of Python per call, which is real
+    time in a loop that synchronises every step; the C getter is ~0.3 us."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    get = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+    if get is None:
+        return torch.cuda.current_stream().cuda_stream
+    return get(torch._C._cuda_getDevice())
+
+
+def _stream_obj():
+    import torch
+    raw = _raw_stream()
+    s = _stream_objs.get(raw)
+    if s is None:
+        s = _stream_objs[raw] = torch.cuda.current_stream()
+    return s
+
+
+def stream_ptr():
+    return _raw_stream()
 
 
 class _Event:
@@ -170,14 +193,13 @@ class _Event:
         self.e = torch.cuda.Event()
 
     def record(self):
-        self.e.record()
+        self.e.record(_stream_obj())
 
     def synchronize(self):
         self.e.synchronize()
 
     def make_current_stream_wait(self):
-        import torch
-        torch.cuda.current_stream().wait_event(self.e)
+        _stream_obj().wait_event(self.e)
 
 
 def new_event():

@@ -367,50 +367,61 @@ struct ScatterArgs {
   const uint8_t* st_frames[SERL_MAX_CAMS];   // (n, frame_bytes)
   const float* st_state; const float* st_next_state; const float* st_actions;
   const float* st_rewards; const float* st_masks; const uint8_t* st_dones; const uint8_t* st_valid;
+  long long row_stride;          // 0: every staging field is a packed (n, ...) array; else: byte distance between rows k, k+1
 };
+
+// staging row k of a field: packed arrays, or fields interleaved in one record per row (one H2D copy per flush)
+template <class T>
+__device__ inline const T* st_row(const T* base, int k, size_t packed_elems, long long stride) {
+  return stride ? reinterpret_cast<const T*>(reinterpret_cast<const uint8_t*>(base) + (size_t)k * (size_t)stride) : base + (size_t)k * packed_elems;
+}
 
 // grid: x = chunk of the frame, y = cam, z = write k.  Ordered writes: launch once per dependency level.
 __global__ void __launch_bounds__(256) replay_scatter_kernel(const ScatterArgs a) {
   const serl_replay_view& rv = a.rv;
   const int k = blockIdx.z, cam = blockIdx.y;
-  const int dst = a.dst_slot[k], ss = a.src_slot[k];
+  const int dst = *st_row(a.dst_slot, k, 1, a.row_stride), ss = *st_row(a.src_slot, k, 1, a.row_stride);
   const size_t fb = (size_t)rv.height * rv.width * rv.channels;
-  const uint8_t* s = ss >= 0 ? rv.frames[cam] + (size_t)ss * fb : a.st_frames[cam] + (size_t)k * fb;
-  uint8_t* d = const_cast<uint8_t*>(rv.frames[cam]) + (size_t)dst * fb;
-  if ((fb & 15) == 0) {
-    const uint4* s4 = reinterpret_cast<const uint4*>(s);
-    uint4* d4 = reinterpret_cast<uint4*>(d);
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < (fb >> 4); q += (size_t)gridDim.x * blockDim.x)
-      d4[q] = s4[q];
-  } else {
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < fb; q += (size_t)gridDim.x * blockDim.x)
-      d[q] = s[q];
+  if (cam < rv.num_cams) {
+    const uint8_t* s = ss >= 0 ? rv.frames[cam] + (size_t)ss * fb : st_row(a.st_frames[cam], k, fb, a.row_stride);
+    uint8_t* d = const_cast<uint8_t*>(rv.frames[cam]) + (size_t)dst * fb;
+    if ((fb & 15) == 0 && ((reinterpret_cast<uintptr_t>(s) | reinterpret_cast<uintptr_t>(d)) & 15) == 0) {
+      const uint4* s4 = reinterpret_cast<const uint4*>(s);
+      uint4* d4 = reinterpret_cast<uint4*>(d);
+      for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < (fb >> 4); q += (size_t)gridDim.x * blockDim.x)
+        d4[q] = s4[q];
+    } else {
+      for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < fb; q += (size_t)gridDim.x * blockDim.x)
+        d[q] = s[q];
+    }
   }
   if (cam == 0 && blockIdx.x == 0) {
     const int ns = rv.num_stack * rv.state_dim;
     float* st = const_cast<float*>(rv.state); float* nst = const_cast<float*>(rv.next_state);
     float* ac = const_cast<float*>(rv.actions);
+    const float* s_st = st_row(a.st_state, k, ns, a.row_stride); const float* s_nst = st_row(a.st_next_state, k, ns, a.row_stride);
+    const float* s_ac = st_row(a.st_actions, k, rv.action_dim, a.row_stride);
     for (int e = threadIdx.x; e < ns; e += blockDim.x) {
-      st[(size_t)dst * ns + e] = ss >= 0 ? rv.state[(size_t)ss * ns + e] : a.st_state[(size_t)k * ns + e];
-      nst[(size_t)dst * ns + e] = ss >= 0 ? rv.next_state[(size_t)ss * ns + e] : a.st_next_state[(size_t)k * ns + e];
+      st[(size_t)dst * ns + e] = ss >= 0 ? rv.state[(size_t)ss * ns + e] : s_st[e];
+      nst[(size_t)dst * ns + e] = ss >= 0 ? rv.next_state[(size_t)ss * ns + e] : s_nst[e];
     }
     for (int e = threadIdx.x; e < rv.action_dim; e += blockDim.x)
-      ac[(size_t)dst * rv.action_dim + e] = ss >= 0 ? rv.actions[(size_t)ss * rv.action_dim + e]
-                                                     : a.st_actions[(size_t)k * rv.action_dim + e];
+      ac[(size_t)dst * rv.action_dim + e] = ss >= 0 ? rv.actions[(size_t)ss * rv.action_dim + e] : s_ac[e];
     if (threadIdx.x == 0) {
-      const_cast<float*>(rv.rewards)[dst] = ss >= 0 ? rv.rewards[ss] : a.st_rewards[k];
-      const_cast<float*>(rv.masks)[dst] = ss >= 0 ? rv.masks[ss] : a.st_masks[k];
-      const_cast<uint8_t*>(rv.dones)[dst] = ss >= 0 ? rv.dones[ss] : a.st_dones[k];
-      const_cast<uint8_t*>(rv.valid)[dst] = a.st_valid[k];
+      const_cast<float*>(rv.rewards)[dst] = ss >= 0 ? rv.rewards[ss] : *st_row(a.st_rewards, k, 1, a.row_stride);
+      const_cast<float*>(rv.masks)[dst] = ss >= 0 ? rv.masks[ss] : *st_row(a.st_masks, k, 1, a.row_stride);
+      const_cast<uint8_t*>(rv.dones)[dst] = ss >= 0 ? rv.dones[ss] : *st_row(a.st_dones, k, 1, a.row_stride);
+      const_cast<uint8_t*>(rv.valid)[dst] = *st_row(a.st_valid, k, 1, a.row_stride);
     }
   }
 }
 
 __global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) { if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += inc; }
 
-__global__ void replay_set_valid_kernel(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n) {
+__global__ void replay_set_valid_kernel(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n, int32_t* size_dev, int32_t size) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) valid[slots[k]] = vals[k];
+  if (k == 0 && size_dev) *size_dev = size;
 }
 
 }  // namespace serl
@@ -487,16 +498,23 @@ extern "C" int serl_replay_scatter(const serl_replay_view* rv, const serl_scatte
   for (int c = 0; c < rv->num_cams; ++c) a.st_frames[c] = rq->frames[c];
   a.st_state = rq->state; a.st_next_state = rq->next_state; a.st_actions = rq->actions;
   a.st_rewards = rq->rewards; a.st_masks = rq->masks; a.st_dones = rq->dones; a.st_valid = rq->valid;
+  a.row_stride = rq->row_stride;
   const size_t fb = (size_t)rv->height * rv->width * rv->channels;
   int chunks = (int)((fb / 16 + 255) / 256); if (chunks < 1) chunks = 1; if (chunks > 16) chunks = 16;
-  dim3 grid(chunks, rv->num_cams, rq->n);
+  dim3 grid(chunks, rv->num_cams > 0 ? rv->num_cams : 1, rq->n);
   replay_scatter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
   return check_launch("replay_scatter_kernel");
 }
 
 extern "C" int serl_replay_set_valid(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n, void* stream) {
   if (n <= 0) return SERL_OK;
-  replay_set_valid_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(valid, slots, vals, n);
+  replay_set_valid_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(valid, slots, vals, n, nullptr, 0);
+  return check_launch("replay_set_valid_kernel");
+}
+
+extern "C" int serl_replay_commit(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n, int32_t* size_dev, int32_t size, void* stream) {
+  if (n < 0 || !size_dev) { set_last_error("serl_replay_commit: invalid arguments"); return SERL_ERR_INVALID; }
+  replay_set_valid_kernel<<<n > 0 ? ceil_div(n, 128) : 1, 128, 0, static_cast<cudaStream_t>(stream)>>>(valid, slots, vals, n, size_dev, size);
   return check_launch("replay_set_valid_kernel");
 }
 

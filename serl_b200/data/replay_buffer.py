@@ -93,27 +93,50 @@ class DeviceRing:
         self._draw_step = 0
         self._dev_step_mirror = 0                                         # host mirror of step_dev (graph replays)
         self._lock = threading.RLock()
-        # pinned staging (struct of arrays) + device mirror
+        # Pinned staging, one interleaved record per staged slot write, behind a small header holding the validity changes:
+        #   [touched slots int32 x 4n | touched values u8 x 4n | record 0 | record 1 | ...]
+        # so a flush is ONE host->device copy of the used prefix, one scatter launch and one commit launch.  Two host
+        # buffers alternate: the copy out of one overlaps the inserts into the other (no host sync per flush).
         n = self.STAGE
-        pin = lambda *s, dt=torch.float32: L.pin(torch.zeros(*s, dtype=dt))
-        self._st = dict(frames={c: pin(n, *self.frame_shape, dt=torch.uint8) for c in self.cams},
-                        state=pin(n, self.T * self.S), next_state=pin(n, self.T * self.S), actions=pin(n, self.A),
-                        rewards=pin(n), masks=pin(n), dones=pin(n, dt=torch.uint8), valid=pin(n, dt=torch.uint8),
-                        dst=pin(n, dt=torch.int32), src=pin(n, dt=torch.int32))
-        # numpy views of the pinned staging area: host-side writes never go through the torch dispatcher
-        self._stn = {k: ({c: t.numpy() for c, t in v.items()} if isinstance(v, dict) else v.numpy()) for k, v in self._st.items()}
-        self._sd = {k: ({c: torch.empty_like(t, device=dev) for c, t in v.items()} if isinstance(v, dict)
-                        else torch.empty_like(v, device=dev)) for k, v in self._st.items()}
-        self._touched_host = pin(n * 4, dt=torch.int32)
-        self._touched_val_host = pin(n * 4, dt=torch.uint8)
-        self._touched_dev = torch.empty(n * 4, dtype=torch.int32, device=dev)
-        self._touched_val_dev = torch.empty(n * 4, dtype=torch.uint8, device=dev)
+        fb = int(np.prod(self.frame_shape)) if self.cams else 0
+        ns = self.T * self.S
+        off, fields = 0, {}
+        for c in self.cams:
+            fields[("frames", c)] = (off, np.uint8, self.frame_shape); off += (fb + 15) // 16 * 16
+        for name, cnt in (("state", ns), ("next_state", ns), ("actions", self.A), ("rewards", 1), ("masks", 1)):
+            fields[name] = (off, np.float32, (cnt,)); off += 4 * cnt
+        for name in ("dst", "src"):
+            fields[name] = (off, np.int32, (1,)); off += 4
+        for name in ("dones", "valid"):
+            fields[name] = (off, np.uint8, (1,)); off += 1
+        self._row_bytes = (off + 15) // 16 * 16
+        self._hdr_bytes = (4 * n * 4 + 4 * n + 15) // 16 * 16
+        self._fields = fields
+        total = self._hdr_bytes + n * self._row_bytes
+        self._stage_host = [L.pin(torch.zeros(total, dtype=torch.uint8)) for _ in range(2)]
+        self._stage_dev = torch.empty(total, dtype=torch.uint8, device=dev)
+        self._stage_evt = [None, None]                                   # copy-out completion of each host buffer
+        self._cur = 0
+        self._stn = [self._stage_views(b.numpy()) for b in self._stage_host]
         self._n_pending = 0
         self._pending_dst = set()
         self._touched = set()
-        self._flush_evt = None
         self._sample_evt = None
         self.h2d_bytes = 0
+
+    def _stage_views(self, base: np.ndarray) -> dict:
+        """Strided numpy views of one staging buffer: field -> (STAGE, ...) array whose row k lives in record k."""
+        n, rb, hb = self.STAGE, self._row_bytes, self._hdr_bytes
+        out = {"touched": base[:4 * n * 4].view(np.int32), "touched_val": base[4 * n * 4:4 * n * 4 + 4 * n], "frames": {}}
+        for key, (off, dt, shape) in self._fields.items():
+            item = np.dtype(dt).itemsize
+            inner = tuple(int(np.prod(shape[i + 1:])) * item for i in range(len(shape)))
+            v = np.ndarray((n, *shape), dtype=dt, buffer=base, offset=hb + off, strides=(rb, *inner))
+            if isinstance(key, tuple):
+                out["frames"][key[1]] = v
+            else:
+                out[key] = v[:, 0] if shape == (1,) else v
+        return out
 
     # ---- reference API ---------------------------------------------------------------------------
     def __len__(self) -> int:
@@ -132,7 +155,10 @@ class DeviceRing:
                 or len(self._touched) > 3 * self.STAGE):
             self.flush()
         k = self._n_pending
-        st = self._stn
+        if k == 0 and self._stage_evt[self._cur] is not None:   # this buffer's previous copy-out (two flushes ago) must be over
+            self._stage_evt[self._cur].synchronize()
+            self._stage_evt[self._cur] = None
+        st = self._stn[self._cur]
         st["dst"][k], st["src"][k] = dst, src_slot
         if src_slot < 0:
             for c in self.cams:
@@ -175,40 +201,40 @@ class DeviceRing:
             stream_ptr = L.stream_ptr()
             if self._sample_evt is not None:
                 self._sample_evt.make_current_stream_wait()   # never overwrite slots a sampling kernel still reads
-            if n:
-                st, sd = self._st, self._sd
-                for k in ("state", "next_state", "actions", "rewards", "masks", "dones", "valid", "dst", "src"):
-                    sd[k][:n].copy_(st[k][:n], non_blocking=True)
-                    self.h2d_bytes += st[k][:n].numel() * st[k].element_size()
-                for c in self.cams:
-                    sd["frames"][c][:n].copy_(st["frames"][c][:n], non_blocking=True)
-                    self.h2d_bytes += st["frames"][c][:n].numel()
-                rq = L.ScatterRequest()
-                rq.n = n
-                rq.dst_slot, rq.src_slot = sd["dst"].data_ptr(), sd["src"].data_ptr()
-                for j, c in enumerate(self.cams):
-                    rq.frames[j] = sd["frames"][c].data_ptr()
-                rq.state, rq.next_state, rq.actions = sd["state"].data_ptr(), sd["next_state"].data_ptr(), sd["actions"].data_ptr()
-                rq.rewards, rq.masks, rq.dones, rq.valid = (sd["rewards"].data_ptr(), sd["masks"].data_ptr(),
-                                                            sd["dones"].data_ptr(), sd["valid"].data_ptr())
-                v = self.view()
-                L.call("serl_replay_scatter", C.byref(v), C.byref(rq), stream_ptr)
-            if self._touched:
-                slots = np.fromiter(self._touched, dtype=np.int32)
-                m = len(slots)
-                self._touched_host.numpy()[:m] = slots
-                self._touched_val_host.numpy()[:m] = self._valid_host[slots]
-                self._touched_dev[:m].copy_(self._touched_host[:m], non_blocking=True)
-                self._touched_val_dev[:m].copy_(self._touched_val_host[:m], non_blocking=True)
-                L.call("serl_replay_set_valid", self.valid.data_ptr(), self._touched_dev.data_ptr(), self._touched_val_dev.data_ptr(),
-                       m, stream_ptr)
             if n or self._touched:
-                self.size_dev.fill_(self._size)
-                # the pinned staging area is reused by the next insert: wait for the copies issued above
+                cur = self._cur
+                if self._stage_evt[cur] is not None:          # only reachable when a flush carries validity changes alone
+                    self._stage_evt[cur].synchronize()
+                    self._stage_evt[cur] = None
+                st, host, dv = self._stn[cur], self._stage_host[cur], self._stage_dev
+                m = len(self._touched)
+                if m:
+                    slots = np.fromiter(self._touched, dtype=np.int32, count=m)
+                    st["touched"][:m] = slots
+                    st["touched_val"][:m] = self._valid_host[slots]
+                nbytes = self._hdr_bytes + n * self._row_bytes
+                dv[:nbytes].copy_(host[:nbytes], non_blocking=True)       # the ONE host->device copy of this flush
+                self.h2d_bytes += nbytes
+                base = dv.data_ptr() + self._hdr_bytes
+                if n:
+                    rq = L.ScatterRequest()
+                    rq.n, rq.row_stride = n, self._row_bytes
+                    f = self._fields
+                    rq.dst_slot, rq.src_slot = base + f["dst"][0], base + f["src"][0]
+                    for j, c in enumerate(self.cams):
+                        rq.frames[j] = base + f[("frames", c)][0]
+                    rq.state, rq.next_state, rq.actions = base + f["state"][0], base + f["next_state"][0], base + f["actions"][0]
+                    rq.rewards, rq.masks, rq.dones, rq.valid = (base + f["rewards"][0], base + f["masks"][0], base + f["dones"][0],
+                                                                base + f["valid"][0])
+                    v = self.view()
+                    L.call("serl_replay_scatter", C.byref(v), C.byref(rq), stream_ptr)
+                # validity changes (applied after the slot writes, like the host ring logic orders them) + the new size
+                L.call("serl_replay_commit", self.valid.data_ptr(), dv.data_ptr(), dv.data_ptr() + 4 * self.STAGE * 4, m,
+                       self.size_dev.data_ptr(), self._size, stream_ptr)
                 evt = L.new_event()
                 evt.record()
-                evt.synchronize()
-                self._flush_evt = evt
+                self._stage_evt[cur] = evt
+                self._cur = cur ^ 1
             self._n_pending = 0
             self._pending_dst.clear()
             self._touched.clear()

@@ -54,7 +54,7 @@ def test_host_ring_bookkeeping_equals_reference_semantics(dry, T, cap, n):
         assert len(rb) == ora.size and rb._insert_index == ora.cursor and rb._first == ora.episode_start
         np.testing.assert_array_equal(rb._valid_host, ora.valid)
     rb.flush()
-    assert "serl_replay_scatter" in dry and "serl_replay_set_valid" in dry
+    assert "serl_replay_scatter" in dry and "serl_replay_commit" in dry
 
 
 def test_drq_learner_iteration_call_sequence(dry):
@@ -76,7 +76,7 @@ def test_drq_learner_iteration_call_sequence(dry):
     agent, info = agent.update_critics(batch)
     assert set(info) == {"critic", "critic_lr", "actor_lr", "temperature_lr"}
     assert set(info["critic"]) == {"critic_loss", "predicted_qs", "target_qs"}
-    seq = [c for c in dry if c not in ("serl_replay_scatter", "serl_replay_set_valid")]     # pending inserts are flushed by sample()
+    seq = [c for c in dry if c not in ("serl_replay_scatter", "serl_replay_set_valid", "serl_replay_commit")]     # pending inserts are flushed by sample()
     assert seq[0] == "serl_rng_schedule" and seq.count("serl_replay_sample_crop") == 2       # online + demo halves
     assert seq.count("serl_conv2d_nhwc_f32") == 2 * 12                                       # 12 convs per camera, ONE trunk pass
     assert seq.count("serl_adam_polyak") == 1 and seq[-1] == "serl_adam_polyak"
