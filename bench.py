@@ -117,6 +117,25 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+TRUNK_KERNELS = {
+    False: "frozen ResNet-10 trunk, fp32 build (conv_igemm_f32 + groupnorm_f32 + maxpool3x3s2_f32)",
+    True: "frozen ResNet-10 trunk, tcgen05 build (stem_tc + conv3x3_tc + conv_tc kernels and their elementwise GroupNorm / pool / residual passes)",
+}
+
+
+def trunk_traffic(args):
+    """DRAM bytes per step of the trunk kernels (dram__bytes_read.sum + dram__bytes_write.sum summed over the trunk's launches of
+    one step) from the committed ncu capture of this same command, or None when no capture matches the configuration."""
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "trunk_traffic.json")
+    try:
+        with open(path) as f:
+            t = json.load(f)
+        key = f"{args.precision}_b{args.batch}_c{args.cams}"
+        return t.get(key, {}).get("dram_bytes_per_step")
+    except (OSError, ValueError):
+        return None
+
+
 def workload_config(args):
     return {"workload": f"async_drq_sim: {args.cams}x 128x128x3 camera, batch {args.batch} (global), replay {args.capacity} in HBM, "
                         "critic grad step incl. sampling + DrQ shift", "global_batch": args.batch, "cams": args.cams,
@@ -335,9 +354,9 @@ def run_b200(args):
             "clocks": clk,
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h / args.steps},
             "gpu_launches": launches, "cuda_graph": True, "replicas_identical": replicas_identical,
-            "roofline": {"kernel": "frozen ResNet-10 trunk (conv_igemm + groupnorm + maxpool kernels)", "bound": "tensor",
+            "roofline": {"kernel": TRUNK_KERNELS[args.precision != "fp32"], "bound": "tensor",
                          "achieved": trunk_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": trunk_tflops / pk["tensor"],
-                         "traffic": None, "peak_source": pk["src"], "ms_per_step": trunk_ms,
+                         "traffic": trunk_traffic(args), "peak_source": pk["src"], "ms_per_step": trunk_ms,
                          "timing": "CUDA events around the trunk section of eagerly launched steps (the headline loop replays a CUDA graph)",
                          "algorithmic": f"{images} images x {TRUNK_GFLOP_PER_IMAGE} GFLOP"},
             "sampler": {"kernel": "sample_frames_kernel", "timing": "20 launches captured in one CUDA graph, replayed 5x, CUDA events", "bound": "hbm", "achieved": samp_gbs, "peak": pk["hbm"], "unit": "GB/s",

@@ -9,6 +9,7 @@ re-associated so that GroupNorm never makes its own pass over HBM:
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -30,6 +31,10 @@ USE_FUSED_STEM_POOL = True
 # GroupNorm affines derived inside the consumers from the conv epilogue sums (no serl_gn_finalize launches in the chain).
 USE_FUSED_GN = True
 GN_EPS = 1e-5
+
+# The 1x1 / stride-2 projection conv of a block only depends on the block input: run it on a side stream next to the
+# conv -> GroupNorm+ReLU -> conv chain (joined before the residual add).
+USE_PROJ_SIDE_STREAM = os.environ.get("SERL_PROJ_SIDE", "1") != "0"
 
 FMT = {"bf16": (L.FMT_BF16, torch.bfloat16), "fp16": (L.FMT_FP16, torch.float16)}
 
@@ -152,6 +157,13 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
         gB, bB = w[f"{b}/MyGroupNorm_1/scale"], w[f"{b}/MyGroupNorm_1/bias"]
         proj = stride != 1 or cin != f
         last = i == len(STAGES) - 1
+        side = engine.side[1] if (proj and USE_PROJ_SIDE_STREAM and hasattr(engine, "side")) else None
+        if proj:
+            gP, bP = w[f"{b}/norm_proj/scale"], w[f"{b}/norm_proj/bias"]
+            if side is not None:
+                side.fork()
+                with side:
+                    _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, sP, N, s, s, cin, so, so, f, 1, stride, 0)
         _conv(p, x, wp[f"{b}/Conv_0/kernel"], yA, sA, N, s, s, cin, so, so, f, 3, stride, lo)
         # materialise relu(GN(yA)) in place (one HBM-speed pass); the conv operands are then plain async copies
         if USE_FUSED_GN:
@@ -160,9 +172,10 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
             abA = _finalize(sA, gA, bA, p.aff[0], N, f, so * so)
             L.call("serl_affine_relu_h16", yA.data_ptr(), abA[0].data_ptr(), abA[1].data_ptr(), N, so * so, f, p.fmt, _s())
         _conv(p, yA, wp[f"{b}/Conv_1/kernel"], yB, sB, N, so, so, f, so, so, f, 3, 1, 1)
-        if proj:
+        if proj and side is None:
             _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, sP, N, s, s, cin, so, so, f, 1, stride, 0)
-            gP, bP = w[f"{b}/norm_proj/scale"], w[f"{b}/norm_proj/bias"]
+        elif proj:
+            side.join()
         o16, o32 = (None if last else out.data_ptr()), (feats.data_ptr() if last else None)
         if USE_FUSED_GN:
             L.call("serl_block_combine_gn_h16", yB.data_ptr(), sB.data_ptr(), gB.data_ptr(), bB.data_ptr(), yP.data_ptr() if proj else x.data_ptr(),
