@@ -115,7 +115,7 @@ _PROTOS = {
     "serl_temperature_loss": [vp, vp, f32, f32, vp, vp, C.c_int, vp],
     "serl_adam_polyak": [C.POINTER(AdamDesc), vp],
 }
-EXPORTS = sorted(list(_PROTOS) + ["serl_last_error", "serl_version", "serl_device_sm_count"])
+EXPORTS = sorted(list(_PROTOS) + ["serl_last_error", "serl_version", "serl_device_sm_count", "serl_launch_count"])
 
 _lib = None
 
@@ -136,6 +136,8 @@ def load():
     lib.serl_last_error.restype = C.c_char_p
     lib.serl_last_error.argtypes = []
     lib.serl_version.restype = C.c_int
+    lib.serl_launch_count.restype = C.c_ulonglong
+    lib.serl_launch_count.argtypes = []
     lib.serl_device_sm_count.argtypes = [C.c_int]
     for name, args in _PROTOS.items():
         fn = getattr(lib, name)
@@ -153,6 +155,11 @@ def call(name: str, *args):
     if rc != 0:
         raise SerlError(f"{name} failed ({rc}): {lib.serl_last_error().decode()}")
     return rc
+
+
+def launch_count() -> int:
+    """Kernels libserl_b200 has enqueued in this process so far (launches recorded into a CUDA graph count once, at capture)."""
+    return int(load().serl_launch_count())
 
 
 # ---- torch plumbing indirections (device memory / streams / events); tests may patch these for dry runs -------

@@ -49,6 +49,7 @@ class SACAgent:
         self.explicit_randomness = None     # tests: dict with eps / dropout / subsample (and crop offsets)
         self.use_cuda_graphs = True         # replay the whole step as one CUDA graph from its 3rd identical call on
         self._graphs = {}
+        self._launch_adj = 0                # graph capture / replay correction of the library's launch counter
 
     # ---- construction (sac.py:322-400,486-542) ------------------------------------------------------
     @classmethod
@@ -111,7 +112,9 @@ class SACAgent:
 
     @property
     def kernel_launches(self) -> int:
-        return sum(e.launches for e in self._engines.values())
+        """Kernels of libserl_b200 executed so far in this process: the library's own launch counter, minus launches that
+        were only recorded during graph capture, plus the recorded count for every replay."""
+        return L.launch_count() + self._launch_adj
 
     # ---- CUDA graphs: the ~150 launches of a step are captured once and replayed -------------------------
     def _graph_key(self, tag, batch):
@@ -138,16 +141,19 @@ class SACAgent:
             ring._dev_step_mirror = p["step"] + 1
         if entry == "warm":
             g = torch.cuda.CUDAGraph()
-            l0, s0 = {b: e.launches for b, e in self._engines.items()}, self.state.step
+            l0, s0, c0 = {b: e.launches for b, e in self._engines.items()}, self.state.step, L.launch_count()
             with torch.cuda.graph(g):
                 body(batch, True)
-            entry = (g, {b: e.launches - l0.get(b, 0) for b, e in self._engines.items()}, self.state.step - s0)
+            recorded = L.launch_count() - c0
+            self._launch_adj -= recorded                              # recorded, not executed
+            entry = (g, {b: e.launches - l0.get(b, 0) for b, e in self._engines.items()}, self.state.step - s0, recorded)
             self._graphs[key] = entry
             self.state.step = s0
             for b, e in self._engines.items():
                 e.launches = l0.get(b, e.launches)
-        g, launches, steps = entry
+        g, launches, steps, recorded = entry
         g.replay()
+        self._launch_adj += recorded
         for b, n in launches.items():
             self._engines[b].launches += n
         self.state.step += steps

@@ -33,6 +33,7 @@ def dry(monkeypatch):
     monkeypatch.setattr(L, "stream_ptr", lambda: 0)
     monkeypatch.setattr(L, "new_event", lambda: Ev())
     monkeypatch.setattr(L, "pin", lambda t: t)
+    monkeypatch.setattr(L, "launch_count", lambda: len(calls))
     return calls
 
 
