@@ -213,6 +213,53 @@ def fill_ring_synthetic(rb, seed):
     rb.size_dev.fill_(cap)
 
 
+def measure_dual_camera_rlpd(args, steps=50):
+    """Supplementary measurement on BASELINE configs[2]: dual 128x128 cameras, batch 256 drawn 50/50 from the online ring and a
+    20-trajectory demo ring (RLPD), same metric, same timing rules (device-resident value + e2e with host insert / loss readback)."""
+    import torch
+    from helpers import fake_env, random_transitions
+    from serl_b200.utils.launcher import make_drq_agent, make_replay_buffer
+    from serl_b200.utils.train_utils import concat_batches
+    cams, half = ("cam0", "cam1"), args.batch // 2
+    env = fake_env(cams)
+    rb = make_replay_buffer(env, capacity=args.capacity, type="memory_efficient_replay_buffer", image_keys=list(cams), seed=2000)
+    demo = make_replay_buffer(env, capacity=20 * 101, type="memory_efficient_replay_buffer", image_keys=list(cams), seed=2001)
+    fill_ring_synthetic(rb, seed=7)
+    fill_ring_synthetic(demo, seed=8)
+    rng = np.random.default_rng(1)
+    trs = random_transitions(rng, 8, cams, mean_ep=1000)
+    agent = make_drq_agent(42, trs[0]["observations"], trs[0]["actions"], image_keys=cams, encoder_type="resnet-pretrained", precision=args.precision)
+    it = rb.get_iterator(sample_args={"batch_size": half, "pack_obs_and_next_obs": True})
+    dit = demo.get_iterator(sample_args={"batch_size": args.batch - half, "pack_obs_and_next_obs": True})
+    nxt = lambda: concat_batches(next(it), next(dit), axis=0)
+    for _ in range(5):
+        agent.update_critics(nxt())
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        agent.update_critics(nxt())
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / steps
+    h0, e0 = rb.h2d_bytes, time.perf_counter()
+    for s in range(steps):
+        rb.insert(trs[s % len(trs)])
+        _, info = agent.update_critics(nxt())
+        loss = float(info["critic"]["critic_loss"])
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - e0) * 1e3 / steps
+    assert np.isfinite(loss)
+    out = {"workload": f"async_drq_sim + demos (50/50 RLPD): 2x 128x128x3 cameras, batch {args.batch} = {half} online + {args.batch - half} demo, "
+                       f"replay {args.capacity} + {20 * 101} in HBM, critic grad step incl. sampling + DrQ shift",
+           "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps,
+           "e2e": {"value": 1e3 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": (rb.h2d_bytes - h0) / steps, "d2h_bytes_per_step": 4.0}}
+    agent._graphs.clear()
+    del agent, rb, demo
+    torch.cuda.synchronize()
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -361,6 +408,12 @@ def run_b200(args):
                          "algorithmic": f"{images} images x {TRUNK_GFLOP_PER_IMAGE} GFLOP"},
             "sampler": {"kernel": "sample_frames_kernel", "timing": "20 launches captured in one CUDA graph, replayed 5x, CUDA events", "bound": "hbm", "achieved": samp_gbs, "peak": pk["hbm"], "unit": "GB/s",
                         "frac": samp_gbs / pk["hbm"], "ms_per_step": samp_ms, "algorithmic_bytes": samp_bytes}}
+    if world == 1 and args.cams == 1 and not os.environ.get("SERL_BENCH_SKIP_DUAL"):
+        # the stock sim script is dual-camera: report BASELINE configs[2] beside the headline configuration
+        try:
+            line["dual_camera_rlpd"] = measure_dual_camera_rlpd(args)
+        except Exception as e:                  # noqa: BLE001
+            line["dual_camera_rlpd"] = {"value": None, "error": str(e)}
     try:
         if os.environ.get("SERL_BENCH_SKIP_CPU"):
             raise RuntimeError("skipped (SERL_BENCH_SKIP_CPU)")
