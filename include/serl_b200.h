@@ -205,6 +205,8 @@ int serl_layernorm_tanh_fwd(const float* z, int ld_z, const float* scale, const 
 int serl_layernorm_tanh_bwd(const float* dt, int ld_dt, const float* t, int ld_t, const float* xhat, const float* rstd,
                             const float* scale, int rows_per_group, int group_stride, float* dz, float* dy,
                             float* dscale, float* dbias, int R, int D, void* stream);
+int serl_layernorm_param_grad(const float* dy, const float* xhat, float* dscale, float* dbias, int rows_per_group, int R, int D,
+                              void* stream);   /* dscale/dbias half of serl_layernorm_tanh_bwd (when it was called with NULLs) */
 int serl_colsum_f32(const float* x, float* out, int groups, int rows, int D, long long ld, int accumulate, void* stream);
 int serl_copy2d_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int R, int D, void* stream);
 int serl_fill_f32(float* x, float v, int n, void* stream);

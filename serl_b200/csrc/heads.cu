@@ -228,6 +228,18 @@ extern "C" int serl_layernorm_tanh_bwd(const float* dt, int ld_dt, const float* 
   return SERL_OK;
 }
 
+// the parameter-gradient half of serl_layernorm_tanh_bwd on its own (dy, xhat as that call left them): lets the caller put it
+// on a side stream, off the dz -> next-layer chain
+extern "C" int serl_layernorm_param_grad(const float* dy, const float* xhat, float* dscale, float* dbias, int rows_per_group, int R, int D,
+                                         void* stream) {
+  if (!dy || !xhat || !dscale || !dbias || rows_per_group < 1 || R % rows_per_group != 0) {
+    set_last_error("serl_layernorm_param_grad: invalid arguments"); return SERL_ERR_INVALID;
+  }
+  const int groups = R / rows_per_group;
+  ln_param_grad_kernel<<<groups * ceil_div(D, 32), 256, 0, ST(stream)>>>(dy, xhat, dscale, dbias, groups, rows_per_group, D);
+  return check_launch("ln_param_grad_kernel");
+}
+
 extern "C" int serl_copy2d_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int R, int D, void* stream) {
   size_t total = (size_t)R * D;
   int blocks = (int)((total + 255) / 256); if (blocks > 1184) blocks = 1184; if (blocks < 1) blocks = 1;

@@ -110,7 +110,7 @@ class Engine:
             self.enc_xhat_p, self.enc_rstd_p = e(B, 64), e(B)
             self.masks_u8 = {c: torch.empty(B, 4096, dtype=torch.uint8, device=device) for c in cfg.cams}
             self.d_enc_z = {c: e(B, 256) for c in cfg.cams}          # per camera: the side stream reads it while the next one is written
-            self.d_enc_y, self.d_sle = e(B, 256), e(B, 4096)
+            self.d_enc_y, self.d_sle = {c: e(B, 256) for c in cfg.cams}, e(B, 4096)
             self.d_enc_zp, self.d_enc_yp = e(B, 64), e(B, 64)
         self.sc_main = _EncScratch(cfg, B, device, self.ws)
         self.sc_side = [_EncScratch(cfg, B, device, w) for w in self.ws_side]
@@ -125,7 +125,7 @@ class Engine:
         self.sub = torch.zeros(2, dtype=torch.int32, device=device)
         # gradient scratch
         self.dh, self.dz, self.dy = e(E * B, 256), e(E * B, 256), e(E * B, 256)
-        self.dz0 = e(E * B, 256)                                    # layer-0 dz: layer-1's is still read by the side stream
+        self.dz0, self.dy0 = e(E * B, 256), e(E * B, 256)           # layer-0 dz / dy: layer-1's are still read by the side stream
         self.dX = e(B, self.FA)
         self.dmu, self.dls = e(B, A), e(B, A)
         self.pdh, self.pdz, self.pdy = e(B, 256), e(B, 256), e(B, 256)
@@ -218,11 +218,13 @@ class Engine:
         for j, cam in enumerate(cfg.cams):
             p = f"{ENC}/encoder_{cam}"
             dez = self.d_enc_z[cam]
+            dey = self.d_enc_y[cam]
             ops.ln_tanh_bwd(ops.at(dX, 256 * j), ld, ops.at(X, 256 * j), ld, self.enc_xhat[cam].data_ptr(), self.enc_rstd[cam].data_ptr(),
-                            self.P(st.params, f"{p}/LayerNorm_0/scale"), B, 0, dez.data_ptr(), self.d_enc_y.data_ptr(),
-                            self.P(G, f"{p}/LayerNorm_0/scale"), self.P(G, f"{p}/LayerNorm_0/bias"), B, 256)
+                            self.P(st.params, f"{p}/LayerNorm_0/scale"), B, 0, dez.data_ptr(), dey.data_ptr(), None, None, B, 256)
             side.fork()
             with side:
+                ops.ln_param_grad(dey.data_ptr(), self.enc_xhat[cam].data_ptr(), self.P(G, f"{p}/LayerNorm_0/scale"),
+                                  self.P(G, f"{p}/LayerNorm_0/bias"), B, B, 256)
                 ops.dense_bwd_weight(wss, self.sle_saved[cam].data_ptr(), 4096, dez.data_ptr(), 256, self.P(G, f"{p}/Dense_0/kernel"),
                                      B, 4096, 256)
                 ops.colsum(dez.data_ptr(), self.P(G, f"{p}/Dense_0/bias"), 1, B, 256, 256)
@@ -234,9 +236,11 @@ class Engine:
         off = 256 * len(cfg.cams)
         ops.ln_tanh_bwd(ops.at(dX, off), ld, ops.at(X, off), ld, self.enc_xhat_p.data_ptr(), self.enc_rstd_p.data_ptr(),
                         self.P(st.params, f"{ENC}/LayerNorm_0/scale"), B, 0, self.d_enc_zp.data_ptr(), self.d_enc_yp.data_ptr(),
-                        self.P(G, f"{ENC}/LayerNorm_0/scale"), self.P(G, f"{ENC}/LayerNorm_0/bias"), B, 64)
+                        None, None, B, 64)
         side.fork()
         with side:
+            ops.ln_param_grad(self.d_enc_yp.data_ptr(), self.enc_xhat_p.data_ptr(), self.P(G, f"{ENC}/LayerNorm_0/scale"),
+                              self.P(G, f"{ENC}/LayerNorm_0/bias"), B, B, 64)
             ops.dense_bwd_weight(wss, state.data_ptr(), cfg.state_in, self.d_enc_zp.data_ptr(), 64, self.P(G, f"{ENC}/Dense_0/kernel"),
                                  B, cfg.state_in, 64)
             ops.colsum(self.d_enc_zp.data_ptr(), self.P(G, f"{ENC}/Dense_0/bias"), 1, B, 64, 64)
@@ -269,7 +273,7 @@ class Engine:
         G, Pm = st.grad, st.params
         c = "modules_critic/network"
         FA, R = self.FA, E * B
-        dh, dz, dz0, dy = self.dh.data_ptr(), self.dz.data_ptr(), self.dz0.data_ptr(), self.dy.data_ptr()
+        dh, dz, dz0, dy, dy0 = self.dh.data_ptr(), self.dz.data_ptr(), self.dz0.data_ptr(), self.dy.data_ptr(), self.dy0.data_ptr()
         side, wss = self.side[0], self.ws_side[0]
         wk = self.P(Pm, "modules_critic/Dense_0/kernel")
         if param_grads:
@@ -287,20 +291,20 @@ class Engine:
         else:
             ops.dense_bwd_input(ws, dq.data_ptr(), 1, wk, dh, 256, B, 256, 1, Z=E, dz_z=B, w_z=256, dx_z=B * 256)
         ops.ln_tanh_bwd(dh, 256, acts.h2.data_ptr(), 256, acts.xhat2.data_ptr(), acts.rstd2.data_ptr(), self.P(Pm, f"{c}/LayerNorm_1/scale"), B, 256,
-                        dz, dy, self.P(G, f"{c}/LayerNorm_1/scale") if param_grads else None,
-                        self.P(G, f"{c}/LayerNorm_1/bias") if param_grads else None, R, 256)
+                        dz, dy, None, None, R, 256)
         if param_grads:
             side.fork()
             with side:
+                ops.ln_param_grad(dy, acts.xhat2.data_ptr(), self.P(G, f"{c}/LayerNorm_1/scale"), self.P(G, f"{c}/LayerNorm_1/bias"), B, R, 256)
                 ops.dense_bwd_weight(wss, acts.h1.data_ptr(), 256, dz, 256, self.P(G, f"{c}/Dense_1/kernel"), B, 256, 256, Z=E, x_z=B * 256, dz_z=B * 256)
                 ops.colsum(dz, self.P(G, f"{c}/Dense_1/bias"), E, B, 256, 256)
         ops.dense_bwd_input(ws, dz, 256, self.P(Pm, f"{c}/Dense_1/kernel"), dh, 256, B, 256, 256, Z=E, dz_z=B * 256, dx_z=B * 256)
         ops.ln_tanh_bwd(dh, 256, acts.h1.data_ptr(), 256, acts.xhat1.data_ptr(), acts.rstd1.data_ptr(), self.P(Pm, f"{c}/LayerNorm_0/scale"), B, 256,
-                        dz0, dy, self.P(G, f"{c}/LayerNorm_0/scale") if param_grads else None,
-                        self.P(G, f"{c}/LayerNorm_0/bias") if param_grads else None, R, 256)
+                        dz0, dy0, None, None, R, 256)
         if param_grads:
             side.fork()
             with side:
+                ops.ln_param_grad(dy0, acts.xhat1.data_ptr(), self.P(G, f"{c}/LayerNorm_0/scale"), self.P(G, f"{c}/LayerNorm_0/bias"), B, R, 256)
                 ops.dense_bwd_weight(wss, X.data_ptr(), FA, dz0, 256, self.P(G, f"{c}/Dense_0/kernel"), B, FA, 256, Z=E, x_z=0, dz_z=B * 256)
                 ops.colsum(dz0, self.P(G, f"{c}/Dense_0/bias"), E, B, 256, 256)
         if need_dx:       # input is broadcast over the ensemble: dX = sum_e dZ1_e W1_e^T

@@ -118,6 +118,10 @@ def ln_tanh_bwd(dt, ld_dt, t, ld_t, xhat, rstd, scale, rows_per_group, group_str
            dbias, R, D, _s())
 
 
+def ln_param_grad(dy, xhat, dscale, dbias, rows_per_group, R, D):
+    L.call("serl_layernorm_param_grad", dy, xhat, dscale, dbias, rows_per_group, R, D, _s())
+
+
 def colsum(x, out, groups, rows, D, ld, accumulate=False):
     L.call("serl_colsum_f32", x, out, groups, rows, D, ld, int(accumulate), _s())
 
