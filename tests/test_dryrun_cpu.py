@@ -58,6 +58,39 @@ def test_host_ring_bookkeeping_equals_reference_semantics(dry, T, cap, n):
     assert "serl_replay_scatter" in dry and "serl_replay_commit" in dry
 
 
+def test_staging_records_are_what_the_scatter_kernel_will_read(dry):
+    """Host insert path: every staged slot write is one interleaved record; field k of row r must sit at
+    header + r*row_bytes + offset(k) - the addressing serl_replay_scatter uses with row_stride = row_bytes."""
+    cams = ("a", "b")
+    rb = _ring(cams, 50, 8, 1)
+    trs = random_transitions(np.random.default_rng(3), 5, cams, 8, 1, mean_ep=100)
+    for tr in trs:
+        rb.insert(tr)
+    n = rb._n_pending
+    assert n >= len(trs)                                     # frame-dedup inserts stage obs and next_obs slots
+    raw = rb._stage_host[rb._cur].numpy()
+    st = rb._stn[rb._cur]
+    hb, rbytes, f = rb._hdr_bytes, rb._row_bytes, rb._fields
+    assert rbytes % 16 == 0 and hb % 16 == 0
+    for k in range(n):
+        base = hb + k * rbytes
+        for c in cams:
+            off, _, shape = f[("frames", c)]
+            np.testing.assert_array_equal(raw[base + off: base + off + int(np.prod(shape))].reshape(shape), st["frames"][c][k])
+        for name in ("state", "next_state", "actions", "rewards", "masks"):
+            off, _, shape = f[name]
+            np.testing.assert_array_equal(raw[base + off: base + off + 4 * shape[0]].view(np.float32), np.atleast_1d(st[name][k]))
+        for name in ("dst", "src"):
+            assert raw[base + f[name][0]: base + f[name][0] + 4].view(np.int32)[0] == st[name][k]
+        for name in ("dones", "valid"):
+            assert raw[base + f[name][0]] == st[name][k]
+    # the staged frames are the inserted ones (last transition's next observation went to the last record)
+    np.testing.assert_array_equal(st["frames"]["a"][n - 1], np.asarray(trs[-1]["next_observations"]["a"]).reshape(8, 8, 3))
+    cur = rb._cur
+    rb.flush()
+    assert rb._cur == cur ^ 1 and rb._n_pending == 0          # double-buffered: the next inserts go to the other buffer
+
+
 def test_drq_learner_iteration_call_sequence(dry):
     from serl_b200.utils.launcher import make_drq_agent
     from serl_b200.utils.train_utils import concat_batches
