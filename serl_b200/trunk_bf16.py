@@ -1,10 +1,13 @@
-"""bf16 / tcgen05 build of the frozen ResNet-10 trunk: orchestration + one-time weight packing.
+"""16-bit / tcgen05 build of the frozen ResNet-10 trunk: orchestration + one-time weight packing.
 
 Same layer algebra as the fp32 build (engine.Engine.trunk_forward; reference vision/resnet_v1.py:217-286),
 re-associated so that GroupNorm never makes its own pass over HBM:
-  conv (tensor cores) writes the raw bf16 output and accumulates the GroupNorm sums in its epilogue;
-  a tiny finalize kernel turns the sums into per-(image, channel) affines;
-  the NEXT conv applies relu(a*x+b) to its operand while gathering it (max-pool / block-combine do the same).
+  every conv (tensor cores) writes its raw 16-bit output and accumulates the GroupNorm sums in its epilogue;
+  the consumer of that output derives the per-(image, channel) affine from the sums in registers and applies it:
+    stem:   the 3x3/2 max-pool runs inside the stem epilogue on sign-adjusted raw values, `pool_finish` applies relu(|a|x+b);
+    Conv_0: `affine_relu` materialises relu(GN(y)) in place (one HBM-speed pass), so Conv_1's operands are plain async copies;
+    Conv_1 / conv_proj: `block_combine` applies both affines, adds the residual and the ReLU.
+The projection conv of a block runs on a side stream next to the Conv_0 -> Conv_1 chain.
 """
 from __future__ import annotations
 
