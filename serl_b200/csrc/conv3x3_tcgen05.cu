@@ -100,14 +100,23 @@ constexpr int C3_THREADS = 320;       // warps 0-3 epilogue | 4-7 patch producer
 // gather of tile i+1, the MMAs of tile i and the epilogue of tile i-1 overlap.
 // kResidentB (Ci == 64, Co == BN): the whole 9-tap weight tensor (9 x BN x 128 B) is loaded ONCE per CTA and stays in
 // shared memory - a persistent CTA then streams only input patches (1 CTA / SM, BSTAGES must be 9).
-template <class F, int BN, int BSTAGES, int PSTAGES, bool kResidentB>
+//
+// kCoalEpi (EXPERIMENTAL, opt-in with SERL_C3_COAL=1, not yet validated on hardware - see DESIGN.md section 8): the default
+// epilogue lets every thread store its own output row, so one STG.128 touches 32 different 128-byte lines = 32 L1TEX
+// data-pipe wavefronts; ncu shows those stores taking 29 % of the data pipe that also feeds the tensor cores' operand
+// reads (49 %) and the weight TMA writes.  The variant transposes 64-channel groups through a per-warp 4 KB shared tile
+// so that a store instruction covers 4 rows x 128 contiguous bytes (4 wavefronts): 96 instead of 256 wavefronts per group.
+constexpr int C3_EPI_STAGE = 4 * 32 * 128;             // 4 epilogue warps x 32 rows x 128 B
+
+template <class F, int BN, int BSTAGES, int PSTAGES, bool kResidentB, bool kCoalEpi = false>
 __global__ void __launch_bounds__(C3_THREADS, kResidentB ? 1 : 2) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap wmap, const Conv3Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_STAGE = BN * 128;
   uint8_t* sP = smem;                                   // PSTAGES patches
   uint8_t* sB = smem + PSTAGES * a.patch_bytes;
-  uint64_t* pfull = reinterpret_cast<uint64_t*>(sB + BSTAGES * B_STAGE);
+  uint8_t* sEpi = sB + BSTAGES * B_STAGE;               // kCoalEpi: per-warp output transpose tiles
+  uint64_t* pfull = reinterpret_cast<uint64_t*>(sEpi + (kCoalEpi ? C3_EPI_STAGE : 0));
   uint64_t* pempty = pfull + PSTAGES;
   uint64_t* bfull = pempty + PSTAGES;
   uint64_t* bempty = bfull + BSTAGES;
@@ -216,9 +225,31 @@ __global__ void __launch_bounds__(C3_THREADS, kResidentB ? 1 : 2) conv3x3_tc_ker
           const int g = (n0 + c0) / a.Cg - g_first;
 #pragma unroll
           for (int gg = 0; gg < MAXG; ++gg) if (gg == g) { gs[gg] += s; gss[gg] += ss; }
-          uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)opix * a.Co + n0 + c0);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if constexpr (!kCoalEpi) {
+            uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)opix * a.Co + n0 + c0);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        if constexpr (kCoalEpi) {
+          // row = lane; 16-byte chunk ch of the 64-channel group at lane*128 + ((ch ^ (lane & 7)) << 4): conflict-free both ways
+          uint8_t* tile = sEpi + warp * (32 * 128);
+          const int ch = (c0 & 48) >> 3;
+          *reinterpret_cast<uint4*>(tile + lane * 128 + ((ch ^ (lane & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(tile + lane * 128 + (((ch + 1) ^ (lane & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if ((c0 & 48) == 48) {                                 // 64 channels staged: store them 4 rows x 128 B per instruction
+            __syncwarp();
+            const int cgrp = c0 - 48;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = (lane >> 3) + 4 * i, cc = lane & 7;
+              const int opix_r = __shfl_sync(0xffffffffu, opix, r);
+              const int valid_r = __shfl_sync(0xffffffffu, (int)valid, r);
+              const uint4 v4 = *reinterpret_cast<const uint4*>(tile + r * 128 + ((cc ^ (r & 7)) << 4));
+              if (valid_r) *reinterpret_cast<uint4*>(a.y + (size_t)opix_r * a.Co + n0 + cgrp + cc * 8) = v4;
+            }
+            __syncwarp();
+          }
         }
       }
       // accumulator drained: hand the TMEM stage back before the (slower) statistics
@@ -332,10 +363,10 @@ static EncodeTiledFn get_encode() {
   return fn;
 }
 
-template <class F, int BN, int BSTAGES, int PSTAGES, bool kResidentB>
+template <class F, int BN, int BSTAGES, int PSTAGES, bool kResidentB, bool kCoalEpi = false>
 static int launch_conv3(const CUtensorMap& map, const Conv3Args& a, cudaStream_t st) {
-  const size_t smem = (size_t)PSTAGES * a.patch_bytes + (size_t)BSTAGES * BN * 128 + 1024 + 256;
-  auto kern = conv3x3_tc_kernel<F, BN, BSTAGES, PSTAGES, kResidentB>;
+  const size_t smem = (size_t)PSTAGES * a.patch_bytes + (size_t)BSTAGES * BN * 128 + (kCoalEpi ? C3_EPI_STAGE : 0) + 1024 + 256;
+  auto kern = conv3x3_tc_kernel<F, BN, BSTAGES, PSTAGES, kResidentB, kCoalEpi>;
   static size_t configured = 0;
   if (smem > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv3x3_tc)");
@@ -382,6 +413,10 @@ extern "C" int serl_conv3x3s1_tc_h16(const serl_conv_tc_desc* d, int base_offset
   // shared memory: BN=64: 2 patches (25 KiB) + 7 weight stages (8 KiB); BN=128: 2 patches (<=21 KiB) + 4 weight stages (16 KiB).
   //            with Ci == 64 as well the 72 KiB weight tensor stays resident (1 CTA / SM, 4 patches)
   const bool resident = false && BN == 64 && d->Ci == 64;   // measured slower than two streaming CTAs per SM (profiles/r01_trunk_kernels.md)
+  static int coal = -1;                                   // EXPERIMENTAL coalesced epilogue, off unless SERL_C3_COAL=1
+  if (coal < 0) { const char* e = getenv("SERL_C3_COAL"); coal = (e && atoi(e) != 0) ? 1 : 0; }
+  if (coal && d->fmt == SERL_FMT_FP16)                     // 16 KB of the weight ring goes to the transpose tiles
+    return BN == 64 ? launch_conv3<C3Fp16, 64, 5, 2, false, true>(map, a, st) : launch_conv3<C3Fp16, 128, 3, 2, false, true>(map, a, st);
   if (d->fmt == SERL_FMT_FP16) {
     if (resident) return launch_conv3<C3Fp16, 64, 9, 4, true>(map, a, st);
     return BN == 64 ? launch_conv3<C3Fp16, 64, 7, 2, false>(map, a, st) : launch_conv3<C3Fp16, 128, 4, 2, false>(map, a, st);
