@@ -101,7 +101,7 @@ constexpr int C3_THREADS = 320;       // warps 0-3 epilogue | 4-7 patch producer
 // kResidentB (Ci == 64, Co == BN): the whole 9-tap weight tensor (9 x BN x 128 B) is loaded ONCE per CTA and stays in
 // shared memory - a persistent CTA then streams only input patches (1 CTA / SM, BSTAGES must be 9).
 //
-// kCoalEpi (EXPERIMENTAL, opt-in with SERL_C3_COAL=1, not yet validated on hardware - see DESIGN.md section 8): the default
+// kCoalEpi (EXPERIMENTAL, opt-in with SERL_EPI_COAL=1, not yet validated on hardware - see DESIGN.md section 8): the default
 // epilogue lets every thread store its own output row, so one STG.128 touches 32 different 128-byte lines = 32 L1TEX
 // data-pipe wavefronts; ncu shows those stores taking 29 % of the data pipe that also feeds the tensor cores' operand
 // reads (49 %) and the weight TMA writes.  The variant transposes 64-channel groups through a per-warp 4 KB shared tile
@@ -413,8 +413,8 @@ extern "C" int serl_conv3x3s1_tc_h16(const serl_conv_tc_desc* d, int base_offset
   // shared memory: BN=64: 2 patches (25 KiB) + 7 weight stages (8 KiB); BN=128: 2 patches (<=21 KiB) + 4 weight stages (16 KiB).
   //            with Ci == 64 as well the 72 KiB weight tensor stays resident (1 CTA / SM, 4 patches)
   const bool resident = false && BN == 64 && d->Ci == 64;   // measured slower than two streaming CTAs per SM (profiles/r01_trunk_kernels.md)
-  static int coal = -1;                                   // EXPERIMENTAL coalesced epilogue, off unless SERL_C3_COAL=1
-  if (coal < 0) { const char* e = getenv("SERL_C3_COAL"); coal = (e && atoi(e) != 0) ? 1 : 0; }
+  static int coal = -1;                                   // EXPERIMENTAL coalesced epilogue, off unless SERL_EPI_COAL=1
+  if (coal < 0) { const char* e = getenv("SERL_EPI_COAL"); coal = (e && atoi(e) != 0) ? 1 : 0; }
   if (coal && d->fmt == SERL_FMT_FP16)                     // 16 KB of the weight ring goes to the transpose tiles
     return BN == 64 ? launch_conv3<C3Fp16, 64, 5, 2, false, true>(map, a, st) : launch_conv3<C3Fp16, 128, 3, 2, false, true>(map, a, st);
   if (d->fmt == SERL_FMT_FP16) {

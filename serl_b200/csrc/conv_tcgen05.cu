@@ -129,14 +129,19 @@ __device__ inline void tc_tma_2d(void* smem_dst, const CUtensorMap* map, int c0,
 //   warp 8     tcgen05.mma issuer       warp 9   TMA issuer for the weight (B) tile of every k-block
 // A/B share one stage ring (full = 128 deferred cp.async arrivals + 1 expect_tx arrival, empty = tcgen05.commit); TMEM holds
 // two accumulators (afull / aempty) so tile i+1's mainloop overlaps tile i's epilogue.
-template <class F, int BN, int STAGES, bool kStem, bool kAffine>
+// kCoalEpi (EXPERIMENTAL, opt-in with SERL_EPI_COAL=1, not yet validated on hardware - DESIGN.md section 8): the default
+// epilogue stores one output row per thread (32 data-pipe wavefronts per STG.128); the variant transposes 32-channel groups
+// through a per-warp 2 KB shared tile so that a store instruction covers 8 rows x 64 contiguous bytes.
+constexpr int TC_EPI_STAGE = 4 * 32 * 64;
+
+template <class F, int BN, int STAGES, bool kStem, bool kAffine, bool kCoalEpi = false>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const ConvTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_STAGE = BN * TC_BK * 2;
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * TC_A_STAGE;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + STAGES * B_STAGE + (kCoalEpi ? TC_EPI_STAGE : 0));   // kCoalEpi: transpose tiles first
   uint64_t* empty = full + STAGES;
   uint64_t* afull = empty + STAGES;
   uint64_t* aempty = afull + 2;
@@ -250,9 +255,30 @@ __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_con
             float* st = a.stats + ((size_t)n_img * 4 + (n0 + c0) / a.Cg) * 2;
             atomicAdd(st, s); atomicAdd(st + 1, ss);
           }
-          uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)gm * a.Co + n0 + c0);
-          dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if constexpr (!kCoalEpi) {
+            uint4* dst = reinterpret_cast<uint4*>(a.y + (size_t)gm * a.Co + n0 + c0);
+            dst[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            dst[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        if constexpr (kCoalEpi) {
+          // row = lane; 16-byte chunk ch of the 32-channel group at lane*64 + ((ch ^ ((lane >> 1) & 3)) << 4): conflict-free both ways
+          uint8_t* tile = sB + STAGES * B_STAGE + warp * (32 * 64);
+          const int ch = (c0 & 16) >> 3, sw = (lane >> 1) & 3;
+          *reinterpret_cast<uint4*>(tile + lane * 64 + ((ch ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(tile + lane * 64 + (((ch + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          if (c0 & 16) {                                          // 32 channels staged: 8 rows x 64 contiguous bytes per store
+            __syncwarp();
+            const int cgrp = c0 - 16;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r = (lane >> 2) + 8 * i, cc = lane & 3;
+              const int gm_r = m0 + warp * 32 + r;
+              const uint4 v4 = *reinterpret_cast<const uint4*>(tile + r * 64 + ((cc ^ ((r >> 1) & 3)) << 4));
+              if (ok && gm_r < a.M) *reinterpret_cast<uint4*>(a.y + (size_t)gm_r * a.Co + n0 + cgrp + cc * 8) = v4;
+            }
+            __syncwarp();
+          }
         }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -771,10 +797,10 @@ static TcEncodeTiledFn tc_get_encode() {
   return fn;
 }
 
-template <class F, int BN, int STAGES, bool kStem, bool kAffine>
+template <class F, int BN, int STAGES, bool kStem, bool kAffine, bool kCoalEpi = false>
 static int launch_conv_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
-  constexpr size_t smem = (size_t)STAGES * (TC_A_STAGE + BN * TC_BK * 2) + 1024 + 256;
-  auto kern = conv_tc_kernel<F, BN, STAGES, kStem, kAffine>;
+  constexpr size_t smem = (size_t)STAGES * (TC_A_STAGE + BN * TC_BK * 2) + (kCoalEpi ? TC_EPI_STAGE : 0) + 1024 + 256;
+  auto kern = conv_tc_kernel<F, BN, STAGES, kStem, kAffine, kCoalEpi>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv_tc)");
@@ -843,6 +869,9 @@ static int conv_tc_dispatch(const serl_conv_tc_desc* d, ConvTcArgs& a, cudaStrea
   }
   a.cblocks = d->Ci / 64; a.num_kb = d->kh * d->kw * a.cblocks;
   if (d->in_a) { set_last_error("serl_conv2d_tc_h16: operand transform is not supported (materialise GroupNorm+ReLU with serl_affine_relu_h16)"); return SERL_ERR_UNSUPPORTED; }
+  static int coal = -1;                                   // EXPERIMENTAL coalesced epilogue, off unless SERL_EPI_COAL=1
+  if (coal < 0) { const char* e = getenv("SERL_EPI_COAL"); coal = (e && atoi(e) != 0) ? 1 : 0; }
+  if (coal) return d->Co == 64 ? launch_conv_tc<F, 64, 4, false, false, true>(a, d->fmt, st) : launch_conv_tc<F, 128, 3, false, false, true>(a, d->fmt, st);
   if (d->Co == 64) return launch_conv_tc<F, 64, 4, false, false>(a, d->fmt, st);
   return launch_conv_tc<F, 128, 3, false, false>(a, d->fmt, st);
 }
