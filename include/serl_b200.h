@@ -106,7 +106,7 @@ enum {
 int serl_rng_schedule(uint32_t* rng_state, uint32_t* keys, int do_aug, int do_update, void* stream);
 int serl_normal_fill(const uint32_t* key, float* out, int n, void* stream);            /* jax.random.normal   */
 int serl_dropout_mask_fill(const uint32_t* key, uint32_t fold, float keep, uint8_t* mask, int n, void* stream);
-int serl_subsample_idx(const uint32_t* key, int ensemble, int32_t* out /*2*/, void* stream); /* sac.py:153-158 */
+int serl_subsample_idx(const uint32_t* key, int ensemble, int32_t* out /*n*/, int n, void* stream); /* randint(key,(n,),0,E), sac.py:153-158 */
 
 /* Host mirrors of the integer RNG specs (same code compiled for the host; usable without a GPU). */
 int serl_host_rng_schedule(uint32_t* rng_state_host, uint32_t* keys_host, int do_aug, int do_update);
@@ -235,6 +235,13 @@ typedef struct serl_adam_desc {
   float b1, b2, eps, tau;
   int32_t polyak;            /* soft target update after the step                                 */
   float* lr_out;             /* optional device float[3]                                          */
+  /* Flat-buffer extras (serl_b200/params.py): `n` counts parameter slots only; indices in
+     [seg_end[0], seg_end[0] + gap) hold no parameter (info scalars of the gradient buffer) and are
+     skipped.  Leaves in [aux_lo, aux_hi) are updated by TWO transforms (reference
+     common/common.py:136-168: the proprio encoder gets gradients from the critic loss AND from the
+     actor loss, common/encoding.py:48-70): group 0 through grad/m/v[i] and group 1 (the actor tx)
+     through grad/m/v[i + aux_off]; the two updates are summed before they are applied.            */
+  int32_t gap, aux_lo, aux_hi, aux_off;
 } serl_adam_desc;
 int serl_adam_polyak(const serl_adam_desc* d, void* stream);
 

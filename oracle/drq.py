@@ -120,9 +120,11 @@ def trunk_forward(params: Dict[str, torch.Tensor], cam: str, images_u8: torch.Te
 
 
 def encode(params, cams: Sequence[str], feats: Dict[str, torch.Tensor], state: torch.Tensor,
-           dropout_masks: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+           dropout_masks: Optional[Dict[str, torch.Tensor]] = None, stop_gradient: bool = False) -> torch.Tensor:
     """encoding.py:26-72 with the per-camera head of resnet_v1.py:340-374.
-    feats[cam] (B,4,4,512); state (B,T,S); dropout_masks[cam] (B,4096) bool keep-mask or None."""
+    feats[cam] (B,4,4,512); state (B,T,S); dropout_masks[cam] (B,4096) bool keep-mask or None.
+    stop_gradient (encoding.py:48-49): applied to each per-camera IMAGE embedding only - the proprio
+    Dense -> LayerNorm -> tanh below (:55-70) stays differentiable."""
     outs = []
     for cam in cams:
         pre = f"{ENC}/encoder_{cam}"
@@ -134,7 +136,8 @@ def encode(params, cams: Sequence[str], feats: Dict[str, torch.Tensor], state: t
             sle = torch.where(dropout_masks[cam], sle / keep, torch.zeros_like(sle))
         z = sle @ params[f"{pre}/Dense_0/kernel"] + params[f"{pre}/Dense_0/bias"]
         z = layer_norm(z, params[f"{pre}/LayerNorm_0/scale"], params[f"{pre}/LayerNorm_0/bias"])
-        outs.append(torch.tanh(z))
+        img = torch.tanh(z)
+        outs.append(img.detach() if stop_gradient else img)               # encoding.py:48-49
     s = state.reshape(state.shape[0], -1).to(outs[0].dtype)
     z = s @ params[f"{ENC}/Dense_0/kernel"] + params[f"{ENC}/Dense_0/bias"]
     z = layer_norm(z, params[f"{ENC}/LayerNorm_0/scale"], params[f"{ENC}/LayerNorm_0/bias"])
@@ -307,11 +310,11 @@ def _features(state: OracleState, cfg: OracleConfig, obs: dict, dtype):
     return feats
 
 
-def _enc(params, cfg, feats, obs_state, masks):
+def _enc(params, cfg, feats, obs_state, masks, stop_gradient=False):
     if not cfg.pixel:
         return torch.as_tensor(np.asarray(obs_state)).to(next(iter(params.values())).dtype)
     m = None if masks is None else {c: torch.as_tensor(v) for c, v in masks.items()}
-    return encode(params, cfg.cams, feats, torch.as_tensor(np.asarray(obs_state)), m)
+    return encode(params, cfg.cams, feats, torch.as_tensor(np.asarray(obs_state)), m, stop_gradient)
 
 
 def update(state: OracleState, cfg: OracleConfig, batch: dict, rnd: UpdateRandomness,
@@ -358,11 +361,11 @@ def update(state: OracleState, cfg: OracleConfig, batch: dict, rnd: UpdateRandom
     if "actor" in nets:                                               # sac.py:193-221
         r = rnd.actor
         temperature = F.softplus(const[lam]).detach()
-        with torch.no_grad():
-            enc_o = _enc(const, cfg, feats_o, obs["state"], r.dropout if cfg.pixel else None)
-        if not cfg.pixel:
-            enc_o = _enc(const, cfg, None, obs["state"], None)
-        mu, sd = policy_forward(leaves, enc_o)                        # encoder output stop-gradiented (:185)
+        # forward_policy(obs, grad_params=params) (sac.py:198-200) -> Policy.__call__: encoder(obs, train, stop_gradient=True)
+        # (actor_critic_nets.py:185).  EncodingWrapper stops the gradient at the per-camera image embeddings ONLY
+        # (encoding.py:48-49); the proprio Dense/LayerNorm (:55-70) is differentiated w.r.t. `leaves`.
+        enc_o = _enc(leaves, cfg, feats_o, obs["state"], r.dropout if cfg.pixel else None, stop_gradient=True)
+        mu, sd = policy_forward(leaves, enc_o)
         a, logp = tanh_normal_sample_logp(mu, sd, torch.as_tensor(r.eps))
         with torch.no_grad():
             enc_c = _enc(const, cfg, feats_o, obs["state"], None)

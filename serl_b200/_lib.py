@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libserl_b200.so")
 MAX_CAMS = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 (KEY_CROP_OBS, KEY_CROP_NEXT, KEY_CRITIC_NEXT, KEY_CRITIC_SUBSAMPLE, KEY_ACTOR_DROPOUT, KEY_ACTOR_SAMPLE,
  KEY_TEMP_NEXT) = range(7)
@@ -66,7 +66,8 @@ class StemPoolDesc(C.Structure):
 class AdamDesc(C.Structure):
     _fields_ = [("params", vp), ("target", vp), ("m", vp), ("v", vp), ("grad", vp), ("n", i32), ("seg_end", i32 * 3),
                 ("live", i32 * 3), ("counts", vp), ("lr", f32 * 3), ("warmup", i32 * 3), ("b1", f32), ("b2", f32),
-                ("eps", f32), ("tau", f32), ("polyak", i32), ("lr_out", vp)]
+                ("eps", f32), ("tau", f32), ("polyak", i32), ("lr_out", vp), ("gap", i32), ("aux_lo", i32),
+                ("aux_hi", i32), ("aux_off", i32)]
 
 
 _PROTOS = {
@@ -78,7 +79,7 @@ _PROTOS = {
     "serl_rng_schedule": [vp, vp, C.c_int, C.c_int, vp],
     "serl_normal_fill": [vp, vp, C.c_int, vp],
     "serl_dropout_mask_fill": [vp, u32, f32, vp, C.c_int, vp],
-    "serl_subsample_idx": [vp, C.c_int, vp, vp],
+    "serl_subsample_idx": [vp, C.c_int, vp, C.c_int, vp],
     "serl_host_rng_schedule": [vp, vp, C.c_int, C.c_int],
     "serl_host_crop_offsets": [vp, C.c_int, C.c_int, vp],
     "serl_host_draw_indices": [u64, u64, u32, C.c_int, C.c_int, vp, vp],

@@ -49,6 +49,7 @@ class SACAgent:
         self.explicit_randomness = None     # tests: dict with eps / dropout / subsample (and crop offsets)
         self.use_cuda_graphs = True         # replay the whole step as one CUDA graph from its 3rd identical call on
         self._graphs = {}
+        self._graphs_version = store.version   # captured graphs bake parameter-derived state (packed trunk weights, stem sign mask)
         self._launch_adj = 0                # graph capture / replay correction of the library's launch counter
 
     # ---- construction (sac.py:322-400,486-542) ------------------------------------------------------
@@ -100,9 +101,18 @@ class SACAgent:
     def replace(self, **kw):
         if "state" in kw:
             self.state = kw.pop("state")
+            self.invalidate_graphs()
         if kw:
             raise TypeError(f"replace: unknown fields {sorted(kw)}")
         return self
+
+    def invalidate_graphs(self):
+        """Drops every captured CUDA graph (and the packed 16-bit trunk weights derived from the fp32 ones): called when
+        parameters were written from outside the step (`state.replace(params=...)`, checkpoint restore)."""
+        self._graphs.clear()
+        self._graphs_version = self._store.version
+        for eng in self._engines.values():
+            eng.__dict__.pop("_tc_weights", None)
 
     # ---- engines ---------------------------------------------------------------------------------
     def _engine(self, B: int) -> Engine:
@@ -128,6 +138,8 @@ class SACAgent:
     def _run_step(self, key, batch, body):
         """body(batch, graph_mode) enqueues one step.  1st call with a key: eager (warm-up: lazy allocations, function
         attributes); 2nd: capture + replay; later: replay only."""
+        if self._graphs_version != self._store.version:          # TrainState.replace(params=...) since the last capture
+            self.invalidate_graphs()
         if key is None:
             return body(batch, False)
         entry = self._graphs.get(key)
@@ -142,8 +154,16 @@ class SACAgent:
         if entry == "warm":
             g = torch.cuda.CUDAGraph()
             l0, s0, c0 = {b: e.launches for b, e in self._engines.items()}, self.state.step, L.launch_count()
-            with torch.cuda.graph(g):
-                body(batch, True)
+            # thread-local capture mode + the ring locks: a DataStore insert thread must not enqueue its flush (an H2D copy
+            # on another stream) into - or invalidate - this capture
+            import contextlib
+            with contextlib.ExitStack() as stack:
+                for p in batch.parts:
+                    lock = getattr(p["ring"], "_lock", None)
+                    if lock is not None:
+                        stack.enter_context(lock)
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    body(batch, True)
             recorded = L.launch_count() - c0
             self._launch_adj -= recorded                              # recorded, not executed
             entry = (g, {b: e.launches - l0.get(b, 0) for b, e in self._engines.items()}, self.state.step - s0, recorded)
@@ -240,19 +260,16 @@ class SACAgent:
             for cam in self._cfg.cams:
                 eng.trunk_forward(cam, eng.pix[cam], eng.feats[cam])
 
-    def _world(self) -> int:
-        dist = _dist()
-        return dist.get_world_size() if (dist is not None and self.data_parallel) else 1
+    def _dp(self, pmap_axis) -> bool:
+        """ONE predicate for both halves of the data-parallel exchange (1/world pre-scaling in the loss kernels and the SUM
+        all-reduce): the reference's `pmap_axis is not None`, or the `data_parallel` switch, in a multi-rank job."""
+        return (pmap_axis is not None or self.data_parallel) and _dist() is not None
 
-    def _allreduce(self, eng: Engine, lo: int, hi: int):
-        """jax.lax.pmean(grads_and_aux) (common.py:213-214): the loss kernels already scale their gradients by 1/world
-        (grad_scale), so a SUM all-reduce of the live gradient segment yields the mean; info scalars are averaged."""
-        dist = _dist()
-        if dist is None:
-            return
-        dist.all_reduce(self._store.grad[lo:hi], op=dist.ReduceOp.SUM)
-        dist.all_reduce(eng.info[:12], op=dist.ReduceOp.SUM)
-        eng.info[:12].mul_(1.0 / dist.get_world_size())
+    def _allreduce(self, lo: int, hi: int):
+        """jax.lax.pmean(grads_and_aux) (common.py:213-214) as ONE collective: the loss kernels scale gradients AND info
+        scalars by 1/world, and the infos sit inside the flat gradient buffer next to the segment they belong to
+        (params.py), so a single SUM all-reduce of [lo, hi) yields the mean of both."""
+        _dist().all_reduce(self._store.grad[lo:hi], op=_dist().ReduceOp.SUM)
 
     def _update_on_engine(self, eng: Engine, nets: FrozenSet[str], pmap_axis=None, schedule_keys: bool = True, want_info: bool = True):
         assert nets.issubset(ALL_NETS), f"Invalid gradient steps: {nets}"
@@ -261,24 +278,24 @@ class SACAgent:
             eng.launches += 1
         expl = self.explicit_randomness
         st = self._store
-        gscale = 1.0 / self._world() if (pmap_axis is not None or self.data_parallel) else 1.0
+        dp = self._dp(pmap_axis)
+        gscale = 1.0 / _dist().get_world_size() if dp else 1.0
+        at = "actor" in nets or "temperature" in nets
         if "critic" in nets:
             eng.critic_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl)
-        if "actor" in nets or "temperature" in nets:
-            if not ("actor" in nets and "temperature" in nets):
-                raise NotImplementedError("actor and temperature are updated together (update_high_utd, sac.py:586-590)")
-            eng.actor_temp_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl)
-        if pmap_axis is not None or self.data_parallel:
-            if "critic" in nets:
-                self._allreduce(eng, 0, st.seg_end[0])
-            if "actor" in nets:
-                self._allreduce(eng, st.seg_end[0], st.seg_end[2])
+        if at:
+            # any subset is legal (sac.py:270-277): a network that is not updated contributes a zero gradient, its tx still ticks
+            eng.actor_temp_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl, do_actor="actor" in nets,
+                                          do_temperature="temperature" in nets)
+        if dp and nets:
+            # [group 0 | critic infos] and/or [actor, temperature infos | groups 1, 2 | aux]: one contiguous range either way
+            self._allreduce(0 if "critic" in nets else st.info_off + 4, st.n if at else st.info_off + 4)
         eng.optimizer_step([int("critic" in nets), int("actor" in nets), int("temperature" in nets)], polyak="critic" in nets)
         self.state.step += 1
         return self._info(eng, nets) if want_info else None
 
     def _info(self, eng: Engine, nets) -> dict:
-        snap = eng.info.clone()
+        snap = torch.cat([eng.info[:12], eng.lr_info])
         info = {"critic": {}, "actor": {}, "temperature": {}}
         if "critic" in nets:
             info["critic"] = {"critic_loss": snap[0], "predicted_qs": snap[1], "target_qs": snap[2]}

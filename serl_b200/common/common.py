@@ -45,16 +45,23 @@ class TrainState:
 
     @property
     def opt_states(self) -> dict:
-        """Three full-tree Adam states like the reference's (common.py:243); leaves outside a tx's own
-        group are identically zero there, so they are synthesised as zeros here."""
+        """Three full-tree Adam states like the reference's (common.py:243).  A leaf's moments under a tx that never sees
+        a non-zero gradient for it are identically zero and are synthesised here; the proprio-encoder leaves are live under
+        BOTH the critic tx (main buffer) and the actor tx (aux tail of the flat buffers, params.py)."""
         st = self._store
         counts = st.counts.cpu().numpy()
         mu, nu = st.dump(st.m), st.dump(st.v)
+        mu_aux, nu_aux = st.dump_aux(st.m), st.dump_aux(st.v)
         out = {}
         for gid, name in ((1, "actor"), (0, "critic"), (2, "temperature")):
             own = {l.path for l in st.spec if l.group == gid}
-            z = lambda d: nest({k: (v if k in own else np.zeros_like(v)) for k, v in d.items()})
-            out[name] = {"count": int(counts[gid]), "mu": z(mu), "nu": z(nu)}
+
+            def z(d, aux):
+                t = {k: (v if k in own else np.zeros_like(v)) for k, v in d.items()}
+                if gid == 1:
+                    t.update(aux)
+                return nest(t)
+            out[name] = {"count": int(counts[gid]), "mu": z(mu, mu_aux), "nu": z(nu, nu_aux)}
         return out
 
     # -- functional-style updates ------------------------------------------------------------------
@@ -80,6 +87,7 @@ class TrainState:
             os_ = kw.pop("opt_states")
             mu = {l.path: None for l in st.spec}
             nu = dict(mu)
+            mu_aux, nu_aux = {}, {}
             counts = [0, 0, 0]
             for gid, name in ((1, "actor"), (0, "critic"), (2, "temperature")):
                 fm, fn = flatten(os_[name]["mu"]), flatten(os_[name]["nu"])
@@ -87,8 +95,10 @@ class TrainState:
                 for l in st.spec:
                     if l.group == gid:
                         mu[l.path], nu[l.path] = fm[l.path], fn[l.path]
-            st.load(st.m, mu)
-            st.load(st.v, nu)
+                    elif gid == 1 and st.two_tx(l.path):                  # actor-tx twin of the proprio encoder
+                        mu_aux[l.path], nu_aux[l.path] = fm[l.path], fn[l.path]
+            st.load(st.m, mu, mu_aux)
+            st.load(st.v, nu, nu_aux)
             st.counts.copy_(torch.tensor(counts, dtype=torch.int32))
         if kw:
             raise TypeError(f"TrainState.replace: unknown fields {sorted(kw)}")

@@ -35,7 +35,7 @@ unsigned long long launch_count() { return g_launches.load(std::memory_order_rel
 }  // namespace serl
 
 extern "C" const char* serl_last_error(void) { return serl::g_err; }
-extern "C" int serl_version(void) { return 1; }
+extern "C" int serl_version(void) { return 2; }
 extern "C" unsigned long long serl_launch_count(void) { return serl::launch_count(); }
 extern "C" int serl_device_sm_count(int device) {
   int n = 0;

@@ -56,8 +56,17 @@ __global__ void dropout_mask_kernel(const uint32_t* key, uint32_t fold, float ke
   mask[j] = bits_to_uniform01(jax_random_bits_at(k, (uint32_t)n, (uint32_t)j)) < keep ? 1 : 0;
 }
 
-__global__ void subsample_idx_kernel(const uint32_t* key, int ensemble, int32_t* out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) { int a, b; jax_randint2(u32x2{key[0], key[1]}, (uint32_t)ensemble, &a, &b); out[0] = a; out[1] = b; }
+// jax.random.randint(key, (n,), 0, ensemble) (sac.py:152-158): k1, k2 = split(key); element j combines word j of
+// random_bits(k1, (n,)) and random_bits(k2, (n,)) exactly like jax_randint2 does for n = 2.
+__global__ void subsample_idx_kernel(const uint32_t* key, int ensemble, int32_t* out, int n) {
+  const int j = threadIdx.x;
+  if (blockIdx.x != 0 || j >= n) return;
+  const u32x2 k{key[0], key[1]};
+  const uint32_t span = (uint32_t)ensemble;
+  const uint32_t hb = jax_random_bits_at(jax_split_at(k, 2, 0), (uint32_t)n, (uint32_t)j);
+  const uint32_t lb = jax_random_bits_at(jax_split_at(k, 2, 1), (uint32_t)n, (uint32_t)j);
+  uint32_t mult = 65536u % span; mult = (mult * mult) % span;
+  out[j] = (int)(((hb % span) * mult + (lb % span)) % span);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -92,7 +101,9 @@ __global__ void tanh_gaussian_fwd_kernel(const float* __restrict__ mu, const flo
 // TD target + critic loss.  One CTA; E*B is a few thousand.
 //   y_b = r_b + gamma * mask_b * min_j Q'[sub_j, b]  (- alpha * logp'_b if backup_entropy)
 //   loss = mean_{e,b} (Q[e,b] - y_b)^2 ; dQ[e,b] = 2 (Q - y) / (E*B) * grad_scale
-// info[0..2] = {critic_loss, mean Q, mean y}
+// info[0..2] = {critic_loss, mean Q, mean y} * grad_scale: grad_scale = 1/world under data parallelism, so that the ONE
+// SUM all-reduce that carries the gradients also turns the per-rank infos into their mean (jax.lax.pmean(grads_and_aux),
+// common.py:213-214); 1 otherwise.  Same convention in actor_loss_kernel / temperature_loss_kernel.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) critic_loss_kernel(const float* __restrict__ q, const float* __restrict__ q_next,
                                                            const int32_t* __restrict__ sub, int n_sub,
@@ -124,7 +135,7 @@ __global__ void __launch_bounds__(1024) critic_loss_kernel(const float* __restri
   }
   block_sum2(sl, sq, red);
   block_sum2(sy, dummy, red);
-  if (threadIdx.x == 0) { info[0] = sl / (float)(E * B); info[1] = sq / (float)(E * B); info[2] = sy / (float)B; }
+  if (threadIdx.x == 0) { info[0] = grad_scale * sl / (float)(E * B); info[1] = grad_scale * sq / (float)(E * B); info[2] = grad_scale * sy / (float)B; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -161,7 +172,7 @@ __global__ void __launch_bounds__(1024) actor_loss_kernel(const float* __restric
     }
   }
   block_sum2(sobj, slp, red);
-  if (threadIdx.x == 0) { info[0] = -sobj / (float)B; info[1] = alpha; info[2] = -slp / (float)B; }
+  if (threadIdx.x == 0) { info[0] = grad_scale * -sobj / (float)B; info[1] = grad_scale * alpha; info[2] = grad_scale * -slp / (float)B; }
 }
 
 // dQ seed for the actor pass: every entry -grad_scale/(E*B)
@@ -180,16 +191,18 @@ __global__ void __launch_bounds__(1024) temperature_loss_kernel(const float* __r
   block_sum2(s, dummy, red);
   if (threadIdx.x == 0) {
     const float ent = -s / (float)B, lam = lagrange[0];
-    info[0] = softplusf(lam) * (ent - target_entropy);
+    info[0] = grad_scale * softplusf(lam) * (ent - target_entropy);
     dlagrange[0] = grad_scale * (1.f / (1.f + expf(-lam))) * (ent - target_entropy);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Fused optimizer step over the flat trainable buffer.
-// Every `update` call ticks all three txs (common.py:142-147).  Each trainable leaf belongs to exactly
-// one tx group (its gradient under the other two is identically zero, so their moments stay 0 and their
-// updates are exactly 0 - see DESIGN.md "Adam groups").  For group gid: g = live ? grad : 0.
+// Every `update` call ticks all three txs (common.py:142-147).  A trainable leaf whose gradient under a tx is
+// identically zero keeps zero moments and a zero update there, so only the txs that ever see a non-zero gradient
+// need state: one per leaf, except the proprio-encoder leaves [aux_lo, aux_hi), which the critic loss AND the actor
+// loss both differentiate (encoding.py:48-70: stop_gradient covers the image embeddings only) - they carry a second
+// (actor-tx) moment pair in the aux tail.  For group gid: g = live ? grad : 0.
 //   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p += -lr_t * (m / (1-b1^t)) / (sqrt(v / (1-b2^t)) + eps)
 // then, if polyak: target = p_new * tau + target * (1 - tau)   (common.py:131-133, over the whole tree).
 // counts[3] (device, int32) are incremented by the tail thread; lr_t follows optimizers.py:23-29.
@@ -197,29 +210,40 @@ __global__ void __launch_bounds__(1024) temperature_loss_kernel(const float* __r
 struct AdamArgs {
   float* p; float* target; float* m; float* v; const float* grad;
   int n;
-  int seg_end[3];            // flat layout: [0,seg_end[0]) group 0, [seg_end[0],seg_end[1]) group 1, ...
+  int seg_end[3];            // flat layout: [0,seg_end[0]) group 0, gap, [seg_end[0]+gap,seg_end[1]) group 1, ...
   int live[3];
   int32_t* counts;           // per group
   float lr[3]; int warmup[3];
   float b1, b2, eps, tau;
   int polyak;
   float* lr_out;             // (3) learning rates actually used (info["*_lr"])
+  int gap, aux_lo, aux_hi, aux_off;   // info gap after group 0; leaves with a second (actor-tx) Adam state at [i + aux_off]
 };
+
+// one optax adam transform on one element: returns the update -lr * mhat / (sqrt(vhat) + eps)
+__device__ inline float adam_update(const AdamArgs& a, int gid, float g, float* mp, float* vp) {
+  const int cnt = a.counts[gid];
+  const float t = (float)(cnt + 1);
+  const float lr = cnt < a.warmup[gid] ? a.lr[gid] * ((float)cnt / (float)a.warmup[gid]) : a.lr[gid];
+  const float m = a.b1 * *mp + (1.f - a.b1) * g;
+  const float v = a.b2 * *vp + (1.f - a.b2) * g * g;
+  *mp = m; *vp = v;
+  const float mhat = m / (1.f - powf(a.b1, t));
+  const float vhat = v / (1.f - powf(a.b2, t));
+  return (mhat / (sqrtf(vhat) + a.eps)) * (-lr);             // optax: scale_by_adam then scale(-lr)
+}
 
 __global__ void adam_polyak_kernel(const AdamArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
+  if (i >= a.seg_end[0] && i < a.seg_end[0] + a.gap) return;   // info scalars, not parameters
   const int gid = i < a.seg_end[0] ? 0 : (i < a.seg_end[1] ? 1 : 2);
-  const int cnt = a.counts[gid];
-  const float t = (float)(cnt + 1);
-  const float lr = cnt < a.warmup[gid] ? a.lr[gid] * ((float)cnt / (float)a.warmup[gid]) : a.lr[gid];
-  const float g = a.live[gid] ? a.grad[i] : 0.f;
-  const float m = a.b1 * a.m[i] + (1.f - a.b1) * g;
-  const float v = a.b2 * a.v[i] + (1.f - a.b2) * g * g;
-  a.m[i] = m; a.v[i] = v;
-  const float mhat = m / (1.f - powf(a.b1, t));
-  const float vhat = v / (1.f - powf(a.b2, t));
-  const float pn = a.p[i] + (mhat / (sqrtf(vhat) + a.eps)) * (-lr);   // optax: scale_by_adam then scale(-lr)
+  float u = adam_update(a, gid, a.live[gid] ? a.grad[i] : 0.f, a.m + i, a.v + i);
+  if (i >= a.aux_lo && i < a.aux_hi) {                         // second transform (actor tx); updates summed in tx order actor, critic
+    const int j = i + a.aux_off;
+    u = adam_update(a, 1, a.live[1] ? a.grad[j] : 0.f, a.m + j, a.v + j) + u;
+  }
+  const float pn = a.p[i] + u;
   a.p[i] = pn;
   if (a.polyak) a.target[i] = pn * a.tau + a.target[i] * (1.f - a.tau);
 }
@@ -272,8 +296,9 @@ extern "C" int serl_dropout_mask_fill(const uint32_t* key, uint32_t fold, float 
   return check_launch("dropout_mask_kernel");
 }
 
-extern "C" int serl_subsample_idx(const uint32_t* key, int ensemble, int32_t* out, void* stream) {
-  subsample_idx_kernel<<<1, 32, 0, ST(stream)>>>(key, ensemble, out);
+extern "C" int serl_subsample_idx(const uint32_t* key, int ensemble, int32_t* out, int n, void* stream) {
+  if (n < 1 || n > 32 || ensemble < 1 || ensemble > 65535) { set_last_error("serl_subsample_idx: need 1 <= n <= 32, 1 <= ensemble < 65536"); return SERL_ERR_INVALID; }
+  subsample_idx_kernel<<<1, 32, 0, ST(stream)>>>(key, ensemble, out, n);
   return check_launch("subsample_idx_kernel");
 }
 
@@ -321,6 +346,10 @@ extern "C" int serl_adam_polyak(const serl_adam_desc* d, void* stream) {
   a.p = d->params; a.target = d->target; a.m = d->m; a.v = d->v; a.grad = d->grad; a.n = d->n; a.counts = d->counts;
   for (int g = 0; g < 3; ++g) { a.seg_end[g] = d->seg_end[g]; a.live[g] = d->live[g]; a.lr[g] = d->lr[g]; a.warmup[g] = d->warmup[g]; }
   a.b1 = d->b1; a.b2 = d->b2; a.eps = d->eps; a.tau = d->tau; a.polyak = d->polyak; a.lr_out = d->lr_out;
+  a.gap = d->gap; a.aux_lo = d->aux_lo; a.aux_hi = d->aux_hi; a.aux_off = d->aux_off;
+  if (a.gap < 0 || a.aux_lo > a.aux_hi || (a.aux_hi > a.aux_lo && (a.aux_lo < 0 || a.aux_hi > d->seg_end[0] || a.aux_lo + a.aux_off < d->n))) {
+    set_last_error("serl_adam_polyak: invalid gap / aux range"); return SERL_ERR_INVALID;
+  }
   adam_polyak_kernel<<<ceil_div(d->n, 256), 256, 0, ST(stream)>>>(a);
   if (int e = check_launch("adam_polyak_kernel")) return e;
   adam_tick_kernel<<<1, 32, 0, ST(stream)>>>(a);

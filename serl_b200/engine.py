@@ -22,7 +22,7 @@ import torch
 
 from . import _lib as L
 from . import ops
-from .params import ENC, STAGES, ParamStore
+from .params import ENC, INFO_GAP, STAGES, ParamStore
 
 f32 = torch.float32
 
@@ -112,6 +112,9 @@ class Engine:
             self.d_enc_z = {c: e(B, 256) for c in cfg.cams}          # per camera: the side stream reads it while the next one is written
             self.d_enc_y, self.d_sle = {c: e(B, 256) for c in cfg.cams}, e(B, 4096)
             self.d_enc_zp, self.d_enc_yp = e(B, 64), e(B, 64)
+            # actor pass: the proprio Dense/LayerNorm stays differentiable under the policy's stop_gradient (encoding.py:48-70)
+            self.enc_xhat_pa, self.enc_rstd_pa = e(B, 64), e(B)
+            self.dXp_p, self.d_enc_zpa, self.d_enc_ypa = e(B, 64), e(B, 64), e(B, 64)
         self.sc_main = _EncScratch(cfg, B, device, self.ws)
         self.sc_side = [_EncScratch(cfg, B, device, w) for w in self.ws_side]
         # critic / policy activations
@@ -122,15 +125,19 @@ class Engine:
         self.mu, self.ls, self.u, self.std, self.eps = e(B, A), e(B, A), e(B, A), e(B, A), e(B, A)
         self.logp = e(B)
         self.act_scratch = e(B, A)
-        self.sub = torch.zeros(2, dtype=torch.int32, device=device)
+        self.sub = torch.zeros(max(cfg.subsample or 1, 1), dtype=torch.int32, device=device)
         # gradient scratch
         self.dh, self.dz, self.dy = e(E * B, 256), e(E * B, 256), e(E * B, 256)
         self.dz0, self.dy0 = e(E * B, 256), e(E * B, 256)           # layer-0 dz / dy: layer-1's are still read by the side stream
         self.dX = e(B, self.FA)
         self.dmu, self.dls = e(B, A), e(B, A)
         self.pdh, self.pdz, self.pdy = e(B, 256), e(B, 256), e(B, 256)
-        self.info = torch.zeros(16, dtype=f32, device=device)      # [0:3] critic, [4:7] actor, [8] temp, [12:15] lrs
-        self.info_hist = torch.zeros(16, dtype=f32, device=device)
+        # info scalars live INSIDE the flat gradient buffer (params.py: info gap), next to the segments they travel with in
+        # the data-parallel all-reduce: [0:3] critic | [4:7] actor, [8] temperature.  Learning rates are separate.
+        self.info = store.grad[store.info_off:store.info_off + INFO_GAP]
+        self.info.zero_()
+        self.info_hist = torch.zeros(INFO_GAP, dtype=f32, device=device)
+        self.lr_info = torch.zeros(4, dtype=f32, device=device)
         self.launches = 0
 
     # ------------------------------------------------------------------------------------------
@@ -183,7 +190,9 @@ class Engine:
 
     # ---- trainable encoder heads (common/encoding.py:26-72, vision/resnet_v1.py:340-374) -------
     def encode(self, buf, feats_rows: slice, state: torch.Tensor, out: torch.Tensor, ld_out: int,
-               masks: Optional[Dict[str, torch.Tensor]], save: bool, sc: Optional[_EncScratch] = None):
+               masks: Optional[Dict[str, torch.Tensor]], save: bool, sc: Optional[_EncScratch] = None, save_proprio_actor: bool = False):
+        """save: keep what the critic-loss backward needs (every head).  save_proprio_actor: keep the proprio LayerNorm
+        statistics for the ACTOR-loss backward (the only encoder branch the policy's stop_gradient leaves differentiable)."""
         sc = sc or self.sc_main
         cfg, B, ws = self.cfg, self.B, sc.ws
         if not cfg.pixel:
@@ -203,9 +212,10 @@ class Engine:
             self.launches += 4
         ops.dense_fwd(ws, state.data_ptr(), cfg.state_in, self.P(buf, f"{ENC}/Dense_0/kernel"), self.P(buf, f"{ENC}/Dense_0/bias"),
                       sc.enc_zp.data_ptr(), 64, B, cfg.state_in, 64)
+        xh, rs = (self.enc_xhat_p, self.enc_rstd_p) if save else ((self.enc_xhat_pa, self.enc_rstd_pa) if save_proprio_actor else (None, None))
         ops.ln_tanh_fwd(sc.enc_zp.data_ptr(), 64, self.P(buf, f"{ENC}/LayerNorm_0/scale"), self.P(buf, f"{ENC}/LayerNorm_0/bias"),
-                        B, 0, ops.at(out, 256 * len(cfg.cams)), ld_out, self.enc_xhat_p.data_ptr() if save else None,
-                        self.enc_rstd_p.data_ptr() if save else None, B, 64)
+                        B, 0, ops.at(out, 256 * len(cfg.cams)), ld_out, None if xh is None else xh.data_ptr(),
+                        None if rs is None else rs.data_ptr(), B, 64)
         self.launches += 2
 
     def encode_backward(self, dX: torch.Tensor, X: torch.Tensor, feats_rows: slice, state: torch.Tensor):
@@ -352,6 +362,19 @@ class Engine:
         ops.dense_bwd_weight(ws, Xp.data_ptr(), F, dz, 256, self.P(G, f"{n}/Dense_0/kernel"), B, F, 256)
         ops.colsum(dz, self.P(G, f"{n}/Dense_0/bias"), 1, B, 256, 256)
         self.launches += 17
+        if self.cfg.pixel:
+            # Policy.__call__ -> encoder(..., stop_gradient=True) (actor_critic_nets.py:185) stops the gradient at the per-camera
+            # image embeddings only (encoding.py:48-49); the proprio Dense -> LayerNorm -> tanh (:55-70) is differentiated by
+            # jax.grad(policy_loss_fn) w.r.t. the full tree (sac.py:198-200).  Its gradient goes to the ACTOR-tx twin (aux tail)
+            # of those leaves: d enc[:, off:] = dz0 @ W0[off:, :]^T, then back through LayerNorm / tanh / Dense.
+            off, S = 256 * len(self.cfg.cams), self.cfg.state_in
+            ops.dense_bwd_input(ws, dz, 256, self.P(Pm, f"{n}/Dense_0/kernel") + 4 * off * 256, self.dXp_p.data_ptr(), 64, B, 64, 256)
+            ops.ln_tanh_bwd(self.dXp_p.data_ptr(), 64, ops.at(Xp, off), F, self.enc_xhat_pa.data_ptr(), self.enc_rstd_pa.data_ptr(),
+                            self.P(Pm, f"{ENC}/LayerNorm_0/scale"), B, 0, self.d_enc_zpa.data_ptr(), self.d_enc_ypa.data_ptr(),
+                            st.aux_addr(G, f"{ENC}/LayerNorm_0/scale"), st.aux_addr(G, f"{ENC}/LayerNorm_0/bias"), B, 64)
+            ops.dense_bwd_weight(ws, self.pol_state.data_ptr(), S, self.d_enc_zpa.data_ptr(), 64, st.aux_addr(G, f"{ENC}/Dense_0/kernel"), B, S, 64)
+            ops.colsum(self.d_enc_zpa.data_ptr(), st.aux_addr(G, f"{ENC}/Dense_0/bias"), 1, B, 64, 64)
+            self.launches += 4
 
     # ---- the three losses --------------------------------------------------------------------------
     def _policy_pass(self, feats_rows, state, key_slot_eps, key_slot_drop, keys, act_out, ld_act, save, explicit=None):
@@ -368,7 +391,9 @@ class Engine:
             self.eps.copy_(explicit["eps"])
             for cam in (cfg.cams if cfg.pixel else ()):
                 self.masks_u8[cam].copy_(explicit["dropout"][cam])
-        self.encode(st.params, feats_rows, state, self.Xp, self.F, self.masks_u8 if cfg.pixel else None, save=False)
+        self.encode(st.params, feats_rows, state, self.Xp, self.F, self.masks_u8 if cfg.pixel else None, save=False,
+                    save_proprio_actor=save and cfg.pixel)
+        self.pol_state = state                                   # proprio input of the pass policy_backward differentiates
         self.policy_forward(st.params, self.Xp, save)
         ops.tanh_gaussian_fwd(self.mu, self.ls, self.eps, cfg.std_min, cfg.std_max, act_out, ld_act, self.logp, self.u, self.std, B, A)
         self.launches += 1
@@ -394,7 +419,7 @@ class Engine:
         n_sub = 0
         if cfg.subsample is not None:
             if explicit is None:
-                ops.subsample_idx(ops.key_ptr(keys, L.KEY_CRITIC_SUBSAMPLE), E, self.sub)
+                ops.subsample_idx(ops.key_ptr(keys, L.KEY_CRITIC_SUBSAMPLE), E, self.sub, cfg.subsample)
                 self.launches += 1
             else:
                 self.sub.copy_(explicit["critic"]["subsample"])
@@ -410,11 +435,22 @@ class Engine:
         s0.join()                                               # weight / bias gradients
         self.launches += 2
 
-    def actor_temp_loss_and_grads(self, keys, grad_scale=1.0, explicit=None):
-        """sac.py:193-234 + gradients w.r.t. group-1 / group-2 parameters."""
+    def actor_temp_loss_and_grads(self, keys, grad_scale=1.0, explicit=None, do_actor=True, do_temperature=True):
+        """sac.py:193-234 + gradients w.r.t. group-1 / group-2 parameters (and the actor-tx twin of the proprio encoder)."""
         cfg, B, E, A, st = self.cfg, self.B, self.cfg.ensemble, self.cfg.action_dim, self.store
         obs_rows, next_rows = slice(0, B), slice(B, 2 * B)
         lam = self.P(st.params, "modules_temperature/lagrange")
+        if do_actor:
+            self._actor_loss_and_grads(keys, grad_scale, explicit, obs_rows, lam)
+        if do_temperature:
+            # temperature: entropy of pi(.|s') with a fresh dropout mask / sample
+            self._policy_pass(next_rows, self.state_n, L.KEY_TEMP_NEXT, L.KEY_TEMP_NEXT, keys, self.act_scratch.data_ptr(), A, save=False,
+                              explicit=None if explicit is None else explicit["temperature"])
+            ops.temperature_loss(self.logp, lam, cfg.target_entropy, grad_scale, self.P(st.grad, "modules_temperature/lagrange"), ops.at(self.info, 8), B)
+            self.launches += 1
+
+    def _actor_loss_and_grads(self, keys, grad_scale, explicit, obs_rows, lam):
+        cfg, B, E, A, st = self.cfg, self.B, self.cfg.ensemble, self.cfg.action_dim, self.store
         # actor: a, logp ~ pi_theta(s); q = mean_e Q_e(s, a) with constant critic params
         self._policy_pass(obs_rows, self.state_o, L.KEY_ACTOR_SAMPLE, L.KEY_ACTOR_DROPOUT, keys, ops.at(self.Xc, self.F), self.FA, save=True,
                           explicit=None if explicit is None else explicit["actor"])
@@ -425,14 +461,10 @@ class Engine:
         ops.actor_loss(self.q, self.logp, lam, ops.at(self.dX, self.F), self.FA, ops.at(self.Xc, self.F), self.FA, self.std, self.ls, self.eps,
                        cfg.std_min, cfg.std_max, grad_scale, self.dmu, self.dls, ops.at(self.info, 4), E, B, A)
         self.policy_backward(self.Xp)
-        # temperature: entropy of pi(.|s') with a fresh dropout mask / sample
-        self._policy_pass(next_rows, self.state_n, L.KEY_TEMP_NEXT, L.KEY_TEMP_NEXT, keys, self.act_scratch.data_ptr(), A, save=False,
-                          explicit=None if explicit is None else explicit["temperature"])
-        ops.temperature_loss(self.logp, lam, cfg.target_entropy, grad_scale, self.P(st.grad, "modules_temperature/lagrange"), ops.at(self.info, 8), B)
-        self.launches += 3
+        self.launches += 2
 
     def optimizer_step(self, live, polyak: bool):
         cfg, st = self.cfg, self.store
         ops.adam_polyak(st.params, st.target, st.m, st.v, st.grad, st.seg_end, live, st.counts, cfg.lr, cfg.warmup, cfg.tau, polyak,
-                        lr_out=self.info[12:15])
+                        lr_out=self.lr_info, n=st.n_main, gap=INFO_GAP, aux=(st.aux_lo, st.aux_hi, st.aux_off))
         self.launches += 2

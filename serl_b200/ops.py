@@ -151,8 +151,8 @@ def dropout_mask_fill(key_addr, fold, keep, mask, n):
     L.call("serl_dropout_mask_fill", key_addr, fold, float(keep), _p(mask), n, _s())
 
 
-def subsample_idx(key_addr, ensemble, out):
-    L.call("serl_subsample_idx", key_addr, ensemble, _p(out), _s())
+def subsample_idx(key_addr, ensemble, out, n):
+    L.call("serl_subsample_idx", key_addr, ensemble, _p(out), int(n), _s())
 
 
 def counter_add(counter, inc=1):
@@ -182,10 +182,12 @@ def temperature_loss(logp, lagrange, target_entropy, grad_scale, dlagrange, info
 
 
 def adam_polyak(params, target, m, v, grad, seg_end: Sequence[int], live: Sequence[int], counts, lr, warmup, tau, polyak,
-                lr_out=None, b1=0.9, b2=0.999, eps=1e-8):
+                lr_out=None, b1=0.9, b2=0.999, eps=1e-8, n=None, gap=0, aux=(0, 0, 0)):
+    """aux = (aux_lo, aux_hi, aux_off): leaves with a second (actor-tx) Adam state at flat index i + aux_off."""
     d = L.AdamDesc()
     d.params, d.target, d.m, d.v, d.grad = _p(params), _p(target), _p(m), _p(v), _p(grad)
-    d.n = params.numel()
+    d.n = params.numel() if n is None else int(n)
+    d.gap, d.aux_lo, d.aux_hi, d.aux_off = int(gap), int(aux[0]), int(aux[1]), int(aux[2])
     for g in range(3):
         d.seg_end[g], d.live[g], d.lr[g], d.warmup[g] = int(seg_end[g]), int(live[g]), float(lr[g]), int(warmup[g])
     d.counts = _p(counts)

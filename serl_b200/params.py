@@ -13,6 +13,16 @@ same parameters.
 
 Optimizer groups (DESIGN.md "Adam groups"): 0 = critic tx (trainable encoder heads + critic),
 1 = actor tx (policy MLP + heads), 2 = temperature tx (lagrange).  Leaves are 16-byte aligned.
+
+Flat layout (floats):  [ group 0 | info gap (INFO_GAP) | group 1 | group 2 | aux ]
+  * info gap: in the GRADIENT buffer it holds the loss kernels' info scalars ([0:4] critic, [4:12] actor /
+    temperature), so that a data-parallel step exchanges gradients AND infos with ONE all-reduce of one
+    contiguous range (critic step: [0, seg_end[0]+4); actor/temperature step: [seg_end[0]+4, n)).
+  * aux: the proprio-encoder leaves (`modules_actor/encoder/{Dense_0,LayerNorm_0}`) are the only leaves that
+    receive a non-zero gradient from TWO losses - the critic loss, and the actor loss, whose `stop_gradient`
+    covers the image embeddings only (common/encoding.py:48-49 vs :55-70).  Both Adam transforms therefore
+    keep live moments for them (common/common.py:136-168).  The aux tail of the grad / m / v buffers holds the
+    ACTOR tx's gradient and moments of those leaves (same relative order); params / target have no aux part.
 """
 from __future__ import annotations
 
@@ -24,6 +34,8 @@ import numpy as np
 import torch
 
 ENC = "modules_actor/encoder"
+INFO_GAP = 16
+PROPRIO_LEAVES = (f"{ENC}/Dense_0/kernel", f"{ENC}/Dense_0/bias", f"{ENC}/LayerNorm_0/scale", f"{ENC}/LayerNorm_0/bias")
 STAGES = ((64, 1), (128, 2), (256, 2), (512, 2))
 
 
@@ -126,8 +138,11 @@ def trainable_spec(cams: Sequence[str], state_in: int, action_dim: int, ensemble
           Leaf("modules_actor/Dense_0/kernel", (H, A), 1), Leaf("modules_actor/Dense_0/bias", (A,), 1),
           Leaf("modules_actor/Dense_1/kernel", (H, A), 1), Leaf("modules_actor/Dense_1/bias", (A,), 1)]
     L += [Leaf("modules_temperature/lagrange", (), 2)]
-    off = 0
+    off, group = 0, 0
     for leaf in L:
+        if leaf.group != group and group == 0:
+            off += INFO_GAP                                   # info scalars live between group 0 and group 1 (gradient buffer)
+        group = leaf.group
         leaf.offset = off
         off += (leaf.size + 3) // 4 * 4
     return L
@@ -162,15 +177,37 @@ class ParamStore:
     def __init__(self, spec: List[Leaf], device):
         self.spec = spec
         self.leaf = {l.path: l for l in spec}
-        self.n = spec[-1].offset + (spec[-1].size + 3) // 4 * 4
+        self.n_main = spec[-1].offset + (spec[-1].size + 3) // 4 * 4
         self.seg_end = [0, 0, 0]
         for l in spec:
             self.seg_end[l.group] = l.offset + (l.size + 3) // 4 * 4
-        self.seg_end[1] = max(self.seg_end[1], self.seg_end[0])
-        self.seg_end[2] = self.n
+        self.info_off = self.seg_end[0]                       # [info_off, info_off + INFO_GAP): info scalars in the grad buffer
+        self.seg_end[1] = max(self.seg_end[1], self.seg_end[0] + INFO_GAP)
+        self.seg_end[2] = self.n_main
+        # leaves with two live Adam txs (critic + actor): contiguous in the spec; their actor-tx state lives in the aux tail
+        two = [self.leaf[p] for p in PROPRIO_LEAVES if p in self.leaf]
+        self.aux_lo = two[0].offset if two else 0
+        self.aux_hi = (two[-1].offset + (two[-1].size + 3) // 4 * 4) if two else 0
+        assert all(a.offset + (a.size + 3) // 4 * 4 == b.offset for a, b in zip(two, two[1:])), "proprio leaves must be contiguous"
+        self.aux_off = self.n_main - self.aux_lo             # aux index of flat index i in [aux_lo, aux_hi) = i + aux_off
+        self.n = self.n_main + (self.aux_hi - self.aux_lo)
         z = lambda: torch.zeros(self.n, dtype=torch.float32, device=device)
         self.params, self.target, self.m, self.v, self.grad = z(), z(), z(), z(), z()
         self.counts = torch.zeros(3, dtype=torch.int32, device=device)
+        self.version = 0                                      # bumped by every out-of-band parameter write (TrainState.replace)
+
+    def two_tx(self, path: str) -> bool:
+        return self.aux_lo <= self.leaf[path].offset < self.aux_hi
+
+    def aux_view(self, buf: torch.Tensor, path: str) -> torch.Tensor:
+        """Actor-tx twin (gradient / moments) of a proprio-encoder leaf."""
+        l = self.leaf[path]
+        assert self.two_tx(path)
+        return buf[l.offset + self.aux_off:l.offset + self.aux_off + l.size].view(l.shape)
+
+    def aux_addr(self, buf: torch.Tensor, path: str) -> int:
+        assert self.two_tx(path)
+        return buf.data_ptr() + 4 * (self.leaf[path].offset + self.aux_off)
 
     def view(self, buf: torch.Tensor, path: str) -> torch.Tensor:
         l = self.leaf[path]
@@ -179,11 +216,20 @@ class ParamStore:
     def addr(self, buf: torch.Tensor, path: str) -> int:
         return buf.data_ptr() + 4 * self.leaf[path].offset
 
-    def load(self, buf: torch.Tensor, values: Dict[str, np.ndarray]):
+    def load(self, buf: torch.Tensor, values: Dict[str, np.ndarray], aux_values: Dict[str, np.ndarray] = None):
         host = torch.zeros(self.n, dtype=torch.float32)
         for l in self.spec:
             host[l.offset:l.offset + l.size] = torch.as_tensor(np.asarray(values[l.path], np.float32)).reshape(-1)
+            if aux_values is not None and self.two_tx(l.path):
+                o = l.offset + self.aux_off
+                host[o:o + l.size] = torch.as_tensor(np.asarray(aux_values[l.path], np.float32)).reshape(-1)
         buf.copy_(host)
+        self.version += 1
+
+    def dump_aux(self, buf: torch.Tensor) -> Dict[str, np.ndarray]:
+        host = buf.detach().cpu().numpy()
+        return {l.path: host[l.offset + self.aux_off:l.offset + self.aux_off + l.size].reshape(l.shape).copy()
+                for l in self.spec if self.two_tx(l.path)}
 
     def dump(self, buf: torch.Tensor) -> Dict[str, np.ndarray]:
         host = buf.detach().cpu().numpy()

@@ -32,6 +32,7 @@ def _perturb(agent, scale=0.05, seed=0):
     noise = torch.randn(st.n, device="cuda", generator=g) * scale
     st.params.add_(noise)
     st.target.copy_(st.params + torch.randn(st.n, device="cuda", generator=g) * scale * 0.1)
+    st.version += 1
     lam = st.leaf["modules_temperature/lagrange"].offset
     st.params[lam] = -4.0
     st.target[lam] = -4.0
@@ -141,6 +142,23 @@ def test_learner_iteration_matches_oracle():
                 ref = oinfo["_grads"]["actor" if leaf.group == 1 else "temperature"][leaf.path].numpy()
                 got = st.view(st.grad, leaf.path).cpu().numpy()
                 assert np.abs(got - ref).max() <= G_TOL * max(np.abs(ref).max(), 1e-8), leaf.path
+            # the ACTOR loss also differentiates the proprio encoder: Policy's stop_gradient covers the image embeddings
+            # only (common/encoding.py:48-49 vs :55-70, sac.py:198-200).  Its gradient lives in the actor-tx twin (aux tail).
+            for path in ("modules_actor/encoder/Dense_0/kernel", "modules_actor/encoder/Dense_0/bias",
+                         "modules_actor/encoder/LayerNorm_0/scale", "modules_actor/encoder/LayerNorm_0/bias"):
+                ref = oinfo["_grads"]["actor"][path].numpy()
+                got = st.aux_view(st.grad, path).cpu().numpy()
+                assert np.abs(ref).max() > 0, f"oracle: actor loss must reach {path}"
+                assert np.abs(got).max() > 0, f"actor-loss gradient into {path} dropped"
+                assert np.abs(got - ref).max() <= G_TOL * np.abs(ref).max(), path
+            # ... and nothing else under modules_actor/encoder (image heads are behind the stop_gradient)
+            for k, v in oinfo["_grads"]["actor"].items():
+                if "/encoder_" in k:
+                    assert float(v.abs().max()) == 0.0, k
+            os_ = agent.state.opt_states
+            from serl_b200.params import flatten
+            assert np.abs(flatten(os_["actor"]["mu"])["modules_actor/encoder/Dense_0/kernel"]).max() > 0
+            assert np.abs(flatten(os_["critic"]["mu"])["modules_actor/encoder/Dense_0/kernel"]).max() > 0
         # update_high_utd = two `update` calls; the oracle's gradient record is of the last one (actor+temperature),
         # the critic-tx entries moved in the first: merge both records for the conditioning mask
         _compare_state(agent, ostate, oinfo, f"iteration {rep}")

@@ -1,6 +1,8 @@
-"""CPU, world_size 2, gloo: the data-parallel host logic of `SACAgent._allreduce` - which gradient segment is exchanged
-for a critic vs an actor/temperature step, mean semantics (kernels pre-scale by 1/world, the collective sums), info
-averaging, and that both ranks end with identical buffers.  Kernels are replaced by a recorder (dry run)."""
+"""CPU, world_size 2, gloo: the data-parallel host logic of `SACAgent._update_on_engine` - ONE all-reduce per `update`,
+which contiguous range of the flat gradient buffer it covers for a critic vs an actor/temperature step (gradient
+segment + the info scalars that sit next to it, + the actor-tx twin of the proprio encoder), mean semantics (kernels
+pre-scale gradients and infos by 1/world, the collective sums), and that both ranks end with identical buffers.
+Kernels are replaced by a recorder (dry run)."""
 import os
 import sys
 
@@ -52,13 +54,20 @@ def _worker(rank, world, port, out):
     eng = agent._engine(4)
     # rank-specific gradients / infos stand in for what the (no-op) kernels would have written
     st.grad.copy_(torch.arange(st.n, dtype=torch.float32) * (rank + 1))
-    eng.info[:12] = float(rank + 1)
+    n_coll = []
+    real_ar = dist.all_reduce
+    dist.all_reduce = lambda t, *a, **k: (n_coll.append(t.numel()), real_ar(t, *a, **k))[1]
     agent.update_critics(rb.sample(4, pack_obs_and_next_obs=True))
     g_after_critic = st.grad.clone()
-    info_after = eng.info[:12].clone()
+    n_critic = list(n_coll)
     st.grad.copy_(torch.arange(st.n, dtype=torch.float32) * (rank + 1))
     agent.update_high_utd(rb.sample(4, pack_obs_and_next_obs=True), utd_ratio=1)
-    torch.save(dict(seg=st.seg_end, n=st.n, g_critic=g_after_critic, g_utd=st.grad.clone(), info=info_after, scales=scales), out.format(rank))
+    g_utd = st.grad.clone()
+    del n_coll[:]
+    st.grad.copy_(torch.arange(st.n, dtype=torch.float32) * (rank + 1))
+    agent.update(rb.sample(4, pack_obs_and_next_obs=True), pmap_axis="devices")       # all three networks: still ONE collective
+    torch.save(dict(seg=st.seg_end, n=st.n, info_off=st.info_off, g_critic=g_after_critic, g_utd=g_utd, g_all=st.grad.clone(),
+                    n_critic=n_critic, n_all=list(n_coll), scales=scales), out.format(rank))
     dist.destroy_process_group()
 
 
@@ -67,17 +76,21 @@ def test_allreduce_segments_and_mean(tmp_path):
     out = str(tmp_path / "rank{}.pt")
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     r0, r1 = torch.load(out.format(0)), torch.load(out.format(1))
-    seg, n = r0["seg"], r0["n"]
+    n, io = r0["n"], r0["info_off"]
+    cut = io + 4                                      # [0, cut): critic-tx segment + critic infos; [cut, n): everything the actor/temperature step owns
     base = torch.arange(n, dtype=torch.float32)
-    # critic step: only the critic-tx segment [0, seg0) is exchanged: sum over ranks of base*(rank+1) = 3*base
+    # critic step: ONE collective over [0, cut): sum over ranks of base*(rank+1) = 3*base; the rest is untouched
+    assert r0["n_critic"] == [cut]
     for r, k in ((r0, 1.0), (r1, 2.0)):
-        torch.testing.assert_close(r["g_critic"][:seg[0]], 3.0 * base[:seg[0]])
-        torch.testing.assert_close(r["g_critic"][seg[0]:], k * base[seg[0]:])        # untouched elsewhere
-    torch.testing.assert_close(r0["g_critic"][:seg[0]], r1["g_critic"][:seg[0]], rtol=0, atol=0)   # replicas identical
-    # update_high_utd: critic segment again, then the actor + temperature segments
+        torch.testing.assert_close(r["g_critic"][:cut], 3.0 * base[:cut])
+        torch.testing.assert_close(r["g_critic"][cut:], k * base[cut:])
+    torch.testing.assert_close(r0["g_critic"][:cut], r1["g_critic"][:cut], rtol=0, atol=0)          # replicas identical
+    # update_high_utd: the critic range, then [cut, n) = actor/temperature infos + groups 1, 2 + the actor-tx twin (aux tail)
     torch.testing.assert_close(r0["g_utd"], 3.0 * base)
     torch.testing.assert_close(r0["g_utd"], r1["g_utd"], rtol=0, atol=0)
-    # infos are averaged (pmean of aux); kernels were asked to pre-scale gradients by 1/world
-    torch.testing.assert_close(r0["info"], torch.full((12,), 1.5))
+    # update(all three networks): one collective over the whole buffer
+    assert r0["n_all"] == [n]
+    torch.testing.assert_close(r0["g_all"], 3.0 * base)
+    # kernels were asked to pre-scale gradients (and infos) by 1/world
     assert r0["scales"] and all(abs(v - 0.5) < 1e-12 for _, v in r0["scales"])
     assert {k for k, _ in r0["scales"]} == {"critic", "actor"}

@@ -270,3 +270,67 @@ def test_adam_polyak_three_txs():
             tr = pr * 0.005 + tr * 0.995
     assert rel_err(P_.cpu().numpy(), pr.numpy()) < TOL and rel_err(T_.cpu().numpy(), tr.numpy()) < TOL
     assert counts.cpu().tolist() == [7, 7, 7]
+
+
+def test_adam_two_txs_on_one_leaf_and_info_gap():
+    """Flat layout of serl_b200/params.py: [group 0 | gap | group 1 | group 2 | aux].  Leaves in [aux_lo, aux_hi) get a
+    gradient from the critic loss AND the actor loss (reference common/encoding.py:48-70 + common/common.py:136-168): the
+    critic tx reads grad/m/v[i], the actor tx reads grad/m/v[i + aux_off], the two updates are summed.  Checked against the
+    literal formulation: three full-vector Adam transforms whose updates are added.  Gap slots must not move."""
+    from oracle.drq import adam_tx_update, lr_schedule
+    from serl_b200 import ops
+    rng = np.random.default_rng(11)
+    gap, seg = 16, [400, 916, 1016]                 # group 0 = [0,400), gap [400,416), group 1 = [416,916), group 2 = [916,1016)
+    n_main, aux_lo, aux_hi = 1016, 100, 164
+    aux_off = n_main - aux_lo
+    n = n_main + (aux_hi - aux_lo)
+    p0 = rng.standard_normal(n).astype(np.float32)
+    P_, T_, M_, V_ = cu(p0), cu(p0), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    counts = torch.zeros(3, dtype=torch.int32, device="cuda")
+    lr_out = torch.zeros(3, device="cuda")
+    pr, tr = torch.as_tensor(p0[:n_main]).double(), torch.as_tensor(p0[:n_main]).double()
+    opts = [{"count": 0, "mu": {"x": torch.zeros(n_main).double()}, "nu": {"x": torch.zeros(n_main).double()}} for _ in range(3)]
+    warm = (0, 3, 0)
+    bounds = [(0, 400), (416, 916), (916, 1016)]
+    for step in range(9):
+        live = [(1, 0, 0), (0, 1, 1), (1, 0, 0), (1, 1, 1)][step % 4]
+        gs = (rng.standard_normal(n) * (step + 1)).astype(np.float32)
+        ops.adam_polyak(P_, T_, M_, V_, cu(gs), seg, live, counts, (3e-4, 1e-3, 3e-4), warm, 0.005, bool(live[0]), lr_out,
+                        n=n_main, gap=gap, aux=(aux_lo, aux_hi, aux_off))
+        total = torch.zeros(n_main).double()
+        for gid in range(3):
+            gg = torch.zeros(n_main).double()
+            if live[gid]:
+                lo, hi = bounds[gid]
+                gg[lo:hi] = torch.as_tensor(gs).double()[lo:hi]
+                if gid == 1:                        # the actor loss also differentiates the two-tx leaves
+                    gg[aux_lo:aux_hi] = torch.as_tensor(gs).double()[aux_lo + aux_off:aux_hi + aux_off]
+            lr = lr_schedule(opts[gid]["count"], (3e-4, 1e-3, 3e-4)[gid], warm[gid])
+            total += adam_tx_update({"x": gg}, opts[gid], lr)["x"]
+        total[400:416] = 0
+        pr = pr + total
+        if live[0]:
+            tr = pr * 0.005 + tr * 0.995
+            tr[400:416] = torch.as_tensor(p0[400:416]).double()
+    got_p, got_t = P_.cpu().numpy(), T_.cpu().numpy()
+    assert rel_err(got_p[:n_main], pr.numpy()) < TOL and rel_err(got_t[:n_main], tr.numpy()) < TOL
+    np.testing.assert_array_equal(got_p[400:416], p0[400:416])                  # gap untouched
+    np.testing.assert_array_equal(got_p[n_main:], p0[n_main:])                  # params have no aux part
+    # the actor-tx moments of the two-tx leaves live in the aux tail and are non-trivial
+    np.testing.assert_allclose(M_.cpu().numpy()[n_main:], opts[1]["mu"]["x"].numpy()[aux_lo:aux_hi], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(M_.cpu().numpy()[aux_lo:aux_hi], opts[0]["mu"]["x"].numpy()[aux_lo:aux_hi], rtol=1e-5, atol=1e-7)
+    assert np.abs(M_.cpu().numpy()[n_main:]).max() > 0
+    assert counts.cpu().tolist() == [9, 9, 9]
+
+
+@pytest.mark.parametrize("n,E", [(1, 10), (2, 10), (3, 7), (5, 10)])
+def test_subsample_idx_is_jax_randint(n, E):
+    """critic_subsample_size = n for any n (sac.py:150-158): randint(key, (n,), 0, E), bit-exact vs the pinned PRNG oracle."""
+    from oracle import jax_prng as P
+    from serl_b200 import ops
+    for seed in (0, 1, 99):
+        key = P.prng_key(seed)
+        kd = torch.from_numpy(np.asarray(key, dtype=np.uint32).view(np.int32)).cuda().view(torch.uint32)
+        out = torch.zeros(n, dtype=torch.int32, device="cuda")
+        ops.subsample_idx(kd.data_ptr(), E, out, n)
+        np.testing.assert_array_equal(out.cpu().numpy(), np.asarray(P.randint(key, (n,), 0, E)))

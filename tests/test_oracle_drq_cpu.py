@@ -79,3 +79,69 @@ def test_subsample_is_with_replacement_and_min_over_two():
     info = O.update(state, cfg, batch, rnd, frozenset({"critic"}), torch.float64, new_rng)
     assert np.isfinite(info["critic"]["critic_loss"])
     assert info["critic"]["_target_q"].shape == (16,)
+
+
+def test_actor_loss_differentiates_the_proprio_encoder_but_not_the_image_heads():
+    """Audit of the reference's stop_gradient sites for the pixel agent:
+      * Policy.__call__ calls encoder(obs, train, stop_gradient=True)      (networks/actor_critic_nets.py:185)
+      * EncodingWrapper stops the gradient at each per-camera image embedding (common/encoding.py:48-49) and NOT at the
+        proprio Dense -> LayerNorm -> tanh that follows                    (common/encoding.py:55-70)
+      * policy_loss_fn differentiates w.r.t. the full tree                 (agents/continuous/sac.py:198-200)
+    so d(actor loss) reaches modules_actor/encoder/{Dense_0,LayerNorm_0} and is exactly zero for encoder_<cam>/*.
+    The autograd result is checked against central finite differences of the literal formulation (perturbing ONLY the
+    `grad_params` copy, like jax.grad does: forward_critic inside the actor loss reads self.state.params)."""
+    import torch.nn.functional as F
+    from serl_b200.params import ENC, init_trainable, trainable_spec
+    rng = np.random.default_rng(3)
+    cams, S, A, E, B = ("front",), 7, 4, 3, 5
+    spec = trainable_spec(cams, S, A, E, pixel=True)
+    params = {k: torch.as_tensor(v).double() for k, v in init_trainable(rng, spec, 1e-2).items()}
+    for k in params:
+        params[k] = params[k] + 0.05 * torch.as_tensor(rng.standard_normal(params[k].shape))
+    cfg = O.OracleConfig(cams=cams, ensemble=E, subsample=2, pixel=True)
+    feats = {"front": torch.as_tensor(np.abs(rng.standard_normal((B, 4, 4, 512))))}     # frozen-trunk output (stop_gradient)
+    state_obs = rng.standard_normal((B, 1, S))
+    eps = torch.as_tensor(rng.standard_normal((B, A)))
+    drop = {"front": torch.as_tensor(rng.random((B, 4096)) < 0.9)}
+    lam = "modules_temperature/lagrange"
+
+    def actor_loss(grad_params):
+        enc = O.encode(grad_params, cams, feats, torch.as_tensor(state_obs), drop, stop_gradient=True)
+        mu, sd = O.policy_forward(grad_params, enc)
+        a, logp = O.tanh_normal_sample_logp(mu, sd, eps)
+        with torch.no_grad():
+            enc_c = O.encode(params, cams, feats, torch.as_tensor(state_obs), None)
+        q = O.critic_forward(params, enc_c, a, True).mean(dim=0)
+        return -(q - F.softplus(params[lam]).detach() * logp).mean()
+
+    leaves = {k: v.clone().requires_grad_(True) for k, v in params.items()}
+    grads = dict(zip(leaves, torch.autograd.grad(actor_loss(leaves), list(leaves.values()), allow_unused=True)))
+    for k, g in grads.items():
+        if "/encoder_" in k or k.startswith("modules_critic") or k == lam:
+            assert g is None or float(g.abs().max()) == 0.0, k
+    for k in (f"{ENC}/Dense_0/kernel", f"{ENC}/Dense_0/bias", f"{ENC}/LayerNorm_0/scale", f"{ENC}/LayerNorm_0/bias"):
+        g = grads[k]
+        assert g is not None and float(g.abs().max()) > 0, k
+        idx = tuple(int(i) for i in np.unravel_index(int(g.abs().argmax()), g.shape))
+        h = 1e-6
+        vals = []
+        for sgn in (+1, -1):
+            pert = {kk: v.clone() for kk, v in params.items()}
+            pert[k][idx] += sgn * h
+            vals.append(float(actor_loss(pert)))
+        fd = (vals[0] - vals[1]) / (2 * h)
+        assert abs(fd - float(g[idx])) < 1e-6 * max(1.0, abs(fd)), (k, fd, float(g[idx]))
+    # and the oracle's update() routes it to the ACTOR transform: Adam moments of the actor tx become non-zero there
+    st = O.OracleState.create({k: v.clone() for k, v in params.items()}, P.prng_key(1), torch.float64)
+    batch = dict(observations={"state": state_obs, "front": None}, next_observations={"state": state_obs, "front": None},
+                 rewards=np.zeros(B, np.float32), masks=np.ones(B, np.float32), actions=np.zeros((B, A), np.float32))
+    rnd = O.UpdateRandomness(actor=O.LossRandomness(eps=eps.numpy(), dropout={"front": drop["front"].numpy()}))
+    real_features = O._features
+    O._features = lambda *a, **k: feats
+    try:
+        O.update(st, cfg, batch, rnd, frozenset({"actor"}), torch.float64)
+    finally:
+        O._features = real_features
+    assert float(st.opt["actor"]["mu"][f"{ENC}/Dense_0/kernel"].abs().max()) > 0
+    assert float(st.opt["critic"]["mu"][f"{ENC}/Dense_0/kernel"].abs().max()) == 0
+    assert float(st.opt["actor"]["mu"][f"{ENC}/encoder_front/Dense_0/kernel"].abs().max()) == 0
