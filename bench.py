@@ -4,10 +4,12 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--precision fp32|bf16]
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...        (N > 1)
 
-Workload = BASELINE.json configs[1]: `async_drq_sim`, single 128x128 camera, batch 256, replay 100k in HBM.
+Workload = the configuration BASELINE.json's metric is quoted on ("B=256, 2x128x128 obs" = configs[2]): `async_drq_sim` with
+its stock dual 128x128x3 cameras, batch 256 drawn 50/50 (RLPD) from the online replay ring and a 20-trajectory demo ring,
+replay 200k in HBM (`--cams 1 --no-rlpd --capacity 100000` gives configs[1], also reported under "single_camera").
 A "step" = one critic gradient step (`update_critics` equivalent) INCLUDING replay sampling + DrQ shift
 (SURVEY.md §8d unit of work).  N > 1: the global batch of 256 is split across ranks (strong scaling), each rank
-owns a replay shard, one gradient all-reduce(mean) per step.
+owns a shard of the online ring (the small demo ring is replicated), ONE gradient all-reduce(mean) per step.
 
   value      steps/s with everything resident in HBM, CUDA-event timed, max over ranks.
   e2e        the same through the public API with host buffers: every step inserts one fresh transition from
@@ -48,10 +50,15 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("SERL_PRECISION", "fp16"), choices=["fp32", "bf16", "fp16"],
                     help="trunk arithmetic: fp16 (default: tensor cores, fp32 accumulate, meets the 1e-2 bar), bf16, or fp32 (1e-5 parity build)")
     ap.add_argument("--batch", type=int, default=256)
-    ap.add_argument("--cams", type=int, default=1)
-    ap.add_argument("--capacity", type=int, default=100_000)
-    ap.add_argument("--ref-rows", type=int, default=16, help="rows of the batch the CPU reference processes per step")
-    return ap.parse_args()
+    ap.add_argument("--cams", type=int, default=2)
+    ap.add_argument("--capacity", type=int, default=None, help="online replay slots (default 200k dual-camera, 100k single)")
+    ap.add_argument("--no-rlpd", dest="rlpd", action="store_false", help="draw the whole batch from the online ring (configs[1])")
+    ap.add_argument("--ref-rows", type=int, default=64, help="rows of the batch the CPU reference processes per step")
+    ap.add_argument("--sustain-s", type=float, default=1.0, help="length of the additional sustained run (seconds of timed steps)")
+    a = ap.parse_args()
+    if a.capacity is None:
+        a.capacity = 200_000 if a.cams == 2 else 100_000
+    return a
 
 
 def peaks():
@@ -65,7 +72,11 @@ def peaks():
 # ------------------------------------------------------------------------------------------------
 # CPU reference arm: the oracle port of the reference step (sample on host + update_critics), bounded sample
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps(args, steps, warmup, rows, budget_s=None):
+def cpu_reference_steps(args, steps, warmup, rows, budget_s=None, reference_structure=True):
+    """reference_structure: the JAX reference evaluates the frozen encoder once per network call - policy(s'), target
+    critic(s') and critic(s) in critic_loss_fn (sac.py:118-176): THREE trunk passes of `rows` images per camera - while
+    the oracle (like the B200 path) shares one pass over obs and one over next_obs.  For a timing that has the reference's
+    structure the third pass (target critic on next_obs) is executed as well and its result discarded."""
     import torch
     from helpers import random_transitions
     from oracle import drq as O
@@ -89,7 +100,10 @@ def cpu_reference_steps(args, steps, warmup, rows, budget_s=None):
     for s in range(warmup + steps):
         t0 = time.perf_counter()
         _, packed = ring.sample(0, s, rows)
-        O.update_critics(state, cfg, unpack(packed), dtype=torch.float32)
+        batch = unpack(packed)
+        O.update_critics(state, cfg, batch, dtype=torch.float32)
+        if reference_structure:
+            O._features(state, cfg, batch["next_observations"], torch.float32)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
@@ -105,14 +119,15 @@ def run_reference(args):
     if rank != 0:
         return
     v, t, cores, done = cpu_reference_steps(args, args.steps, min(args.warmup, 1), args.ref_rows, budget_s=150.0)
-    sample = (f"{done} timed steps (150 s budget) of {args.ref_rows} of {args.batch} rows per step (host numpy sampling + torch-CPU fp32 restatement of update_critics, "
-              f"trunk shared between policy/critic/target like the B200 path; the JAX reference recomputes it 3x); "
-              f"steps/s scaled by rows/batch")
+    sample = (f"{done} timed steps (150 s budget) of {args.ref_rows} of {args.batch} rows per step: host numpy sampling + torch-CPU fp32 "
+              f"restatement of update_critics with the reference's three frozen-encoder passes (policy(s'), target critic(s'), critic(s)); "
+              f"steps/s EXTRAPOLATED x{args.batch / args.ref_rows:g} by rows/batch (per-row cost dominates); jax[cpu] is not installable here")
     line = {"metric": "drq_critic_grad_steps_per_sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
             "config": workload_config(args),
-            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample,
+                             "extrapolated_x": args.batch / args.ref_rows},
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -130,15 +145,17 @@ def trunk_traffic(args):
     try:
         with open(path) as f:
             t = json.load(f)
-        key = f"{args.precision}_b{args.batch}_c{args.cams}"
+        key = f"{args.precision}_b{args.batch // max(int(os.environ.get('WORLD_SIZE', 1)), 1)}_c{args.cams}"
         return t.get(key, {}).get("dram_bytes_per_step")
     except (OSError, ValueError):
         return None
 
 
 def workload_config(args):
-    return {"workload": f"async_drq_sim: {args.cams}x 128x128x3 camera, batch {args.batch} (global), replay {args.capacity} in HBM, "
-                        "critic grad step incl. sampling + DrQ shift", "global_batch": args.batch, "cams": args.cams,
+    rl = (f" = {args.batch // 2} online + {args.batch - args.batch // 2} demo (50/50 RLPD, demo ring of 20 trajectories)" if args.rlpd else "")
+    name = "BASELINE configs[2]" if (args.cams == 2 and args.rlpd) else ("BASELINE configs[1]" if args.cams == 1 and not args.rlpd else "custom")
+    return {"workload": f"{name}: async_drq_sim, {args.cams}x 128x128x3 camera(s), batch {args.batch} (global){rl}, replay {args.capacity} in HBM, "
+                        "critic grad step incl. sampling + DrQ shift", "global_batch": args.batch, "cams": args.cams, "rlpd": bool(args.rlpd),
             "replay_capacity": args.capacity, "parallelism": f"dp{args.gpus}", "precision": args.precision,
             "arithmetic": ("frozen ResNet-10 trunk: 16-bit operands on tcgen05 tensor cores with fp32 accumulation; trainable heads, losses, "
                            "Adam in fp32" if args.precision != "fp32" else "everything fp32 (CUDA cores): the 1e-5 parity build"),
@@ -213,50 +230,86 @@ def fill_ring_synthetic(rb, seed):
     rb.size_dev.fill_(cap)
 
 
-def measure_dual_camera_rlpd(args, steps=50):
-    """Supplementary measurement on BASELINE configs[2]: dual 128x128 cameras, batch 256 drawn 50/50 from the online ring and a
-    20-trajectory demo ring (RLPD), same metric, same timing rules (device-resident value + e2e with host insert / loss readback)."""
-    import torch
-    from helpers import fake_env, random_transitions
-    from serl_b200.utils.launcher import make_drq_agent, make_replay_buffer
-    from serl_b200.utils.train_utils import concat_batches
-    cams, half = ("cam0", "cam1"), args.batch // 2
-    env = fake_env(cams)
-    rb = make_replay_buffer(env, capacity=args.capacity, type="memory_efficient_replay_buffer", image_keys=list(cams), seed=2000)
-    demo = make_replay_buffer(env, capacity=20 * 101, type="memory_efficient_replay_buffer", image_keys=list(cams), seed=2001)
-    fill_ring_synthetic(rb, seed=7)
-    fill_ring_synthetic(demo, seed=8)
-    rng = np.random.default_rng(1)
-    trs = random_transitions(rng, 8, cams, mean_ep=1000)
-    agent = make_drq_agent(42, trs[0]["observations"], trs[0]["actions"], image_keys=cams, encoder_type="resnet-pretrained", precision=args.precision)
-    it = rb.get_iterator(sample_args={"batch_size": half, "pack_obs_and_next_obs": True})
-    dit = demo.get_iterator(sample_args={"batch_size": args.batch - half, "pack_obs_and_next_obs": True})
-    nxt = lambda: concat_batches(next(it), next(dit), axis=0)
+class Workload:
+    """Replay rings + agent + batch source of one configuration on the current device."""
+
+    def __init__(self, args, cams_n, rlpd, capacity, batch, rank=0, world=1, seed_base=1000):
+        import torch
+        from helpers import fake_env, random_transitions
+        from serl_b200.utils.launcher import make_drq_agent, make_replay_buffer
+        from serl_b200.utils.train_utils import concat_batches
+        self.torch = torch
+        cams = tuple(f"cam{i}" for i in range(cams_n))
+        env = fake_env(cams)
+        self.cams, self.B, self.rlpd = cams, batch // world, rlpd
+        self.rb = make_replay_buffer(env, capacity=capacity // world, type="memory_efficient_replay_buffer", image_keys=list(cams),
+                                     seed=seed_base + rank)           # rank folded into the sampler stream
+        fill_ring_synthetic(self.rb, seed=rank)
+        rng = np.random.default_rng(0)
+        self.transitions = random_transitions(rng, 8, cams, mean_ep=1000)
+        self.agent = make_drq_agent(42, self.transitions[0]["observations"], self.transitions[0]["actions"], image_keys=cams,
+                                    encoder_type="resnet-pretrained", precision=args.precision)
+        self.agent.data_parallel = world > 1
+        if rlpd:                                                       # async_drq_sim.py:275-277: batch_size // 2 from each buffer
+            half = self.B // 2
+            self.demo = make_replay_buffer(env, capacity=20 * 101, type="memory_efficient_replay_buffer", image_keys=list(cams),
+                                           seed=seed_base + 500 + rank)
+            fill_ring_synthetic(self.demo, seed=100 + rank)
+            it = self.rb.get_iterator(sample_args={"batch_size": half, "pack_obs_and_next_obs": True})
+            dit = self.demo.get_iterator(sample_args={"batch_size": self.B - half, "pack_obs_and_next_obs": True})
+            self.next_batch = lambda: concat_batches(next(it), next(dit), axis=0)
+        else:
+            self.demo = None
+            it = self.rb.get_iterator(sample_args={"batch_size": self.B, "pack_obs_and_next_obs": True})
+            self.next_batch = lambda: next(it)
+
+    def timed_steps(self, steps, barrier=None):
+        """`steps` critic steps, CUDA-event timed on the launching stream, a synchronize (and barrier) on both sides."""
+        torch = self.torch
+        sync = barrier or torch.cuda.synchronize
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync()
+        t0.record()
+        for _ in range(steps):
+            self.agent.update_critics(self.next_batch())
+        t1.record()
+        sync()
+        return t0.elapsed_time(t1)
+
+    def e2e_steps(self, steps, barrier=None):
+        """The public-API loop with HOST buffers: every step inserts one fresh transition from host memory (pinned staging ->
+        HBM), draws the batch through the replay iterators, runs agent.update_critics and reads the loss back."""
+        torch = self.torch
+        sync = barrier or torch.cuda.synchronize
+        h0 = self.rb.h2d_bytes
+        sync()
+        e0 = time.perf_counter()
+        for s in range(steps):
+            self.rb.insert(self.transitions[s % len(self.transitions)])
+            _, info = self.agent.update_critics(self.next_batch())
+            loss = float(info["critic"]["critic_loss"])
+        sync()
+        dt = time.perf_counter() - e0
+        assert np.isfinite(loss)
+        return dt, (self.rb.h2d_bytes - h0) / steps, 4.0
+
+    def close(self):
+        self.agent._graphs.clear()
+        self.torch.cuda.synchronize()
+
+
+def measure_single_camera(args, steps=100):
+    """Supplementary measurement on BASELINE configs[1]: single camera, whole batch from one 100k ring."""
+    w = Workload(args, 1, False, 100_000, args.batch)
     for _ in range(5):
-        agent.update_critics(nxt())
-    torch.cuda.synchronize()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(steps):
-        agent.update_critics(nxt())
-    t1.record()
-    torch.cuda.synchronize()
-    ms = t0.elapsed_time(t1) / steps
-    h0, e0 = rb.h2d_bytes, time.perf_counter()
-    for s in range(steps):
-        rb.insert(trs[s % len(trs)])
-        _, info = agent.update_critics(nxt())
-        loss = float(info["critic"]["critic_loss"])
-    torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - e0) * 1e3 / steps
-    assert np.isfinite(loss)
-    out = {"workload": f"async_drq_sim + demos (50/50 RLPD): 2x 128x128x3 cameras, batch {args.batch} = {half} online + {args.batch - half} demo, "
-                       f"replay {args.capacity} + {20 * 101} in HBM, critic grad step incl. sampling + DrQ shift",
+        w.agent.update_critics(w.next_batch())
+    ms = w.timed_steps(steps) / steps
+    dt, h2d, d2h = w.e2e_steps(steps)
+    out = {"workload": f"BASELINE configs[1]: async_drq_sim, 1x 128x128x3 camera, batch {args.batch}, replay 100000 in HBM, critic grad step incl. sampling + DrQ shift",
            "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps,
-           "e2e": {"value": 1e3 / e2e_ms, "unit": "steps/s", "h2d_bytes_per_step": (rb.h2d_bytes - h0) / steps, "d2h_bytes_per_step": 4.0}}
-    agent._graphs.clear()
-    del agent, rb, demo
-    torch.cuda.synchronize()
+           "e2e": {"value": steps / dt, "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}}
+    w.close()
+    del w
     return out
 
 
@@ -267,21 +320,9 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from helpers import fake_env, random_transitions
-    from serl_b200.utils.launcher import make_drq_agent, make_replay_buffer
-    assert args.batch % world == 0
-    B = args.batch // world
-    cams = tuple(f"cam{i}" for i in range(args.cams))
-    env = fake_env(cams)
-    rb = make_replay_buffer(env, capacity=args.capacity // world, type="memory_efficient_replay_buffer", image_keys=list(cams),
-                            seed=1000 + rank)                     # rank folded into the sampler stream
-    fill_ring_synthetic(rb, seed=rank)
-    rng = np.random.default_rng(0)
-    sample_tr = random_transitions(rng, 1, cams)[0]
-    agent = make_drq_agent(42, sample_tr["observations"], sample_tr["actions"], image_keys=cams, encoder_type="resnet-pretrained",
-                           precision=args.precision)
-    agent.data_parallel = world > 1
-    it = rb.get_iterator(sample_args={"batch_size": B, "pack_obs_and_next_obs": True})
+    assert args.batch % world == 0 and (not args.rlpd or (args.batch // world) % 2 == 0)
+    w = Workload(args, args.cams, args.rlpd, args.capacity, args.batch, rank, world)
+    agent, B = w.agent, w.B
     eng = agent._engine(B)
 
     def barrier():
@@ -289,48 +330,42 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident throughput (whole step replayed as one CUDA graph) -------------------------------------
+    # ---- device-resident throughput (whole step replayed as one CUDA graph): EXACTLY args.steps timed steps -------------
     ev = lambda: torch.cuda.Event(enable_timing=True)
     clocks = ClockSampler(local)
     clocks.start()
     for _ in range(max(args.warmup, 3)):
-        agent.update_critics(next(it))
+        agent.update_critics(w.next_batch())
     launches0 = agent.kernel_launches
-    barrier()
     w0 = time.time()
-    t0, t1 = ev(), ev()
-    t0.record()
-    for _ in range(args.steps):
-        agent.update_critics(next(it))
-    t1.record()
-    barrier()
-    clk = clocks.stop(w0, time.time())
-    ms = t0.elapsed_time(t1)
+    ms = w.timed_steps(args.steps, barrier)
     launches = agent.kernel_launches - launches0
+    # ---- the same loop for >= sustain-s seconds: the sustained figure, and enough nvidia-smi samples under load -----------
+    n_sus = max(args.steps, int(args.sustain_s * 1e3 / max(ms / args.steps, 1e-3)) + 1)
+    if world > 1:
+        t = torch.tensor([n_sus], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); n_sus = int(t.item())
+    ms_sus = w.timed_steps(n_sus, barrier)
+    clk = clocks.stop(w0, time.time())
     agent.check_status()
 
     # ---- per-kernel-group durations: the same steps launched eagerly with CUDA events around the sections -----------
-    trunk_ev, samp_ev = [], []
+    trunk_ev = []
     orig_features, orig_load = agent._features, agent._load_batch
 
     def timed_features(e):
         a, b = ev(), ev(); a.record(); orig_features(e); b.record(); trunk_ev.append((a, b))
 
-    def timed_load(e, batch, **kw):
-        a, b = ev(), ev(); a.record(); orig_load(e, batch, **kw); b.record(); samp_ev.append((a, b))
-
     agent.use_cuda_graphs = False
-    agent._features, agent._load_batch = timed_features, timed_load
+    agent._features = timed_features
     for _ in range(min(args.steps, 20)):
-        agent.update_critics(next(it))
+        agent.update_critics(w.next_batch())
     barrier()
-    agent._features, agent._load_batch = orig_features, orig_load
-    del samp_ev
+    agent._features = orig_features
     agent.use_cuda_graphs = True
     trunk_ms = sum(a.elapsed_time(b) for a, b in trunk_ev) / len(trunk_ev)
-    # the sampler kernel is ~10x shorter than a host launch: time it as 20 launches captured in one CUDA graph, replayed
-    # back to back (each launch draws a fresh batch: the device step counter advances inside the graph)
-    handle = next(it)
+    # the sampler kernel(s) of a step are ~10x shorter than a host launch: time them as 20 batch loads captured in one CUDA
+    # graph, replayed back to back (each launch draws a fresh batch: the device step counter advances inside the graph)
+    handle = w.next_batch()
     reps = 20
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
@@ -346,23 +381,7 @@ def run_b200(args):
     del g
 
     # ---- end to end through the public API with host buffers --------------------------------------------
-    pinned = []
-    for tr in random_transitions(rng, 8, cams, mean_ep=1000):
-        pinned.append(tr)
-    h2d0 = rb.h2d_bytes
-    barrier()
-    e0 = time.perf_counter()
-    d2h = 0
-    for s in range(args.steps):
-        rb.insert(pinned[s % len(pinned)])                       # fresh transition from host memory -> pinned staging -> HBM
-        batch = next(it)
-        _, info = agent.update_critics(batch)
-        loss = float(info["critic"]["critic_loss"])              # D2H read of the step's result
-        d2h += 4
-    barrier()
-    e2e_s = time.perf_counter() - e0
-    h2d = (rb.h2d_bytes - h2d0) / args.steps
-    assert np.isfinite(loss)
+    e2e_s, h2d, d2h = w.e2e_steps(args.steps, barrier)
 
     replicas_identical = None
     if world > 1:                                   # data-parallel replicas must stay bit-identical (same reduced gradient everywhere)
@@ -372,10 +391,11 @@ def run_b200(args):
         same = torch.tensor([int(torch.equal(mine, ref))], device="cuda")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         replicas_identical = bool(same.item())
-    tmax = torch.tensor([ms, e2e_s * 1e3], device="cuda", dtype=torch.float64)
+    tmax = torch.tensor([ms, e2e_s * 1e3, ms_sus, trunk_ms, samp_ms], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = tmax.tolist()
+    ms, e2e_ms, ms_sus, trunk_ms, samp_ms = tmax.tolist()
+
     def shutdown():
         # captured NCCL kernels inside live CUDA graphs can block process-group teardown: drop the graphs first, and never
         # let a teardown problem turn into a hung bench (os._exit after the line is out)
@@ -399,28 +419,33 @@ def run_b200(args):
             "dtype": {"fp32": "f32", "bf16": "bf16", "fp16": "f16"}[args.precision], "data": "synthetic", "impl": "b200",
             "config": workload_config(args),
             "clocks": clk,
-            "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h / args.steps},
+            "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "sustained": {"value": n_sus / (ms_sus / 1e3), "unit": "steps/s", "steps": n_sus, "seconds": ms_sus / 1e3,
+                          "note": "same loop, run for >= --sustain-s seconds right after the K timed steps; the clock samples cover both"},
             "gpu_launches": launches, "cuda_graph": True, "replicas_identical": replicas_identical,
             "roofline": {"kernel": TRUNK_KERNELS[args.precision != "fp32"], "bound": "tensor",
                          "achieved": trunk_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": trunk_tflops / pk["tensor"],
-                         "traffic": trunk_traffic(args), "peak_source": pk["src"], "ms_per_step": trunk_ms,
-                         "timing": "CUDA events around the trunk section of eagerly launched steps (the headline loop replays a CUDA graph)",
-                         "algorithmic": f"{images} images x {TRUNK_GFLOP_PER_IMAGE} GFLOP"},
-            "sampler": {"kernel": "sample_frames_kernel", "timing": "20 launches captured in one CUDA graph, replayed 5x, CUDA events", "bound": "hbm", "achieved": samp_gbs, "peak": pk["hbm"], "unit": "GB/s",
-                        "frac": samp_gbs / pk["hbm"], "ms_per_step": samp_ms, "algorithmic_bytes": samp_bytes}}
-    if world == 1 and args.cams == 1 and not os.environ.get("SERL_BENCH_SKIP_DUAL"):
-        # the stock sim script is dual-camera: report BASELINE configs[2] beside the headline configuration
+                         "traffic": trunk_traffic(args), "traffic_source": "profiles/trunk_traffic.json, regenerated from the committed ncu launch list by scripts/trunk_traffic.py",
+                         "peak_source": pk["src"], "ms_per_step": trunk_ms,
+                         "timing": "CUDA events around the trunk section of eagerly launched steps (the headline loop replays a CUDA graph), max over ranks",
+                         "algorithmic": f"{images} images x {TRUNK_GFLOP_PER_IMAGE} GFLOP per rank"},
+            "sampler": {"kernel": "sample_frames_kernel", "timing": "20 batch loads captured in one CUDA graph, replayed 5x, CUDA events", "bound": "hbm", "achieved": samp_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                        "frac": samp_gbs / pk["hbm"], "ms_per_step": samp_ms, "algorithmic_bytes": samp_bytes, "launches_per_step": 2 if args.rlpd else 1}}
+    w.close()
+    if world == 1 and not os.environ.get("SERL_BENCH_SKIP_SINGLE") and (args.cams != 1 or args.rlpd):
+        del w, eng
         try:
-            line["dual_camera_rlpd"] = measure_dual_camera_rlpd(args)
+            line["single_camera"] = measure_single_camera(args)
         except Exception as e:                  # noqa: BLE001
-            line["dual_camera_rlpd"] = {"value": None, "error": str(e)}
+            line["single_camera"] = {"value": None, "error": str(e)}
     try:
         if os.environ.get("SERL_BENCH_SKIP_CPU"):
             raise RuntimeError("skipped (SERL_BENCH_SKIP_CPU)")
-        v, t, cores, done = cpu_reference_steps(args, 4, 1, 8, budget_s=20.0)
-        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port",
-                                "sample": f"{done} timed steps of 8/{args.batch} rows, ~20 s budget (oracle torch-CPU fp32 restatement of sample + update_critics; "
-                                          "jax not installable), steps/s scaled by rows/batch"}
+        rows = 64
+        v, t, cores, done = cpu_reference_steps(args, 2, 1, rows, budget_s=30.0)
+        line["cpu_baseline"] = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "extrapolated_x": args.batch / rows,
+                                "sample": f"{done} timed step(s) of {rows}/{args.batch} rows, ~30 s budget: oracle torch-CPU fp32 restatement of sample + update_critics with the "
+                                          f"reference's three frozen-encoder passes (jax not installable); steps/s EXTRAPOLATED x{args.batch / rows:g} by rows/batch"}
     except Exception as e:                      # noqa: BLE001
         line["cpu_baseline"] = {"value": None, "unit": "steps/s", "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {e}"}
     print(json.dumps(line), flush=True)

@@ -18,7 +18,7 @@ import numpy as np
 from ... import ops
 from ...data.replay_buffer import BatchHandle
 from ...engine import AgentConfig
-from .sac import SACAgent, _leaf
+from .sac import SACAgent, _check_architecture_kwargs, _leaf, register_pytree
 
 
 class DrQAgent(SACAgent):
@@ -27,7 +27,8 @@ class DrQAgent(SACAgent):
                    image_keys: Iterable[str] = ("image",), discount: float = 0.95, critic_ensemble_size: int = 2,
                    critic_subsample_size: Optional[int] = None, temperature_init: float = 1.0, backup_entropy: bool = False,
                    soft_target_update_rate: float = 0.005, target_entropy: Optional[float] = None, policy_kwargs=None,
-                   learning_rate: float = 3e-4, precision: str = "fp32", device=None, **_):
+                   learning_rate: float = 3e-4, precision: str = "fp32", device=None, **kwargs):
+        _check_architecture_kwargs(policy_kwargs, kwargs, pixel=True)
         if encoder_type != "resnet-pretrained":
             raise NotImplementedError(f"encoder_type={encoder_type!r}: only 'resnet-pretrained' is supported "
                                       "(the reference's 'small'/'resnet' paths are broken, SURVEY.md Appendix C.1)")
@@ -73,3 +74,6 @@ class DrQAgent(SACAgent):
     def update_high_utd(self, batch, *, utd_ratio: int, pmap_axis: Optional[str] = None):
         """drq.py:255-294: augment once, then SACAgent.update_high_utd."""
         return super().update_high_utd(batch, utd_ratio=utd_ratio, pmap_axis=pmap_axis, _augment=True)
+
+
+register_pytree(DrQAgent)

@@ -85,9 +85,10 @@ class SACAgent:
     def create_states(cls, seed: int, observations, actions, *, discount=0.95, critic_ensemble_size=2,
                       critic_subsample_size=None, temperature_init=1.0, backup_entropy=False, soft_target_update_rate=0.005,
                       target_entropy=None, policy_kwargs=None, actor_warmup=2000, critic_warmup=2000, learning_rate=3e-4,
-                      device=None, **_):
+                      device=None, **kwargs):
         """State-observation agent (sac.py:486-542).  Optimizer defaults follow SACAgent.create (:333-343):
         2000-step linear warm-up for actor and critic."""
+        _check_architecture_kwargs(policy_kwargs, kwargs, pixel=False)
         pk = policy_kwargs or {}
         S = int(np.asarray(observations).shape[-1])
         A = int(np.asarray(actions).shape[-1])
@@ -130,6 +131,8 @@ class SACAgent:
     def _graph_key(self, tag, batch):
         """Batches that can be replayed: lazy handles whose index draw reads the ring's device-resident counters."""
         if not self.use_cuda_graphs or self.explicit_randomness is not None or not isinstance(batch, BatchHandle):
+            return None
+        if torch.device(self.device).type != "cuda":            # host-logic dry runs (tests) have nothing to capture
             return None
         if any(p.get("indx") is not None for p in batch.parts):
             return None
@@ -416,6 +419,58 @@ class SACAgent:
         out = eng.act_scratch.clone()
         out = out[0] if unbatched else out
         return out if return_device else out.cpu().numpy()
+
+
+_LAUNCHER_NET_KWARGS = {"activations": "tanh", "use_layer_norm": True, "hidden_dims": [256, 256]}     # utils/launcher.py:61-66,95-104
+
+
+def _check_architecture_kwargs(policy_kwargs, extra, pixel):
+    """The kernels implement ONE architecture - the one every SERL launcher builds (utils/launcher.py:50-116): tanh MLPs
+    [256, 256] with LayerNorm, tanh-squashed Gaussian policy with "exp" std parameterisation, shared encoder.  The
+    reference's own defaults when these kwargs are omitted differ (swish, no LayerNorm, "uniform" std; sac.py:402-411,
+    drq.py:113-131), so silently accepting other settings would build a different model than the caller asked for."""
+    pk = dict(policy_kwargs or {})
+    if pk.get("std_parameterization", "exp") != "exp" or not pk.get("tanh_squash_distribution", True) or pk.get("fixed_std") is not None:
+        raise NotImplementedError(f"policy_kwargs={pk}: only the launcher's tanh-squashed 'exp' std parameterisation is implemented")
+    for name in ("critic_network_kwargs", "policy_network_kwargs"):
+        nk = extra.pop(name, None)
+        if nk is None:
+            continue
+        act = nk.get("activations", "tanh")
+        act = getattr(act, "__name__", act)
+        if act != "tanh" or not nk.get("use_layer_norm", True) or list(nk.get("hidden_dims", [256, 256])) != [256, 256] \
+                or nk.get("dropout_rate") not in (None, 0, 0.0):
+            raise NotImplementedError(f"{name}={nk}: only {_LAUNCHER_NET_KWARGS} (utils/launcher.py) is implemented")
+    if extra.pop("shared_encoder", True) is not True:
+        raise NotImplementedError("shared_encoder=False is not implemented (every SERL launcher shares the encoder)")
+    for k in ("actor_optimizer_kwargs", "critic_optimizer_kwargs", "temperature_optimizer_kwargs", "image_keys", "augmentation_function"):
+        if extra.get(k) not in (None, {}):
+            if k.endswith("optimizer_kwargs") and set(extra[k]) <= {"learning_rate"} and extra[k].get("learning_rate", 3e-4) == 3e-4:
+                extra.pop(k)
+                continue
+            raise NotImplementedError(f"{k}={extra[k]!r} is not supported; use learning_rate=")
+        extra.pop(k, None)
+    if extra:
+        raise TypeError(f"unexpected keyword arguments {sorted(extra)}")
+
+
+def register_pytree(cls):
+    """The learner scripts treat the agent as a JAX pytree: `jax.device_put(jax.tree_map(jnp.array, agent), sharding)`
+    (examples/async_drq_sim/async_drq_sim.py:347-349) and `jax.block_until_ready(agent)` (:296).  This agent's arrays live in
+    HBM behind the C-ABI, so it registers as a LEAF-LESS pytree node (the whole object travels as static aux data): both calls
+    become identity operations.  No-op when jax is not importable."""
+    try:
+        from jax import tree_util
+    except Exception:                                   # noqa: BLE001
+        return False
+    try:
+        tree_util.register_pytree_node(cls, lambda a: ((), a), lambda aux, _children: aux)
+    except ValueError:                                  # already registered
+        pass
+    return True
+
+
+register_pytree(SACAgent)
 
 
 def _host_split(key: np.ndarray, n: int) -> np.ndarray:

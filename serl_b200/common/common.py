@@ -64,6 +64,15 @@ class TrainState:
             out[name] = {"count": int(counts[gid]), "mu": z(mu, mu_aux), "nu": z(nu, nu_aux)}
         return out
 
+    # -- checkpoints (async_drq_sim.py:303-307 passes `agent.state` to flax.training.checkpoints) --------------
+    def state_dict(self) -> dict:
+        return {"step": int(self.step), "params": self.params, "target_params": self.target_params,
+                "opt_states": self.opt_states, "rng": self.rng}
+
+    def load_state_dict(self, d: dict) -> "TrainState":
+        return self.replace(step=d["step"], params=d["params"], target_params=d["target_params"], opt_states=d["opt_states"],
+                            rng=d["rng"])
+
     # -- functional-style updates ------------------------------------------------------------------
     def replace(self, **kw) -> "TrainState":
         st = self._store
@@ -103,3 +112,18 @@ class TrainState:
         if kw:
             raise TypeError(f"TrainState.replace: unknown fields {sorted(kw)}")
         return self
+
+
+def _register_flax_serialization():
+    try:
+        from flax import serialization
+    except Exception:                                   # noqa: BLE001
+        return False
+    try:
+        serialization.register_serialization_state(TrainState, lambda s: s.state_dict(), lambda s, d: s.load_state_dict(d))
+    except ValueError:
+        pass
+    return True
+
+
+_register_flax_serialization()

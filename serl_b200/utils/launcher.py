@@ -50,8 +50,8 @@ def make_trainer_config(port_number: int = 5488, broadcast_port: int = 5489):
 
 
 def make_wandb_logger(project: str = "agentlace", description: str = "serl_launcher", debug: bool = False):
-    """utils/launcher.py:180-198: the reference's WandBLogger is consumed unchanged when importable."""
-    from serl_launcher.common.wandb import WandBLogger
+    """utils/launcher.py:180-198."""
+    from ..common.wandb import WandBLogger
     cfg = WandBLogger.get_default_config()
     cfg.update({"project": project, "exp_descriptor": description, "tag": description})
     return WandBLogger(wandb_config=cfg, variant={}, debug=debug)
