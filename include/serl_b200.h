@@ -224,6 +224,23 @@ int serl_actor_loss(const float* q, const float* logp, const float* lagrange, co
 int serl_temperature_loss(const float* logp, const float* lagrange, float target_entropy, float grad_scale,
                           float* dlagrange, float* info /*1*/, int B, void* stream);
 
+/* Stride-1 3x3 convolution + GroupNorm(4 groups) [+ residual] [+ ReLU] in one kernel (vision/resnet_v1.py:129-156: the
+   ResNetBlock body after / including each 3x3 conv).  An image's accumulators stay in tensor memory until its statistics are
+   complete, so no raw conv output and no normalisation pass ever touch HBM:
+       y = [relu]( GN(conv3x3(x, w); gamma, beta) [+ res | + GN_res(res)] )
+   x (N,H,W,Ci), res / y (N,H,W,Co) 16-bit NHWC; w packed [Co][9*Ci] K-major ((kh,kw,ci) order); out_f32 (N,H,W,Co) replaces y
+   for the last block.  res_stats (N,4,2) + res_gamma/res_beta: the residual is a RAW projection-conv output whose own
+   GroupNorm is applied on the fly.  Shapes: the four ResNet-10 block shapes at 128x128 input (H=W in {32,16,8,4}, Ci=Co). */
+typedef struct serl_conv3x3_res_desc {
+  const void* x; const void* w; void* y; float* out_f32; const void* res;
+  const float* gamma; const float* beta;
+  const float* res_stats; const float* res_gamma; const float* res_beta;
+  int32_t* error;
+  int32_t N, H, W, Ci, Co, relu, fmt;
+  float eps;
+} serl_conv3x3_res_desc;
+int serl_conv3x3_res_h16(const serl_conv3x3_res_desc* d, void* stream);
+
 /* ---- optimizer (common/common.py:124-168, common/optimizers.py:6-56) --------------------------- */
 typedef struct serl_adam_desc {
   float* params; float* target; float* m; float* v; const float* grad;

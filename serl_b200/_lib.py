@@ -63,6 +63,12 @@ class StemPoolDesc(C.Structure):
                 ("N", i32), ("fmt", i32)]
 
 
+class Conv3x3ResDesc(C.Structure):
+    _fields_ = [("x", vp), ("w", vp), ("y", vp), ("out_f32", vp), ("res", vp), ("gamma", vp), ("beta", vp), ("res_stats", vp),
+                ("res_gamma", vp), ("res_beta", vp), ("error", vp), ("N", i32), ("H", i32), ("W", i32), ("Ci", i32), ("Co", i32),
+                ("relu", i32), ("fmt", i32), ("eps", f32)]
+
+
 class AdamDesc(C.Structure):
     _fields_ = [("params", vp), ("target", vp), ("m", vp), ("v", vp), ("grad", vp), ("n", i32), ("seg_end", i32 * 3),
                 ("live", i32 * 3), ("counts", vp), ("lr", f32 * 3), ("warmup", i32 * 3), ("b1", f32), ("b2", f32),
@@ -91,6 +97,7 @@ _PROTOS = {
     "serl_trunk_stem_prep_h16": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_conv2d_tc_h16": [C.POINTER(ConvTcDesc), vp],
     "serl_conv3x3s1_tc_h16": [C.POINTER(ConvTcDesc), C.c_int, vp],
+    "serl_conv3x3_res_h16": [C.POINTER(Conv3x3ResDesc), vp],
     "serl_gn_finalize": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp],
     "serl_affine_relu_h16": [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_stem_conv_pool_tc_h16": [C.POINTER(StemPoolDesc), vp],

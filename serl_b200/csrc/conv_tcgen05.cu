@@ -590,6 +590,214 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Stem v2 (round 2): the im2col view is produced by the TMA unit, not by threads.
+//
+// An operand row of k-block r' (kernel row r' of the 4x4 space-to-depth kernel) for output position (y, x) is the 128
+// contiguous bytes of s2d pixels (y+r', x..x+3).  Consecutive positions overlap by 96 bytes, which a UMMA descriptor cannot
+// express - but a TENSOR MAP can: the s2d image is described to the TMA unit as the 5-D tensor
+//     (64 elements = 4 px | j = 0..15, stride 4 px | v = 0..3, stride 1 px | y, stride one s2d row | n, stride one image)
+// whose (j, v) dimensions overlap in memory (x = 4j + v).  ONE cp.async.bulk.tensor.5d with box (64, 16, 4, 1, 1) then lands
+// a whole input row as [v][j][128 B] = 64 swizzled operand rows (8 KB) in shared memory - the 4x-redundant column im2col is
+// created by the copy engine, and the row dimension of the window is free (k-block r' simply starts r' row-slots later).
+// A tile = 2 output rows = two adjacent row-slots = 16 swizzle atoms at a constant 1 KB pitch, so the MMA loop is the old
+// one (4 k-blocks x 4 k-steps, resident 32 KB weights) with nothing to build: the shared->shared pass that took 45 % of the
+// L1TEX data pipe in round 1 (profiles/r01_ncu_sampler_stem_full.md) is gone.  TMEM lane m of a tile is output position
+// (row m >> 6, x = 4 (m & 15) + ((m >> 4) & 3)); the epilogue undoes that permutation when it stages values for the pool.
+//
+// Input rows live in a ring of S2_RING row-slots fed row by row (each s2d row is fetched from L2 ONCE per 8-tile unit: 19
+// rows per 16 output rows instead of 5 rows per 2), plus a MIRROR slot behind the last one that always holds a copy of
+// slot 0, so that the pair (last slot, slot 0) is contiguous like every other pair of consecutive rows.
+//   warps 0-7  epilogue: two groups of 4 warps, group g owns channels [32g, 32g+32) of every tile (own 8 KB staging tile,
+//              own named barrier), so the pool carry of a (column, channel-chunk) stays in one thread's registers
+//   warp 8     tcgen05.mma issuer (one thread)          warp 9   TMA: weights once, then one s2d row per slot
+// TMEM: 4 accumulators x 64 columns (tile i+3's MMAs can run while tile i is still being pooled).
+// ---------------------------------------------------------------------------------------------
+constexpr int S2_RING = 16;
+constexpr int S2_ROW_BYTES = 8192;                                               // [v 4][j 16][128 B]
+constexpr int S2_ACC = 4;
+constexpr int S2_UNIT_ROWS = 19;                                                 // s2d rows of an 8-tile unit (16 output rows + 3)
+
+__device__ inline void s2_tma_5d(void* smem_dst, const CUtensorMap* map, int c3, int c4, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %3, %3, %4, %5}], [%2];"
+               ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(0), "r"(c3), "r"(c4) : "memory");
+}
+__device__ inline int s2_sw(int m) { return ((m >> 1) ^ (m >> 5)) & 3; }        // staging-tile chunk swizzle (writer: m = lane; reader: strided m)
+
+template <class F>
+__global__ void __launch_bounds__(TC_THREADS, 1) stem2_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
+                                                                  const ConvTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int BN = 64, W_TILE = BN * 128;
+  uint8_t* sRing = smem;                                        // (S2_RING + 1) x 8 KiB, the last slot mirrors slot 0
+  uint8_t* sW = sRing + (S2_RING + 1) * S2_ROW_BYTES;           // 4 x 8 KiB resident weights
+  uint8_t* sStage = sW + 4 * W_TILE;                            // 2 x 8 KiB pool staging tiles (one per epilogue group)
+  uint64_t* rfull = reinterpret_cast<uint64_t*>(sStage + 2 * ST_POOL_STAGE);
+  uint64_t* rempty = rfull + S2_RING;
+  uint64_t* afull = rempty + S2_RING;
+  uint64_t* aempty = afull + S2_ACC;
+  uint64_t* wfull = aempty + S2_ACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_units = a.N * 4;                                  // 4 units of 8 tiles (16 output rows) per image
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S2_RING; ++s) { tc_mbar_init(&rfull[s], 1); tc_mbar_init(&rempty[s], 1); }
+    for (int s = 0; s < S2_ACC; ++s) { tc_mbar_init(&afull[s], 1); tc_mbar_init(&aempty[s], 8); }
+    tc_mbar_init(wfull, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(S2_ACC * BN)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 9 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 8) {
+    // ------------------------------- epilogue: stats + fused 3x3/2 max-pool -------------------------------
+    const int grp = warp >> 2, quarter = warp & 3;
+    const int m = quarter * 32 + lane;                          // TMEM lane = operand row of the tile
+    uint8_t* stage = sStage + grp * ST_POOL_STAGE;
+    const int tg = threadIdx.x & 127, pj = tg >> 2, qd = tg & 3; // pool phase: pooled column, 8-channel chunk of this group's 32
+    const int bar_id = 1 + grp;
+    uint32_t prevA[4] = {0u, 0u, 0u, 0u};
+    bool ok = true;
+    int ac = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int n_img = u >> 2;
+      for (int tt = 0; tt < 8; ++tt, ++ac) {
+        const int as = ac & (S2_ACC - 1);
+        const int t = (u & 3) * 8 + tt;                          // tile row of the image: conv rows 2t, 2t+1
+        ok = ok && tc_mbar_wait(&afull[as], (uint32_t)((ac / S2_ACC) & 1), a.error);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int c0 = grp * 32 + h * 16;
+          uint32_t v[16];
+          tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c0), v);
+          if (h == 1) {                                          // this warp's last read of the accumulator: hand the stage back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) tc_mbar_arrive(&aempty[as]);
+          }
+          float s = 0.f, ss = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { const float f = __uint_as_float(v[j]); s += f; ss += f * f; }
+          if (!ok) { s = 0.f; ss = 0.f; }
+          s = warp_sum(s); ss = warp_sum(ss);
+          if (ok && lane == 0) { float* st = a.stats + ((size_t)n_img * 4 + c0 / 16) * 2; atomicAdd(st, s); atomicAdd(st + 1, ss); }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] ^= (uint32_t)((a.neg_mask >> (c0 + j)) & 1ull) << 31;
+          uint32_t pk[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pk[j] = F::pack(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          uint8_t* row = stage + m * 64;
+          const int sw = s2_sw(m);
+          *reinterpret_cast<uint4*>(row + (((2 * h) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(row + (((2 * h + 1) ^ sw) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        uint32_t B[4] = {0u, 0u, 0u, 0u}, R1[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+#pragma unroll
+          for (int dc = 0; dc < 3; ++dc) {
+            const int col = 2 * pj + dc;
+            if (col < 64) {
+              const int mm = r * 64 + (col & 3) * 16 + (col >> 2);     // operand row holding position (r, col)
+              const uint4 q4 = *reinterpret_cast<const uint4*>(stage + mm * 64 + ((qd ^ s2_sw(mm)) << 4));
+              uint32_t* acc = r == 0 ? B : R1;
+              if (dc == 0) { acc[0] = q4.x; acc[1] = q4.y; acc[2] = q4.z; acc[3] = q4.w; }
+              else { acc[0] = F::max2(acc[0], q4.x); acc[1] = F::max2(acc[1], q4.y); acc[2] = F::max2(acc[2], q4.z); acc[3] = F::max2(acc[3], q4.w); }
+            }
+          }
+        }
+        const size_t cofs = (size_t)pj * 64 + grp * 32 + qd * 8;
+        if (ok) {
+          if (tt != 0) {
+            *reinterpret_cast<uint4*>(a.y + ((size_t)n_img * 32 + (t - 1)) * 2048 + cofs) =
+                make_uint4(F::max2(prevA[0], B[0]), F::max2(prevA[1], B[1]), F::max2(prevA[2], B[2]), F::max2(prevA[3], B[3]));
+          } else if (t != 0) {
+            *reinterpret_cast<uint4*>(a.pool_side + ((size_t)n_img * 4 + (t >> 3)) * 2048 + cofs) = make_uint4(B[0], B[1], B[2], B[3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) prevA[i] = F::max2(B[i], R1[i]);
+        if (ok && tt == 7)
+          *reinterpret_cast<uint4*>(a.y + ((size_t)n_img * 32 + t) * 2048 + cofs) = make_uint4(prevA[0], prevA[1], prevA[2], prevA[3]);
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // staging tile free for the next tile
+      }
+    }
+  } else if (warp == 8) {
+    // ------------------------------- MMA issuer (one thread) ------------------------------
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t r_lo = (smem_u32(sRing) & 0x3FFFF) >> 4, w_lo = (smem_u32(sW) & 0x3FFFF) >> 4;
+      bool ok = tc_mbar_wait(wfull, 0u, a.error);
+      int ac = 0;
+      uint32_t cbase = 0;                                        // ring counter of the unit's first row
+      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x, cbase += S2_UNIT_ROWS) {
+        for (int tt = 0; tt < 8 && ok; ++tt, ++ac) {
+          const int as = ac & (S2_ACC - 1);
+          ok = tc_mbar_wait(&aempty[as], (uint32_t)((ac / S2_ACC) & 1) ^ 1u, a.error);
+          for (int i = (tt == 0 ? 0 : 3); i < 5 && ok; ++i) {    // rows 2tt .. 2tt+4; all but the last two were waited for by earlier tiles
+            const uint32_t r = cbase + 2 * tt + i;
+            ok = tc_mbar_wait(&rfull[r & (S2_RING - 1)], (r / S2_RING) & 1u, a.error);
+          }
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) {
+            const uint32_t slot = (cbase + 2 * tt + kb) & (S2_RING - 1);    // rows (slot, slot + 1): slot + 1 == S2_RING is the mirror of slot 0
+            const uint64_t ad = desc_hi | (uint64_t)(r_lo + slot * (S2_ROW_BYTES >> 4));
+            const uint64_t bd = desc_hi | (uint64_t)(w_lo + (uint32_t)kb * (W_TILE >> 4));
+#pragma unroll
+            for (int k = 0; k < TC_BK / 16; ++k) tc_mma_bf16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+          }
+          // rows 2tt, 2tt+1 are not read by later tiles (the unit's last tile also releases its three tail rows)
+          const int nrel = tt == 7 ? 5 : 2;
+          for (int i = 0; i < nrel; ++i) tc_commit(&rempty[(cbase + 2 * tt + i) & (S2_RING - 1)]);
+          if (ok) tc_commit(&afull[as]); else tc_mbar_arrive(&afull[as]);
+        }
+      }
+    }
+  } else {
+    // ------------------------------- TMA: resident weights, then one s2d row per ring slot ------------------------
+    if (lane == 0) {
+      tc_mbar_expect_tx(wfull, 4u * W_TILE);
+      for (int kb = 0; kb < 4; ++kb) tc_tma_2d(sW + kb * W_TILE, &wmap, kb * TC_BK, 0, wfull);
+      bool ok = true;
+      uint32_t c = 0;
+      for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x) {
+        const int n = u >> 2, y0 = (u & 3) * 16;
+        for (int i = 0; i < S2_UNIT_ROWS && ok; ++i, ++c) {
+          const uint32_t slot = c & (S2_RING - 1);
+          ok = tc_mbar_wait(&rempty[slot], ((c / S2_RING) & 1u) ^ 1u, a.error);
+          if (!ok) break;
+          tc_mbar_expect_tx(&rfull[slot], slot == 0 ? 2u * S2_ROW_BYTES : (uint32_t)S2_ROW_BYTES);
+          s2_tma_5d(sRing + slot * S2_ROW_BYTES, &xmap, y0 + i, n, &rfull[slot]);
+          if (slot == 0) s2_tma_5d(sRing + S2_RING * S2_ROW_BYTES, &xmap, y0 + i, n, &rfull[slot]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(S2_ACC * BN)) : "memory");
+  }
+}
+
 // ---- stem input: uint8 crops -> normalised 16-bit, 2x2 space-to-depth, zero padded: (N,67,67,16) [12 real + 4 zero ch] ----
 template <class F>
 __global__ void stem_prep_kernel(const uint8_t* __restrict__ x, uint16_t* __restrict__ xs, int N, int H, int W, int Hs, int Ws) {
@@ -859,6 +1067,53 @@ static int launch_stem_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
   return check_launch("stem_tc_kernel");
 }
 
+typedef CUresult (*TcEncodeTiledFn5)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Stem v2: weights map as launch_stem_tc, plus the overlapping 5-D map of the s2d image (see stem2_tc_kernel).
+// Returns SERL_ERR_UNSUPPORTED (and launches nothing) if the driver refuses the overlapping-stride tensor map.
+template <class F>
+static int launch_stem2_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
+  constexpr size_t smem = (size_t)(S2_RING + 1) * S2_ROW_BYTES + 4 * 64 * 128 + 2 * ST_POOL_STAGE + 1024 + 512;
+  auto kern = stem2_tc_kernel<F>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(stem2_tc)");
+    configured = true;
+  }
+  TcEncodeTiledFn enc = tc_get_encode();
+  if (!enc) { set_last_error("serl_stem_conv_pool_tc_h16: cuTensorMapEncodeTiled unavailable"); return SERL_ERR_CUDA; }
+  const CUtensorMapDataType dt = fmt == SERL_FMT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap wmap, xmap;
+  {
+    const cuuint64_t gdim[2] = {256, 64};
+    const cuuint64_t gstr[1] = {512};
+    const cuuint32_t box[2] = {64u, 64u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    CUresult r = enc(&wmap, dt, 2, const_cast<uint16_t*>(a.w), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("serl_stem_conv_pool_tc_h16: weight tensor map failed (%d)", (int)r); return SERL_ERR_CUDA; }
+  }
+  {
+    // s2d image (N, 67, 67, 16) 16-bit seen as (64 el | j: 16 x 128 B | v: 4 x 32 B | y: 67 x 2144 B | n): x = 4 j + v, j and v overlap
+    const cuuint64_t row_bytes = 67ull * 16 * 2, img_bytes = 67ull * row_bytes;
+    const cuuint64_t gdim[5] = {64, 16, 4, 67, (cuuint64_t)a.N};
+    const cuuint64_t gstr[4] = {128, 32, row_bytes, img_bytes};
+    const cuuint32_t box[5] = {64u, 16u, 4u, 1u, 1u};
+    const cuuint32_t estr[5] = {1u, 1u, 1u, 1u, 1u};
+    CUresult r = enc(&xmap, dt, 5, const_cast<uint16_t*>(a.x), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_last_error("serl_stem_conv_pool_tc_h16: overlapping 5-D tensor map refused by the driver (%d)", (int)r); return SERL_ERR_UNSUPPORTED; }
+  }
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int units = a.N * 4;
+  const int grid = units < sms ? units : sms;                   // persistent, one CTA per SM
+  kern<<<grid, TC_THREADS, smem, st>>>(wmap, xmap, a);
+  return check_launch("stem2_tc_kernel");
+}
+
 template <class F>
 static int conv_tc_dispatch(const serl_conv_tc_desc* d, ConvTcArgs& a, cudaStream_t st) {
   if (d->stem) {
@@ -913,6 +1168,14 @@ extern "C" int serl_stem_conv_pool_tc_h16(const serl_stem_pool_desc* d, void* st
   a.N = d->N; a.Hi = 67; a.Wi = 67; a.Ci = 12; a.Co = 64; a.kh = 4; a.kw = 4; a.stride = 1; a.pad = 0;
   a.Ho = 64; a.Wo = 64; a.M = d->N * 64 * 64; a.Cg = 16; a.num_kb = 4; a.cblocks = 1;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SERL_TC_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
+  // v2 (TMA-built im2col, row ring) unless SERL_STEM_V2=0 or the driver refuses its tensor map; v1 (shared->shared im2col) otherwise
+  static int v2 = -1;
+  if (v2 < 0) { const char* e = getenv("SERL_STEM_V2"); v2 = (e && atoi(e) == 0) ? 0 : 1; }
+  if (v2 && !a.debug) {
+    const int rc = d->fmt == SERL_FMT_FP16 ? launch_stem2_tc<Fp16>(a, d->fmt, ST(stream)) : launch_stem2_tc<Bf16>(a, d->fmt, ST(stream));
+    if (rc != SERL_ERR_UNSUPPORTED) return rc;
+    v2 = 0;
+  }
   return d->fmt == SERL_FMT_FP16 ? launch_stem_tc<Fp16, true>(a, d->fmt, ST(stream)) : launch_stem_tc<Bf16, true>(a, d->fmt, ST(stream));
 }
 

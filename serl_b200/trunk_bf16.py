@@ -35,6 +35,11 @@ USE_FUSED_STEM_POOL = True
 USE_FUSED_GN = True
 GN_EPS = 1e-5
 
+# Stride-1 3x3 convs with GroupNorm (+ residual) (+ ReLU) inside the conv kernel (conv3x3_res.cu): an image's accumulators stay
+# in tensor memory until its statistics are complete, so neither the raw conv output nor a normalisation pass touches HBM
+# (no affine_relu after ResNetBlock_0/Conv_0, no block_combine after any Conv_1).  SERL_RES_CONV=0 selects round 1's path.
+USE_RES_CONV = os.environ.get("SERL_RES_CONV", "0") != "0"
+
 # The 1x1 / stride-2 projection conv of a block only depends on the block input: run it on a side stream next to the
 # conv -> GroupNorm+ReLU -> conv chain (joined before the residual add).
 USE_PROJ_SIDE_STREAM = os.environ.get("SERL_PROJ_SIDE", "1") != "0"
@@ -92,6 +97,21 @@ def _conv(plan, x, w, y, stats, N, Hi, Wi, Ci, Ho, Wo, Co, k, stride, pad_lo, in
         L.call("serl_conv3x3s1_tc_h16", C.byref(d), BASE_OFFSET_MODE, _s())
     else:
         L.call("serl_conv2d_tc_h16", C.byref(d), _s())
+
+
+def _conv_res(plan, x, w, y, gamma, beta, N, HW_, C_, *, res=None, res_stats=None, res_gamma=None, res_beta=None, relu=True, out_f32=None):
+    """y = [relu](GN(conv3x3(x)) [+ res | + GN_res(res)]) in one launch (serl_conv3x3_res_h16)."""
+    d = L.Conv3x3ResDesc()
+    d.x, d.w = x.data_ptr(), w.data_ptr()
+    d.y = None if y is None else y.data_ptr()
+    d.out_f32 = None if out_f32 is None else out_f32.data_ptr()
+    d.res = None if res is None else res.data_ptr()
+    d.gamma, d.beta = gamma.data_ptr(), beta.data_ptr()
+    if res_stats is not None:
+        d.res_stats, d.res_gamma, d.res_beta = res_stats.data_ptr(), res_gamma.data_ptr(), res_beta.data_ptr()
+    d.error = plan.error.data_ptr()
+    d.N, d.H, d.W, d.Ci, d.Co, d.relu, d.fmt, d.eps = N, HW_, HW_, C_, C_, int(relu), plan.fmt, GN_EPS
+    L.call("serl_conv3x3_res_h16", C.byref(d), _s())
 
 
 def _finalize(stats, gamma, beta, ab, N, Cc, HW):
@@ -167,13 +187,32 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
                 side.fork()
                 with side:
                     _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, sP, N, s, s, cin, so, so, f, 1, stride, 0)
-        _conv(p, x, wp[f"{b}/Conv_0/kernel"], yA, sA, N, s, s, cin, so, so, f, 3, stride, lo)
-        # materialise relu(GN(yA)) in place (one HBM-speed pass); the conv operands are then plain async copies
-        if USE_FUSED_GN:
-            L.call("serl_affine_relu_gn_h16", yA.data_ptr(), sA.data_ptr(), gA.data_ptr(), bA.data_ptr(), N, so * so, f, GN_EPS, p.fmt, _s())
+        res_ok = USE_RES_CONV and USE_FUSED_GN and {32: 64, 16: 128, 8: 256, 4: 512}.get(so) == f
+        if res_ok and stride == 1 and cin == f:
+            # ResNetBlock_0: both convs are stride-1 3x3: conv -> GN -> ReLU in one kernel (activated output, no affine_relu pass)
+            _conv_res(p, x, wp[f"{b}/Conv_0/kernel"], yA, gA, bA, N, so, f, relu=True)
+            engine.launches -= 1
         else:
-            abA = _finalize(sA, gA, bA, p.aff[0], N, f, so * so)
-            L.call("serl_affine_relu_h16", yA.data_ptr(), abA[0].data_ptr(), abA[1].data_ptr(), N, so * so, f, p.fmt, _s())
+            _conv(p, x, wp[f"{b}/Conv_0/kernel"], yA, sA, N, s, s, cin, so, so, f, 3, stride, lo)
+            # materialise relu(GN(yA)) in place (one HBM-speed pass); the conv operands are then plain async copies
+            if USE_FUSED_GN:
+                L.call("serl_affine_relu_gn_h16", yA.data_ptr(), sA.data_ptr(), gA.data_ptr(), bA.data_ptr(), N, so * so, f, GN_EPS, p.fmt, _s())
+            else:
+                abA = _finalize(sA, gA, bA, p.aff[0], N, f, so * so)
+                L.call("serl_affine_relu_h16", yA.data_ptr(), abA[0].data_ptr(), abA[1].data_ptr(), N, so * so, f, p.fmt, _s())
+        if res_ok:
+            # Conv_1 -> GN -> (+ residual: block input, or GN(projection) applied on the fly) -> ReLU in one kernel: no block_combine
+            if proj and side is None:
+                _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, sP, N, s, s, cin, so, so, f, 1, stride, 0)
+            elif proj:
+                side.join()
+            _conv_res(p, yA, wp[f"{b}/Conv_1/kernel"], None if last else out, gB, bB, N, so, f, res=yP if proj else x,
+                      res_stats=sP if proj else None, res_gamma=gP if proj else None, res_beta=bP if proj else None, relu=True,
+                      out_f32=feats if last else None)
+            engine.launches += 3 + int(proj)
+            free, cur = [cur, iy, iy2, ir], io
+            x, s, cin = out, so, f
+            continue
         _conv(p, yA, wp[f"{b}/Conv_1/kernel"], yB, sB, N, so, so, f, so, so, f, 3, 1, 1)
         if proj and side is None:
             _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, sP, N, s, s, cin, so, so, f, 1, stride, 0)
