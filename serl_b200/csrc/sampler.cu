@@ -313,21 +313,42 @@ __global__ void __launch_bounds__(kFrameThreads) sample_frames_kernel(const Samp
       const int y0 = band * kBandRows, rows = min(kBandRows, H - y0);
       const int r_lo = min(max(y0 + dy, 0), H - 1);
       const uint8_t* sb = smem + band * band_bytes;
-      const uint32_t* s32 = reinterpret_cast<const uint32_t*>(sb);
       uint8_t* dst = (which ? a.next_pix[cam] : a.obs_pix[cam]) + ((size_t)g * H + y0) * row_bytes;
-      // interior chunks: pure funnel-shift copies (no divergence); the <= 1-2 chunks per row that touch the clamped edge
-      // are handled by a second, compact loop so that no warp pays the per-byte path for its 31 interior lanes
-      for (int q = threadIdx.x; q < rows * cpr; q += blockDim.x) {
-        const int yl = q / cpr, jj = q - yl * cpr;
-        const int b0 = jj * 16, a0 = b0 + sh;
-        if (a0 >= 0 && a0 + 16 <= row_bytes) {
+      // interior chunks: a row-shifted copy with ONE aligned 128-bit shared load per lane.  A warp takes whole rows; lane l
+      // loads the aligned 16-byte chunk (l + kq) of the source row (conflict-free: consecutive lanes, consecutive chunks),
+      // gets the next chunk from lane l+1 by shuffle, and funnels the two by the byte shift (uniform per frame).  Round 1
+      // read five 32-bit words per lane at a 16-byte lane stride: 4-way bank conflicts on 85 % of the shared wavefronts
+      // (profiles/r01_ncu_sampler_stem_full.md).  The <= 1 chunk per row that touches the clamped edge is handled by the
+      // compact bytewise loop below.
+      {
+        const int kqg = (sh >= 0) ? (sh >> 4) : -((-sh + 15) >> 4);   // floor(sh / 16)
+        const int bsh = sh - 16 * kqg;                         // 0..15
+        const int wsft = bsh >> 2, bits = (bsh & 3) * 8;
+        const uint4* s128 = reinterpret_cast<const uint4*>(sb);
+        const int cpr4 = row_bytes >> 4;
+        for (int yl = warp; yl < rows; yl += (kFrameThreads >> 5)) {
           const int r = min(max(y0 + yl + dy, 0), H - 1) - r_lo;
-          const int base = r * row_bytes + a0;
-          const int wi = base >> 2, bs = (base & 3) * 8;
-          const uint32_t w0 = s32[wi], w1 = s32[wi + 1], w2 = s32[wi + 2], w3 = s32[wi + 3], w4 = s32[wi + 4];
-          asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)yl * row_bytes + b0),
-                       "r"(__funnelshift_r(w0, w1, bs)), "r"(__funnelshift_r(w1, w2, bs)), "r"(__funnelshift_r(w2, w3, bs)),
-                       "r"(__funnelshift_r(w3, w4, bs)) : "memory");
+          for (int j0 = 0; j0 < cpr; j0 += 31) {              // 31 output chunks per pass (lane 31 only supplies its neighbour)
+            const int jj = j0 + lane, c = jj + kqg;
+            uint4 A = make_uint4(0u, 0u, 0u, 0u);
+            if (c >= 0 && c < cpr4) A = s128[r * cpr4 + c];
+            uint4 Bn;
+            Bn.x = __shfl_down_sync(0xffffffffu, A.x, 1); Bn.y = __shfl_down_sync(0xffffffffu, A.y, 1);
+            Bn.z = __shfl_down_sync(0xffffffffu, A.z, 1); Bn.w = __shfl_down_sync(0xffffffffu, A.w, 1);
+            const int a0 = jj * 16 + sh;
+            if (lane < 31 && jj < cpr && a0 >= 0 && a0 + 16 <= row_bytes) {
+              uint32_t w0, w1, w2, w3, w4;                     // the five words starting at word offset wsft of (A, Bn)
+              switch (wsft) {
+                case 0: w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = Bn.x; break;
+                case 1: w0 = A.y; w1 = A.z; w2 = A.w; w3 = Bn.x; w4 = Bn.y; break;
+                case 2: w0 = A.z; w1 = A.w; w2 = Bn.x; w3 = Bn.y; w4 = Bn.z; break;
+                default: w0 = A.w; w1 = Bn.x; w2 = Bn.y; w3 = Bn.z; w4 = Bn.w; break;
+              }
+              asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(dst + (size_t)yl * row_bytes + jj * 16),
+                           "r"(__funnelshift_r(w0, w1, bits)), "r"(__funnelshift_r(w1, w2, bits)), "r"(__funnelshift_r(w2, w3, bits)),
+                           "r"(__funnelshift_r(w3, w4, bits)) : "memory");
+            }
+          }
         }
       }
       const int ne_l = sh < 0 ? min(cpr, (-sh + 15) >> 4) : 0, ne_r = sh > 0 ? min(cpr - ne_l, (sh + 15) >> 4) : 0;
