@@ -241,6 +241,19 @@ typedef struct serl_conv3x3_res_desc {
 } serl_conv3x3_res_desc;
 int serl_conv3x3_res_h16(const serl_conv3x3_res_desc* d, void* stream);
 
+/* Head of ResNetBlock_1..3 in one kernel (vision/resnet_v1.py:139-154): x (N,2Wo,2Wo,Ci) ->
+       y = relu(GN(conv3x3 stride 2 SAME(x, w); gamma, beta))            (N,Wo,Wo,Co), Co = 2 Ci
+       r = GN(conv1x1 stride 2(x, w_proj); gamma_proj, beta_proj)        (N,Wo,Wo,Co)   (the block's residual branch, normalised)
+   w packed [Co][9*Ci], w_proj [Co][Ci], K-major 16-bit.  Wo in {16, 8, 4} (Co = 128, 256, 512). */
+typedef struct serl_conv3x3s2_res_desc {
+  const void* x; const void* w; const void* w_proj; void* y; void* r;
+  const float* gamma; const float* beta; const float* gamma_proj; const float* beta_proj;
+  int32_t* error;
+  int32_t N, Wo, Ci, Co, fmt;
+  float eps;
+} serl_conv3x3s2_res_desc;
+int serl_conv3x3s2_res_h16(const serl_conv3x3s2_res_desc* d, void* stream);
+
 /* ---- optimizer (common/common.py:124-168, common/optimizers.py:6-56) --------------------------- */
 typedef struct serl_adam_desc {
   float* params; float* target; float* m; float* v; const float* grad;

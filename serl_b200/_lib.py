@@ -69,6 +69,11 @@ class Conv3x3ResDesc(C.Structure):
                 ("relu", i32), ("fmt", i32), ("eps", f32)]
 
 
+class Conv3x3S2ResDesc(C.Structure):
+    _fields_ = [("x", vp), ("w", vp), ("w_proj", vp), ("y", vp), ("r", vp), ("gamma", vp), ("beta", vp), ("gamma_proj", vp),
+                ("beta_proj", vp), ("error", vp), ("N", i32), ("Wo", i32), ("Ci", i32), ("Co", i32), ("fmt", i32), ("eps", f32)]
+
+
 class AdamDesc(C.Structure):
     _fields_ = [("params", vp), ("target", vp), ("m", vp), ("v", vp), ("grad", vp), ("n", i32), ("seg_end", i32 * 3),
                 ("live", i32 * 3), ("counts", vp), ("lr", f32 * 3), ("warmup", i32 * 3), ("b1", f32), ("b2", f32),
@@ -98,6 +103,7 @@ _PROTOS = {
     "serl_conv2d_tc_h16": [C.POINTER(ConvTcDesc), vp],
     "serl_conv3x3s1_tc_h16": [C.POINTER(ConvTcDesc), C.c_int, vp],
     "serl_conv3x3_res_h16": [C.POINTER(Conv3x3ResDesc), vp],
+    "serl_conv3x3s2_res_h16": [C.POINTER(Conv3x3S2ResDesc), vp],
     "serl_gn_finalize": [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, f32, vp],
     "serl_affine_relu_h16": [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_stem_conv_pool_tc_h16": [C.POINTER(StemPoolDesc), vp],

@@ -472,6 +472,322 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Head of ResNetBlock_1..3 in ONE kernel: the stride-2 3x3 conv (SAME: pad low 0 / high 1) -> GroupNorm -> ReLU  AND  the
+// 1x1 stride-2 projection conv -> GroupNorm of the residual branch (vision/resnet_v1.py:139-154).  Both read the same
+// block input; the projection's operand IS tap (0, 0) of the 3x3 conv (input pixel (2y, 2x)), so it costs one extra weight
+// tile per channel block and a second TMEM accumulator per tile - the separate projection kernels of round 1 (58 us per
+// 512 images) and the affine_relu passes after Conv_0 disappear.  Same item / two-pass resident-epilogue structure as
+// conv3x3_res_kernel (UT = MT = 2 tiles of 128 positions, 2 x 2 x 128 TMEM columns).
+// Operands by TMA with a traversal stride of 2 in x and y (elementStrides): the input is read as its four parity planes
+// P[p][q](y', x') = in(2y' + p, 2x' + q); tap (r, s) reads plane (r & 1, s & 1) shifted by (r >> 1, s >> 1).  Row shifts are
+// descriptor offsets; the one column shift (s = 2) needs a second copy of the q = 0 planes -> six variants per 64-channel
+// block instead of nine im2col taps, each an exact [row][image][x] tile; the out-of-range column / row of SAME's high
+// padding is zero-filled by the hardware.
+// ---------------------------------------------------------------------------------------------
+struct C3sArgs {
+  const float* gamma0; const float* beta0;               // GroupNorm after the 3x3 conv (MyGroupNorm_0)
+  const float* gammaP; const float* betaP;               // GroupNorm of the projection (norm_proj)
+  int32_t* error;
+  int N, Ci, Co, cblocks, n_items, n_tiles_n;
+  float eps;
+};
+
+template <class F, int W, int VST, int WST>
+__global__ void __launch_bounds__(R3_THREADS, 1) conv3x3s2_res_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
+                                                                       const __grid_constant__ CUtensorMap pmap, const __grid_constant__ CUtensorMap omap,
+                                                                       const __grid_constant__ CUtensorMap rmap, const C3sArgs a) {
+  using Gm = R3Geom<W>;
+  constexpr int BN = 128, G = Gm::G, TPI = Gm::TPI, TR = Gm::TR, ROWB = Gm::ROWB, UT = 2, MT = 2, IPU = UT * G / TPI;
+  static_assert(Gm::UT == 2 && Gm::MT == 2, "stride-2 kernel: 16x16 / 8x8 / 4x4 output maps");
+  constexpr int PATCH = (TR + 1) * ROWB;                 // one extra row: the r = 2 taps read plane rows y' + 1
+  constexpr int VSTAGE = MT * PATCH;
+  constexpr int B_STAGE = BN * 128;
+  constexpr int STG = 2 * 128 * 128;                     // one output tile: two 64-channel halves
+  constexpr int HC = 64;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sV = smem;
+  uint8_t* sB = sV + VST * VSTAGE;
+  uint8_t* sS = sB + WST * B_STAGE;
+  float* sCh = reinterpret_cast<float*>(sS + 2 * STG);   // [2 norms][BN][2]: gamma, beta
+  float* sStat = sCh + 2 * BN * 2;                       // [2 norms][IPU][4 groups][2]: mean, rstd
+  float* sRed = sStat + 2 * IPU * 8;                     // [2 norms][IPU][4 groups][2]: sum, sum of squares
+  uint64_t* vfull = reinterpret_cast<uint64_t*>(sRed + 2 * IPU * 8);
+  uint64_t* vempty = vfull + VST;
+  uint64_t* wfull = vempty + VST;
+  uint64_t* wempty = wfull + WST;
+  uint64_t* afull = wempty + WST;                        // per tile slot (conv + projection accumulators together)
+  uint64_t* aempty = afull + 2;
+  uint64_t* sfull = aempty + 2;
+  uint64_t* sfree = sfull + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Cg = a.Co / 4;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < VST; ++s) { r3_mbar_init(&vfull[s], 1); r3_mbar_init(&vempty[s], 1); }
+    for (int s = 0; s < WST; ++s) { r3_mbar_init(&wfull[s], 1); r3_mbar_init(&wempty[s], 1); }
+    for (int s = 0; s < 2; ++s) { r3_mbar_init(&afull[s], 1); r3_mbar_init(&aempty[s], 8); r3_mbar_init(&sfull[s], 1); r3_mbar_init(&sfree[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < 2 * IPU * 8; i += blockDim.x) sRed[i] = 0.f;
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(r3_smem(tmem_slot)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  if (warp == 9 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&xmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&wmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&pmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&omap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&rmap) : "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto tile_img = [&](int unit, int j) { return unit * IPU + (TPI > 1 ? 0 : j * G); };
+  auto tile_y0 = [&](int j) { return TPI > 1 ? j * TR : 0; };
+  // variant v -> parity plane (p, q) and column shift xs; taps served by it: (tap index r*3+s, plane-row offset)
+  //   v: 0 (0,0,0)  1 (0,1,0)  2 (0,0,1)  3 (1,0,0)  4 (1,1,0)  5 (1,0,1)
+
+  if (warp < 8) {
+    // =============================== epilogue ===============================
+    const int quarter = warp & 3, chalf = warp >> 2;
+    const int m = quarter * 32 + lane;
+    const int img_l = (m / W) % G;
+    const int et = threadIdx.x;
+    bool ok = true;
+    uint32_t tc = 0, sc = 0;
+    int stores_pending = 0;
+    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      const int unit = item / a.n_tiles_n, n0 = (item % a.n_tiles_n) * BN;
+      // ---------------- pass 1: statistics of both accumulators ----------------
+      for (int j = 0; j < UT; ++j) {
+        const uint32_t ts = (tc + j) & 1u;
+        ok = ok && r3_mbar_wait(&afull[ts], ((tc + j) >> 1) & 1u, a.error);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int img_u = (TPI > 1 ? 0 : j * G) + img_l;
+#pragma unroll
+        for (int which = 0; which < 2; ++which) {
+          float gs[2] = {0.f, 0.f}, gss[2] = {0.f, 0.f};
+#pragma unroll
+          for (int cc = 0; cc < HC; cc += 16) {
+            uint32_t v[16];
+            r3_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + ts * 256 + which * 128 + chalf * HC + cc, v);
+            float s = 0.f, ss = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { const float f = __uint_as_float(v[i]); s += f; ss += f * f; }
+            const int gl = (cc * 2 >= HC && Cg < HC) ? 1 : 0;
+            gs[gl] += s; gss[gl] += ss;
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const bool same = (G == 1) || (G == 2 && o != 8) || (G == 8 && o < 4);
+            if (same) {
+#pragma unroll
+              for (int g = 0; g < 2; ++g) { gs[g] += __shfl_xor_sync(0xffffffffu, gs[g], o); gss[g] += __shfl_xor_sync(0xffffffffu, gss[g], o); }
+            }
+          }
+          const bool head = (G == 1) ? lane == 0 : (G == 2 ? (lane & 23) == 0 : (lane & 3) == 0);
+          if (head && ok) {
+            const int g0 = (n0 + chalf * HC) / Cg;
+            float* red = sRed + which * IPU * 8;
+            atomicAdd(&red[(img_u * 4 + g0) * 2], gs[0]); atomicAdd(&red[(img_u * 4 + g0) * 2 + 1], gss[0]);
+            if (Cg < HC) { atomicAdd(&red[(img_u * 4 + g0 + 1) * 2], gs[1]); atomicAdd(&red[(img_u * 4 + g0 + 1) * 2 + 1], gss[1]); }
+          }
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      {
+        const float count = (float)(W * W) * (float)Cg;
+        for (int e = et; e < 2 * IPU * 4; e += R3_EPI_THREADS) {
+          const float s = sRed[e * 2], ss = sRed[e * 2 + 1];
+          const float mean = s / count;
+          const float var = fmaxf(ss / count - mean * mean, 0.f);
+          sStat[e * 2] = mean; sStat[e * 2 + 1] = rsqrtf(var + a.eps);
+        }
+        for (int c = et; c < 2 * BN; c += R3_EPI_THREADS) {
+          const int which = c / BN, cg = n0 + (c % BN);
+          sCh[c * 2] = which ? a.gammaP[cg] : a.gamma0[cg];
+          sCh[c * 2 + 1] = which ? a.betaP[cg] : a.beta0[cg];
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int i = et; i < 2 * IPU * 8; i += R3_EPI_THREADS) sRed[i] = 0.f;
+      // ---------------- pass 2: relu(GN(conv)) -> y, GN(projection) -> r, tile by tile ----------------
+      for (int j = 0; j < UT; ++j, ++tc) {
+        const uint32_t ts = tc & 1u;
+        const int img_u = (TPI > 1 ? 0 : j * G) + img_l;
+        const int g0 = (n0 + chalf * HC) / Cg;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which, ++sc) {
+          const uint32_t sb = sc & 1u;
+          ok = ok && r3_mbar_wait(&sfull[sb], (sc >> 1) & 1u, a.error);
+          const float2 st0 = *reinterpret_cast<const float2*>(sStat + ((which * IPU + img_u) * 4 + g0) * 2);
+          const float2 st1 = *reinterpret_cast<const float2*>(sStat + ((which * IPU + img_u) * 4 + (Cg < HC ? g0 + 1 : g0)) * 2);
+          const float2* chp = reinterpret_cast<const float2*>(sCh) + which * BN + chalf * HC;
+          uint8_t* srow = sS + sb * STG + chalf * (128 * 128) + m * 128;
+#pragma unroll
+          for (int cc = 0; cc < HC; cc += 16) {
+            uint32_t v[16];
+            r3_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + ts * 256 + which * 128 + chalf * HC + cc, v);
+            const float2 sg = (cc * 2 >= HC && Cg < HC) ? st1 : st0;
+            float o[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float2 q = chp[cc + i];
+              const float av = sg.y * q.x;
+              float y = fmaf(__uint_as_float(v[i]), av, q.y - sg.x * av);
+              if (which == 0) y = fmaxf(y, 0.f);
+              o[i] = y;
+            }
+            const int k0 = cc >> 3;
+            *reinterpret_cast<uint4*>(srow + (((k0) ^ (m & 7)) << 4)) = make_uint4(F::pack(o[0], o[1]), F::pack(o[2], o[3]), F::pack(o[4], o[5]), F::pack(o[6], o[7]));
+            *reinterpret_cast<uint4*>(srow + (((k0 + 1) ^ (m & 7)) << 4)) = make_uint4(F::pack(o[8], o[9]), F::pack(o[10], o[11]), F::pack(o[12], o[13]), F::pack(o[14], o[15]));
+          }
+          if (which == 1) {                                                // both accumulators of the tile slot drained
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) r3_mbar_arrive(&aempty[ts]);
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          if (et == 0) {
+            if (ok) {
+              const int nimg = tile_img(unit, j), y0r = tile_y0(j);
+#pragma unroll
+              for (int h = 0; h < 2; ++h) r3_tma_store_4d(which ? &rmap : &omap, sS + sb * STG + h * (128 * 128), n0 + h * 64, 0, nimg, y0r);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (stores_pending) {
+              asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+              r3_mbar_arrive(&sfree[sb ^ 1u]);
+            }
+            stores_pending = 1;
+          }
+        }
+      }
+    }
+    if (et == 0 && stores_pending) {
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      r3_mbar_arrive(&sfree[(sc - 1) & 1u]);
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+  } else if (warp == 8) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+      const uint32_t v_lo = (r3_smem(sV) & 0x3FFFF) >> 4, b_lo = (r3_smem(sB) & 0x3FFFF) >> 4;
+      bool ok = true;
+      uint32_t tc = 0, vc = 0, wc = 0;
+      for (int item = blockIdx.x; item < a.n_items && ok; item += gridDim.x, tc += UT) {
+        for (int jj = 0; jj < MT && ok; ++jj) ok = r3_mbar_wait(&aempty[(tc + jj) & 1u], (((tc + jj) >> 1) & 1u) ^ 1u, a.error);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int cb = 0; cb < a.cblocks && ok; ++cb) {
+          for (int v = 0; v < 6 && ok; ++v, ++vc) {
+            const uint32_t vs = vc % VST;
+            ok = r3_mbar_wait(&vfull[vs], (vc / VST) & 1u, a.error);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // weight tiles served by this variant, in ring order: [tap (r=0), (projection if v == 0), tap (r=2) if the plane row p == 0]
+            const int ntiles = v == 0 ? 3 : (v < 3 ? 2 : 1);
+            for (int e = 0; e < ntiles && ok; ++e, ++wc) {
+              const uint32_t ws = wc % WST;
+              ok = r3_mbar_wait(&wfull[ws], (wc / WST) & 1u, a.error);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const bool is_proj = (v == 0 && e == 1);
+              const int ro = (v == 0) ? (e == 2) : (v < 3 ? (e == 1) : 0);      // the r = 2 tap of a p == 0 plane reads plane row y' + 1
+              const bool first_conv = (cb == 0 && v == 0 && e == 0);
+              const uint64_t bd = desc_hi | (uint64_t)(b_lo + ws * (B_STAGE >> 4));
+#pragma unroll
+              for (int jj = 0; jj < MT; ++jj) {
+                const uint32_t ts = (tc + jj) & 1u;
+                const uint32_t tmem_d = tmem_base + ts * 256 + (is_proj ? 128u : 0u);
+                const uint64_t ad = desc_hi | (uint64_t)(v_lo + ((vs * VSTAGE + jj * PATCH + ro * ROWB) >> 4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const uint32_t acc = is_proj ? (uint32_t)((cb | k) != 0) : (uint32_t)(!(first_conv && k == 0));
+                  r3_mma(tmem_d, ad + 2 * k, bd + 2 * k, idesc, acc);
+                }
+              }
+              r3_commit(&wempty[ws]);
+            }
+            r3_commit(&vempty[vs]);
+          }
+        }
+        for (int jj = 0; jj < MT; ++jj) { if (ok) r3_commit(&afull[(tc + jj) & 1u]); else r3_mbar_arrive(&afull[(tc + jj) & 1u]); }
+      }
+    }
+  } else if (warp == 9) {
+    // =============================== patch TMA: six parity-plane variants per 64-channel block ===============================
+    if (lane == 0) {
+      bool ok = true;
+      uint32_t vc = 0;
+      for (int item = blockIdx.x; item < a.n_items && ok; item += gridDim.x) {
+        const int unit = item / a.n_tiles_n;
+        for (int cb = 0; cb < a.cblocks && ok; ++cb)
+          for (int v = 0; v < 6 && ok; ++v, ++vc) {
+            const uint32_t vs = vc % VST;
+            ok = r3_mbar_wait(&vempty[vs], ((vc / VST) & 1u) ^ 1u, a.error);
+            if (!ok) break;
+            const int p = v >= 3, q = (v % 3) == 1, xs = (v % 3) == 2;
+            r3_mbar_expect_tx(&vfull[vs], (uint32_t)VSTAGE);
+#pragma unroll
+            for (int jj = 0; jj < MT; ++jj)
+              r3_tma_load_4d(sV + vs * VSTAGE + jj * PATCH, &xmap, cb * 64, q + 2 * xs, tile_img(unit, jj), 2 * tile_y0(jj) + p, &vfull[vs]);
+          }
+      }
+    }
+  } else if (warp == 10) {
+    // =============================== weight TMA (same order as the MMA issuer consumes) ===============================
+    if (lane == 0) {
+      bool ok = true;
+      uint32_t wc = 0;
+      for (int item = blockIdx.x; item < a.n_items && ok; item += gridDim.x) {
+        const int n0 = (item % a.n_tiles_n) * BN;
+        for (int cb = 0; cb < a.cblocks && ok; ++cb)
+          for (int v = 0; v < 6 && ok; ++v) {
+            const int ntiles = v == 0 ? 3 : (v < 3 ? 2 : 1);
+            const int s = v % 3 == 0 ? 0 : (v % 3 == 1 ? 1 : 2);            // kernel column of the variant's taps
+            for (int e = 0; e < ntiles && ok; ++e, ++wc) {
+              const uint32_t ws = wc % WST;
+              ok = r3_mbar_wait(&wempty[ws], ((wc / WST) & 1u) ^ 1u, a.error);
+              if (!ok) break;
+              r3_mbar_expect_tx(&wfull[ws], (uint32_t)B_STAGE);
+              if (v == 0 && e == 1) {
+                r3_tma_load_2d(sB + ws * B_STAGE, &pmap, cb * 64, n0, &wfull[ws]);
+              } else {
+                const int r = v >= 3 ? 1 : (e == 0 ? 0 : 2);
+                r3_tma_load_2d(sB + ws * B_STAGE, &wmap, (r * 3 + s) * a.Ci + cb * 64, n0, &wfull[ws]);
+              }
+            }
+          }
+      }
+    }
+  } else {
+    // =============================== staging hand-over (no residual input in this kernel) ===============================
+    if (lane == 0) {
+      bool ok = true;
+      uint32_t sc = 0;
+      for (int item = blockIdx.x; item < a.n_items && ok; item += gridDim.x)
+        for (int j = 0; j < 2 * UT && ok; ++j, ++sc) {
+          ok = r3_mbar_wait(&sfree[sc & 1u], ((sc >> 1) & 1u) ^ 1u, a.error);
+          if (ok) r3_mbar_arrive(&sfull[sc & 1u]);
+        }
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
 typedef CUresult (*R3EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -537,9 +853,73 @@ static int launch_conv3r(const serl_conv3x3_res_desc* d, cudaStream_t st) {
   return check_launch("conv3x3_res_kernel");
 }
 
+// (N,H,W,C) 16-bit activations read with a traversal stride of 2 in x and y: box covers (64, 2*Wo, G, 2*rows) elements
+static bool r3_act_map_s2(CUtensorMap* map, CUtensorMapDataType dt, const void* ptr, int N, int H, int W, int C, int G, int Wo, int rows) {
+  const cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)N, (cuuint64_t)H};
+  const cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)H * W * C * 2, (cuuint64_t)W * C * 2};
+  const cuuint32_t box[4] = {64u, (cuuint32_t)(2 * Wo), (cuuint32_t)G, (cuuint32_t)(2 * rows)};
+  const cuuint32_t estr[4] = {1u, 2u, 1u, 2u};
+  return r3_get_encode()(map, dt, 4, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static bool r3_w_map(CUtensorMap* map, CUtensorMapDataType dt, const void* w, int K, int Co, int BN) {
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)Co};
+  const cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {64u, (cuuint32_t)BN};
+  const cuuint32_t estr[2] = {1u, 1u};
+  return r3_get_encode()(map, dt, 2, const_cast<void*>(w), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <class F, int W, int VST, int WST>
+static int launch_conv3s2(const serl_conv3x3s2_res_desc* d, cudaStream_t st) {
+  using Gm = R3Geom<W>;
+  constexpr int IPU = 2 * Gm::G / Gm::TPI;
+  constexpr size_t smem = (size_t)VST * 2 * (Gm::TR + 1) * Gm::ROWB + (size_t)WST * 128 * 128 + 2 * 2 * 128 * 128 + 2 * 128 * 8 + 2 * IPU * 32 * 2 +
+                          8 * (2 * VST + 2 * WST + 8) + 64 + 1024;
+  static_assert(smem <= 232448, "conv3x3s2_res_kernel: shared memory budget exceeded");
+  auto kern = conv3x3s2_res_kernel<F, W, VST, WST>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv3x3s2_res)");
+    configured = true;
+  }
+  if (!r3_get_encode()) { set_last_error("serl_conv3x3s2_res_h16: cuTensorMapEncodeTiled unavailable"); return SERL_ERR_CUDA; }
+  const CUtensorMapDataType dt = d->fmt == SERL_FMT_FP16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap xmap, wmap, pmap, omap, rmap;
+  bool good = r3_act_map_s2(&xmap, dt, d->x, d->N, 2 * W, 2 * W, d->Ci, Gm::G, W, Gm::TR + 1);
+  good = good && r3_w_map(&wmap, dt, d->w, 9 * d->Ci, d->Co, 128) && r3_w_map(&pmap, dt, d->w_proj, d->Ci, d->Co, 128);
+  good = good && r3_act_map(&omap, dt, d->y, d->N, W, W, d->Co, Gm::G, Gm::TR) && r3_act_map(&rmap, dt, d->r, d->N, W, W, d->Co, Gm::G, Gm::TR);
+  if (!good) { set_last_error("serl_conv3x3s2_res_h16: cuTensorMapEncodeTiled failed"); return SERL_ERR_CUDA; }
+  C3sArgs a{};
+  a.gamma0 = d->gamma; a.beta0 = d->beta; a.gammaP = d->gamma_proj; a.betaP = d->beta_proj; a.error = d->error;
+  a.N = d->N; a.Ci = d->Ci; a.Co = d->Co; a.cblocks = d->Ci / 64; a.n_tiles_n = d->Co / 128;
+  a.n_items = ((d->N + IPU - 1) / IPU) * a.n_tiles_n; a.eps = d->eps;
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int grid = a.n_items < sms ? a.n_items : sms;
+  kern<<<grid, R3_THREADS, smem, st>>>(xmap, wmap, pmap, omap, rmap, a);
+  return check_launch("conv3x3s2_res_kernel");
+}
+
 }  // namespace serl
 
 using namespace serl;
+
+extern "C" int serl_conv3x3s2_res_h16(const serl_conv3x3s2_res_desc* d, void* stream) {
+  if (!d || !d->x || !d->w || !d->w_proj || !d->y || !d->r || !d->gamma || !d->beta || !d->gamma_proj || !d->beta_proj || !d->error || d->N < 1) {
+    set_last_error("serl_conv3x3s2_res_h16: invalid descriptor"); return SERL_ERR_INVALID;
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bool h = d->fmt == SERL_FMT_FP16;
+  if (d->Co != 2 * d->Ci) { set_last_error("serl_conv3x3s2_res_h16: Co == 2 Ci only (ResNet-10 stage heads)"); return SERL_ERR_UNSUPPORTED; }
+  if (d->Wo == 16 && d->Co == 128) return h ? launch_conv3s2<R3Fp16, 16, 2, 4>(d, st) : launch_conv3s2<R3Bf16, 16, 2, 4>(d, st);
+  if (d->Wo == 8 && d->Co == 256) return h ? launch_conv3s2<R3Fp16, 8, 2, 4>(d, st) : launch_conv3s2<R3Bf16, 8, 2, 4>(d, st);
+  if (d->Wo == 4 && d->Co == 512) return h ? launch_conv3s2<R3Fp16, 4, 2, 4>(d, st) : launch_conv3s2<R3Bf16, 4, 2, 4>(d, st);
+  set_last_error("serl_conv3x3s2_res_h16: unsupported shape (Wo=%d, Ci=%d, Co=%d)", d->Wo, d->Ci, d->Co);
+  return SERL_ERR_UNSUPPORTED;
+}
 
 extern "C" int serl_conv3x3_res_h16(const serl_conv3x3_res_desc* d, void* stream) {
   if (!d || !d->x || !d->w || !d->gamma || !d->beta || !d->error || (!d->y && !d->out_f32) || d->N < 1) {

@@ -40,6 +40,10 @@ GN_EPS = 1e-5
 # (no affine_relu after ResNetBlock_0/Conv_0, no block_combine after any Conv_1).  SERL_RES_CONV=0 selects round 1's path.
 USE_RES_CONV = os.environ.get("SERL_RES_CONV", "0") != "0"
 
+# Head of ResNetBlock_1..3 (stride-2 3x3 conv + GN + ReLU AND the 1x1 stride-2 projection + GN) in one kernel
+# (conv3x3s2_res_kernel): no separate projection conv, no affine_relu pass.  Needs USE_RES_CONV.  SERL_RES_S2=0 keeps round 1's kernels.
+USE_RES_S2 = os.environ.get("SERL_RES_S2", "0") != "0"
+
 # The 1x1 / stride-2 projection conv of a block only depends on the block input: run it on a side stream next to the
 # conv -> GroupNorm+ReLU -> conv chain (joined before the residual add).
 USE_PROJ_SIDE_STREAM = os.environ.get("SERL_PROJ_SIDE", "1") != "0"
@@ -114,6 +118,16 @@ def _conv_res(plan, x, w, y, gamma, beta, N, HW_, C_, *, res=None, res_stats=Non
     L.call("serl_conv3x3_res_h16", C.byref(d), _s())
 
 
+def _conv_s2_res(plan, x, w, w_proj, y, r, gamma, beta, gamma_p, beta_p, N, Wo, Ci, Co):
+    """y = relu(GN(conv3x3 s2 (x))), r = GN(conv1x1 s2 (x)) in one launch (serl_conv3x3s2_res_h16)."""
+    d = L.Conv3x3S2ResDesc()
+    d.x, d.w, d.w_proj, d.y, d.r = x.data_ptr(), w.data_ptr(), w_proj.data_ptr(), y.data_ptr(), r.data_ptr()
+    d.gamma, d.beta, d.gamma_proj, d.beta_proj = gamma.data_ptr(), beta.data_ptr(), gamma_p.data_ptr(), beta_p.data_ptr()
+    d.error = plan.error.data_ptr()
+    d.N, d.Wo, d.Ci, d.Co, d.fmt, d.eps = N, Wo, Ci, Co, plan.fmt, GN_EPS
+    L.call("serl_conv3x3s2_res_h16", C.byref(d), _s())
+
+
 def _finalize(stats, gamma, beta, ab, N, Cc, HW):
     a, b = ab[0].view(-1)[:N * Cc].view(N, Cc), ab[1].view(-1)[:N * Cc].view(N, Cc)
     L.call("serl_gn_finalize", stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(), a.data_ptr(), b.data_ptr(), N, Cc, HW, 1e-5, _s())
@@ -181,13 +195,21 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
         proj = stride != 1 or cin != f
         last = i == len(STAGES) - 1
         side = engine.side[1] if (proj and USE_PROJ_SIDE_STREAM and hasattr(engine, "side")) else None
+        res_ok = USE_RES_CONV and USE_FUSED_GN and {32: 64, 16: 128, 8: 256, 4: 512}.get(so) == f
+        if res_ok and USE_RES_S2 and proj and stride == 2 and f == 2 * cin:
+            gP, bP = w[f"{b}/norm_proj/scale"], w[f"{b}/norm_proj/bias"]
+            _conv_s2_res(p, x, wp[f"{b}/Conv_0/kernel"], wp[f"{b}/conv_proj/kernel"], yA, yP, gA, bA, gP, bP, N, so, cin, f)
+            _conv_res(p, yA, wp[f"{b}/Conv_1/kernel"], None if last else out, gB, bB, N, so, f, res=yP, relu=True, out_f32=feats if last else None)
+            engine.launches += 2
+            free, cur = [cur, iy, iy2, ir], io
+            x, s, cin = out, so, f
+            continue
         if proj:
             gP, bP = w[f"{b}/norm_proj/scale"], w[f"{b}/norm_proj/bias"]
             if side is not None:
                 side.fork()
                 with side:
                     _conv(p, x, wp[f"{b}/conv_proj/kernel"], yP, sP, N, s, s, cin, so, so, f, 1, stride, 0)
-        res_ok = USE_RES_CONV and USE_FUSED_GN and {32: 64, 16: 128, 8: 256, 4: 512}.get(so) == f
         if res_ok and stride == 1 and cin == f:
             # ResNetBlock_0: both convs are stride-1 3x3: conv -> GN -> ReLU in one kernel (activated output, no affine_relu pass)
             _conv_res(p, x, wp[f"{b}/Conv_0/kernel"], yA, gA, bA, N, so, f, relu=True)

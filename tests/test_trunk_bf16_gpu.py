@@ -337,15 +337,49 @@ def test_trunk_res_conv_path_matches_round1_path():
     class Cfg: precision = "fp16"
 
     outs = {}
-    for flag in (False, True):
-        eng = _Eng()
-        eng.cfg, eng.trunk = Cfg, {"cam": w}
-        T.USE_RES_CONV = flag
-        feats = torch.empty(N, 4, 4, 512, device="cuda")
-        T.forward(eng, "cam", pix, feats)
-        torch.cuda.synchronize()
-        T.check_error(eng)
-        outs[flag] = feats.cpu().numpy()
-    T.USE_RES_CONV = False
-    assert np.isfinite(outs[True]).all()
-    assert rel_err(outs[True], outs[False]) < 3e-3
+    keep = (T.USE_RES_CONV, T.USE_RES_S2)
+    try:
+        for flags in ((False, False), (True, False), (True, True)):
+            eng = _Eng()
+            eng.cfg, eng.trunk = Cfg, {"cam": w}
+            T.USE_RES_CONV, T.USE_RES_S2 = flags
+            feats = torch.empty(N, 4, 4, 512, device="cuda")
+            T.forward(eng, "cam", pix, feats)
+            torch.cuda.synchronize()
+            T.check_error(eng)
+            outs[flags] = feats.cpu().numpy()
+    finally:
+        T.USE_RES_CONV, T.USE_RES_S2 = keep
+    for flags in ((True, False), (True, True)):
+        assert np.isfinite(outs[flags]).all(), flags
+        assert rel_err(outs[flags], outs[(False, False)]) < 3e-3, flags
+
+
+@pytest.mark.parametrize("prec", ["fp16", "bf16"])
+@pytest.mark.parametrize("Wo,Co,N", [(16, 128, 3), (16, 128, 150), (8, 256, 5), (8, 256, 600), (4, 512, 19), (4, 512, 512)])
+def test_conv3x3s2_proj_res_matches_float64_block_head(Wo, Co, N, prec):
+    """Head of ResNetBlock_1..3 in one kernel: y = relu(GN(conv3x3 stride 2, SAME = pad low 0 / high 1)), r = GN(conv1x1 stride 2),
+    both from the same block input, vs float64 on the 16-bit operands (reference algebra vision/resnet_v1.py:139-154)."""
+    from oracle.drq import conv_nhwc
+    from serl_b200 import trunk_bf16 as T
+    if prec == "bf16" and N > 100:
+        pytest.skip("large-N variants run once (fp16)")
+    rng = np.random.default_rng(Wo * 100 + N)
+    dt, Ci, Wi = DT[prec], Co // 2, 2 * Wo
+    x = _bf(np.abs(rng.standard_normal((N, Wi, Wi, Ci))).astype(np.float32), prec)
+    w = (rng.standard_normal((3, 3, Ci, Co)) * np.sqrt(2.0 / (9 * Ci))).astype(np.float32)
+    wpj = (rng.standard_normal((1, 1, Ci, Co)) * np.sqrt(2.0 / Ci)).astype(np.float32)
+    g0, b0, gp, bp = [(s + 0.3 * rng.standard_normal(Co)).astype(np.float32) for s in (1, 0, 1, 0)]
+    t64 = lambda v: torch.as_tensor(v).double()
+    ref_y = _gn64(conv_nhwc(x.double(), _bf(w, prec).double(), 2, 0, 1), t64(g0), t64(b0)).relu()
+    ref_r = _gn64(conv_nhwc(x.double(), _bf(wpj, prec).double(), 2, 0, 0), t64(gp), t64(bp))
+    plan = T._Plan(max(N, 1), 128, "cuda", prec)
+    cu = lambda t: torch.as_tensor(t).cuda().contiguous()
+    y = torch.full((N, Wo, Wo, Co), float("nan"), dtype=dt, device="cuda")
+    r = torch.full((N, Wo, Wo, Co), float("nan"), dtype=dt, device="cuda")
+    T._conv_s2_res(plan, cu(x), T.pack_conv_weight(cu(w), dt), T.pack_conv_weight(cu(wpj), dt), y, r, cu(g0), cu(b0), cu(gp), cu(bp), N, Wo, Ci, Co)
+    torch.cuda.synchronize()
+    assert int(plan.error.item()) == 0, f"pipeline barrier timeout (flags {int(plan.error.item())})"
+    gy, gr = y.float().cpu().numpy(), r.float().cpu().numpy()
+    assert np.isfinite(gy).all() and np.isfinite(gr).all()
+    assert rel_err(gy, ref_y.numpy()) < OUT_TOL[prec] and rel_err(gr, ref_r.numpy()) < OUT_TOL[prec]
