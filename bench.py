@@ -348,21 +348,21 @@ def run_b200(args):
     clk = clocks.stop(w0, time.time())
     agent.check_status()
 
-    # ---- per-kernel-group durations: the same steps launched eagerly with CUDA events around the sections -----------
-    trunk_ev = []
-    orig_features, orig_load = agent._features, agent._load_batch
-
-    def timed_features(e):
-        a, b = ev(), ev(); a.record(); orig_features(e); b.record(); trunk_ev.append((a, b))
-
+    # ---- per-section durations: the same steps launched EAGERLY with CUDA events around the sections (one rank's timeline;
+    # eager launches add host gaps inside the short sections, so these are upper bounds of what the graph replay spends) ------
+    orig_load = agent._load_batch
     agent.use_cuda_graphs = False
-    agent._features = timed_features
-    for _ in range(min(args.steps, 20)):
+    agent.section_events = []
+    n_eager = min(args.steps, 20)
+    for _ in range(n_eager):
         agent.update_critics(w.next_batch())
     barrier()
-    agent._features = orig_features
     agent.use_cuda_graphs = True
-    trunk_ms = sum(a.elapsed_time(b) for a, b in trunk_ev) / len(trunk_ev)
+    sec = {}
+    for name, a_, b_ in agent.section_events:
+        sec[name] = sec.get(name, 0.0) + a_.elapsed_time(b_) / n_eager
+    agent.section_events = None
+    trunk_ms = sec["trunk"]
     # the sampler kernel(s) of a step are ~10x shorter than a host launch: time them as 20 batch loads captured in one CUDA
     # graph, replayed back to back (each launch draws a fresh batch: the device step counter advances inside the graph)
     handle = w.next_batch()
@@ -391,10 +391,12 @@ def run_b200(args):
         same = torch.tensor([int(torch.equal(mine, ref))], device="cuda")
         dist.all_reduce(same, op=dist.ReduceOp.MIN)
         replicas_identical = bool(same.item())
-    tmax = torch.tensor([ms, e2e_s * 1e3, ms_sus, trunk_ms, samp_ms], device="cuda", dtype=torch.float64)
+    names = sorted(sec)
+    tmax = torch.tensor([ms, e2e_s * 1e3, ms_sus, trunk_ms, samp_ms] + [sec[k] for k in names], device="cuda", dtype=torch.float64)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms, e2e_ms, ms_sus, trunk_ms, samp_ms = tmax.tolist()
+    ms, e2e_ms, ms_sus, trunk_ms, samp_ms = tmax.tolist()[:5]
+    sec = {k: v for k, v in zip(names, tmax.tolist()[5:])}
 
     def shutdown():
         # captured NCCL kernels inside live CUDA graphs can block process-group teardown: drop the graphs first, and never
@@ -423,6 +425,8 @@ def run_b200(args):
             "sustained": {"value": n_sus / (ms_sus / 1e3), "unit": "steps/s", "steps": n_sus, "seconds": ms_sus / 1e3,
                           "note": "same loop, run for >= --sustain-s seconds right after the K timed steps; the clock samples cover both"},
             "gpu_launches": launches, "cuda_graph": True, "replicas_identical": replicas_identical,
+            "sections_ms": {**{k: round(v, 4) for k, v in sec.items()},
+                            "note": "eagerly launched steps, CUDA events per section, mean over steps, max over ranks; heads = encoder heads + critic / policy MLPs + losses + backward"},
             "roofline": {"kernel": TRUNK_KERNELS[args.precision != "fp32"], "bound": "tensor",
                          "achieved": trunk_tflops, "peak": pk["tensor"], "unit": "TFLOP/s", "frac": trunk_tflops / pk["tensor"],
                          "traffic": trunk_traffic(args), "traffic_source": "profiles/trunk_traffic.json, regenerated from the committed ncu launch list by scripts/trunk_traffic.py",

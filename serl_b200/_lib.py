@@ -87,6 +87,7 @@ _PROTOS = {
     "serl_replay_set_valid": [vp, vp, vp, C.c_int, vp],
     "serl_replay_commit": [vp, vp, vp, C.c_int, vp, C.c_int, vp],
     "serl_counter_add": [vp, u64, vp],
+    "serl_set_pdl": [C.c_int],
     "serl_rng_schedule": [vp, vp, C.c_int, C.c_int, vp],
     "serl_normal_fill": [vp, vp, C.c_int, vp],
     "serl_dropout_mask_fill": [vp, u32, f32, vp, C.c_int, vp],

@@ -62,8 +62,10 @@ class DrQAgent(SACAgent):
         def body(batch, graph_mode):
             ops.rng_schedule(self.state._rng, self._keys, True, True)    # split(rng,3) then update's split(rng,4)
             eng.launches += 1
-            self._load_batch(eng, batch, augment=True, keys=self._keys, graph_mode=graph_mode)
-            self._features(eng)
+            with self._section("sample_crop"):
+                self._load_batch(eng, batch, augment=True, keys=self._keys, graph_mode=graph_mode)
+            with self._section("trunk"):
+                self._features(eng)
             self._update_on_engine(eng, nets, pmap_axis, schedule_keys=False, want_info=False)
 
         self._run_step(self._graph_key(("update_critics", pmap_axis), batch), batch, body)

@@ -48,6 +48,7 @@ class SACAgent:
         self.data_parallel = False          # set True to all-reduce(mean) gradients + infos (reference: pmap_axis)
         self.explicit_randomness = None     # tests: dict with eps / dropout / subsample (and crop offsets)
         self.use_cuda_graphs = True         # replay the whole step as one CUDA graph from its 3rd identical call on
+        self.section_events = None          # bench: list collecting (name, start event, end event) of eagerly launched steps
         self._graphs = {}
         self._graphs_version = store.version   # captured graphs bake parameter-derived state (packed trunk weights, stem sign mask)
         self._launch_adj = 0                # graph capture / replay correction of the library's launch counter
@@ -258,6 +259,23 @@ class SACAgent:
         return BatchHandle([dict(ring=ring, seed=0, step=0, batch=B, indx=idx)], True)
 
     # ---- update (sac.py:243-299) ------------------------------------------------------------------------
+    def _section(self, name):
+        """Context manager timing one section of an EAGER step with CUDA events (bench.py's per-section timeline); no-op otherwise."""
+        import contextlib
+        if self.section_events is None or torch.cuda.is_current_stream_capturing():
+            return contextlib.nullcontext()
+
+        @contextlib.contextmanager
+        def cm():
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            try:
+                yield
+            finally:
+                b.record()
+                self.section_events.append((name, a, b))
+        return cm()
+
     def _features(self, eng: Engine):
         if self._cfg.pixel:
             for cam in self._cfg.cams:
@@ -284,16 +302,19 @@ class SACAgent:
         dp = self._dp(pmap_axis)
         gscale = 1.0 / _dist().get_world_size() if dp else 1.0
         at = "actor" in nets or "temperature" in nets
-        if "critic" in nets:
-            eng.critic_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl)
-        if at:
-            # any subset is legal (sac.py:270-277): a network that is not updated contributes a zero gradient, its tx still ticks
-            eng.actor_temp_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl, do_actor="actor" in nets,
-                                          do_temperature="temperature" in nets)
+        with self._section("heads"):
+            if "critic" in nets:
+                eng.critic_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl)
+            if at:
+                # any subset is legal (sac.py:270-277): a network that is not updated contributes a zero gradient, its tx still ticks
+                eng.actor_temp_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl, do_actor="actor" in nets,
+                                              do_temperature="temperature" in nets)
         if dp and nets:
             # [group 0 | critic infos] and/or [actor, temperature infos | groups 1, 2 | aux]: one contiguous range either way
-            self._allreduce(0 if "critic" in nets else st.info_off + 4, st.n if at else st.info_off + 4)
-        eng.optimizer_step([int("critic" in nets), int("actor" in nets), int("temperature" in nets)], polyak="critic" in nets)
+            with self._section("allreduce"):
+                self._allreduce(0 if "critic" in nets else st.info_off + 4, st.n if at else st.info_off + 4)
+        with self._section("adam_polyak"):
+            eng.optimizer_step([int("critic" in nets), int("actor" in nets), int("temperature" in nets)], polyak="critic" in nets)
         self.state.step += 1
         return self._info(eng, nets) if want_info else None
 

@@ -1,6 +1,7 @@
 // Library-level entry points: error reporting, version, device queries.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include <atomic>
 #include "common.cuh"
@@ -32,11 +33,18 @@ int check_launch(const char* what) {
 }
 unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+static int g_pdl = -1;
+bool pdl_enabled() {
+  if (g_pdl < 0) { const char* e = getenv("SERL_PDL"); g_pdl = (e && atoi(e) != 0) ? 1 : 0; }
+  return g_pdl != 0;
+}
+
 }  // namespace serl
 
 extern "C" const char* serl_last_error(void) { return serl::g_err; }
 extern "C" int serl_version(void) { return 2; }
 extern "C" unsigned long long serl_launch_count(void) { return serl::launch_count(); }
+extern "C" int serl_set_pdl(int enabled) { serl::g_pdl = enabled ? 1 : 0; return SERL_OK; }
 extern "C" int serl_device_sm_count(int device) {
   int n = 0;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {

@@ -13,6 +13,36 @@ namespace serl {
 void set_last_error(const char* fmt, ...);
 int check_launch(const char* what);   // cudaGetLastError -> SERL_OK / SERL_ERR_CUDA (+ message)
 
+// ---------------------------------------------------------------------------------------------
+// Kernel launches + programmatic dependent launch (PDL).
+// A step is ~150 short kernels chained on <= 3 streams; between two dependent kernels the GPU normally idles for the launch
+// latency (~2-3 us, also inside a CUDA graph).  With SERL_PDL=1 every kernel is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization: its CTAs may become resident while the previous kernel of the stream is
+// still running, and `pdl_prologue()` (first statement of EVERY kernel) parks them on `griddepcontrol.wait` until that kernel
+// has completed and its writes are visible - so nothing is read or written early - and then lets the NEXT kernel start
+// launching (`griddepcontrol.launch_dependents`).  Without the launch attribute both instructions are no-ops.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+#endif
+bool pdl_enabled();                   // SERL_PDL environment switch (capi.cu)
+
+template <class... P, class... A>
+inline void launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  if (pdl_enabled()) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+  }
+  cudaLaunchKernelEx(&cfg, kern, static_cast<P>(args)...);          // errors are picked up by check_launch()
+}
+
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
 

@@ -133,6 +133,7 @@ template <class F, int W, int BN, int VST, int WST>
 __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
                                                                      const __grid_constant__ CUtensorMap rmap, const __grid_constant__ CUtensorMap omap,
                                                                      const C3rArgs a) {
+  pdl_prologue();
   using Gm = R3Geom<W>;
   constexpr int G = Gm::G, TPI = Gm::TPI, TR = Gm::TR, ROWB = Gm::ROWB, PATCH = Gm::PATCH, UT = Gm::UT, MT = Gm::MT, IPU = Gm::IPU;
   constexpr bool kResW = (BN == 64);                     // 64 -> 64 layers: whole 3x3 weight tensor resident (9 tiles of 8 KB)
@@ -497,6 +498,7 @@ template <class F, int W, int VST, int WST>
 __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3s2_res_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
                                                                        const __grid_constant__ CUtensorMap pmap, const __grid_constant__ CUtensorMap omap,
                                                                        const __grid_constant__ CUtensorMap rmap, const C3sArgs a) {
+  pdl_prologue();
   using Gm = R3Geom<W>;
   constexpr int BN = 128, G = Gm::G, TPI = Gm::TPI, TR = Gm::TR, ROWB = Gm::ROWB, UT = 2, MT = 2, IPU = UT * G / TPI;
   static_assert(Gm::UT == 2 && Gm::MT == 2, "stride-2 kernel: 16x16 / 8x8 / 4x4 output maps");
@@ -849,7 +851,7 @@ static int launch_conv3r(const serl_conv3x3_res_desc* d, cudaStream_t st) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const int grid = a.n_items < sms ? a.n_items : sms;
-  kern<<<grid, R3_THREADS, smem, st>>>(xmap, wmap, rmap, omap, a);
+  launch_k(kern, grid, R3_THREADS, smem, st, xmap, wmap, rmap, omap, a);
   return check_launch("conv3x3_res_kernel");
 }
 
@@ -899,7 +901,7 @@ static int launch_conv3s2(const serl_conv3x3s2_res_desc* d, cudaStream_t st) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const int grid = a.n_items < sms ? a.n_items : sms;
-  kern<<<grid, R3_THREADS, smem, st>>>(xmap, wmap, pmap, omap, rmap, a);
+  launch_k(kern, grid, R3_THREADS, smem, st, xmap, wmap, pmap, omap, rmap, a);
   return check_launch("conv3x3s2_res_kernel");
 }
 

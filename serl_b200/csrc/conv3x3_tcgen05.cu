@@ -110,6 +110,7 @@ constexpr int C3_EPI_STAGE = 4 * 32 * 128;             // 4 epilogue warps x 32 
 
 template <class F, int BN, int BSTAGES, int PSTAGES, bool kResidentB, bool kCoalEpi = false>
 __global__ void __launch_bounds__(C3_THREADS, kResidentB ? 1 : 2) conv3x3_tc_kernel(const __grid_constant__ CUtensorMap wmap, const Conv3Args a) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_STAGE = BN * 128;
@@ -377,7 +378,7 @@ static int launch_conv3(const CUtensorMap& map, const Conv3Args& a, cudaStream_t
   const long long tiles = ((a.Q + 127) / 128) * (a.Co / BN);
   const long long slots = (kResidentB ? 1ll : 2ll) * sms;               // persistent CTAs per device
   const int grid = (int)(tiles < slots ? tiles : slots);
-  kern<<<grid, C3_THREADS, smem, st>>>(map, a);
+  launch_k(kern, grid, C3_THREADS, smem, st, map, a);
   return check_launch("conv3x3_tc_kernel");
 }
 

@@ -136,6 +136,7 @@ constexpr int TC_EPI_STAGE = 4 * 32 * 64;
 
 template <class F, int BN, int STAGES, bool kStem, bool kAffine, bool kCoalEpi = false>
 __global__ void __launch_bounds__(TC_THREADS, 2) conv_tc_kernel(const __grid_constant__ CUtensorMap wmap, const ConvTcArgs a) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int B_STAGE = BN * TC_BK * 2;
@@ -370,6 +371,7 @@ __device__ inline void st_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t by
 
 template <class F, bool kPool>
 __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_constant__ CUtensorMap wmap, const ConvTcArgs a) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int BN = 64, W_TILE = BN * 128;                     // 8 KiB weight tile per k-block
@@ -627,6 +629,7 @@ __device__ inline int s2_sw(int m) { return ((m >> 1) ^ (m >> 5)) & 3; }        
 template <class F>
 __global__ void __launch_bounds__(TC_THREADS, 1) stem2_tc_kernel(const __grid_constant__ CUtensorMap wmap, const __grid_constant__ CUtensorMap xmap,
                                                                   const ConvTcArgs a) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int BN = 64, W_TILE = BN * 128;
@@ -801,6 +804,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem2_tc_kernel(const __grid_co
 // ---- stem input: uint8 crops -> normalised 16-bit, 2x2 space-to-depth, zero padded: (N,67,67,16) [12 real + 4 zero ch] ----
 template <class F>
 __global__ void stem_prep_kernel(const uint8_t* __restrict__ x, uint16_t* __restrict__ xs, int N, int H, int W, int Hs, int Ws) {
+  pdl_prologue();
   // a byte has 256 values: normalise each (channel, value) pair once per block (true fp32 divisions, as the fp32 build and
   // the oracle do) and look the 16-bit result up afterwards
   __shared__ uint16_t lut[3][256];
@@ -867,6 +871,7 @@ __device__ inline void gn_load8(const GnSrc& g, int n, int C, int c0, float (&a)
 // ---- GroupNorm finalize: sums -> per-(image, channel) affine  y = a*x + b --------------------------------
 __global__ void gn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float* __restrict__ oa, float* __restrict__ ob, int N, int C, int Cg, float count, float eps) {
+  pdl_prologue();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N * C) return;
   const int n = e / C, c = e - n * C, g = c / Cg;
@@ -880,6 +885,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, const float*
 // ---- GroupNorm + ReLU applied in place on the raw 16-bit conv output: x <- relu(a*x + b); thread per 8 channels ----
 template <class F>
 __global__ void affine_relu_kernel(uint16_t* __restrict__ x, const GnSrc g, int N, int HW, int C) {
+  pdl_prologue();
   const int c8n = C >> 3;
   const size_t total = (size_t)N * HW * c8n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -898,6 +904,7 @@ __global__ void affine_relu_kernel(uint16_t* __restrict__ x, const GnSrc g, int 
 template <class F>
 __global__ void maxpool_affine_kernel(const uint16_t* __restrict__ x, const float* __restrict__ ga, const float* __restrict__ gb,
                                      uint16_t* __restrict__ y, int N, int Hi, int Wi, int C, int Ho, int Wo) {
+  pdl_prologue();
   const int c8n = C >> 3;
   const size_t total = (size_t)N * Ho * Wo * c8n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -938,6 +945,7 @@ __global__ void maxpool_affine_kernel(const uint16_t* __restrict__ x, const floa
 template <class F>
 __global__ void pool_finish_kernel(const uint16_t* __restrict__ pooled, const uint16_t* __restrict__ side, const GnSrc g,
                                    uint16_t* __restrict__ y, int N) {
+  pdl_prologue();
   const size_t total = (size_t)N * 32 * 32 * 8;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int c8 = (int)(e & 7); size_t r = e >> 3;
@@ -959,6 +967,7 @@ __global__ void pool_finish_kernel(const uint16_t* __restrict__ pooled, const ui
 template <class F>
 __global__ void block_combine_kernel(const uint16_t* __restrict__ y2, const GnSrc g2, const uint16_t* __restrict__ res, const GnSrc gr, int ar,
                                      uint16_t* __restrict__ out_bf16, float* __restrict__ out_f32, int N, int HW, int C) {
+  pdl_prologue();
   const int c8n = C >> 3;
   const size_t total = (size_t)N * HW * c8n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -1030,7 +1039,7 @@ static int launch_conv_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const int tiles = ceil_div(a.M, TC_BM) * (a.Co / BN);
   const int grid = tiles < 2 * sms ? tiles : 2 * sms;                 // persistent: 2 CTAs per SM walk the tile list
-  kern<<<grid, TC_THREADS, smem, st>>>(map, a);
+  launch_k(kern, grid, TC_THREADS, smem, st, map, a);
   return check_launch("conv_tc_kernel");
 }
 
@@ -1063,7 +1072,7 @@ static int launch_stem_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const int work = kPool ? a.M / TC_BM / 8 : a.M / TC_BM;      // units of 8 tiles when the pool is fused
   const int grid = work < 2 * sms ? work : 2 * sms;
-  kern<<<grid, TC_THREADS, smem, st>>>(map, a);
+  launch_k(kern, grid, TC_THREADS, smem, st, map, a);
   return check_launch("stem_tc_kernel");
 }
 
@@ -1110,7 +1119,7 @@ static int launch_stem2_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const int units = a.N * 4;
   const int grid = units < sms ? units : sms;                   // persistent, one CTA per SM
-  kern<<<grid, TC_THREADS, smem, st>>>(wmap, xmap, a);
+  launch_k(kern, grid, TC_THREADS, smem, st, wmap, xmap, a);
   return check_launch("stem2_tc_kernel");
 }
 
@@ -1135,8 +1144,8 @@ extern "C" int serl_trunk_stem_prep_h16(const uint8_t* x, void* xs, int N, int H
   const int Hs = H / 2 + 3, Ws = W / 2 + 3;
   size_t total = (size_t)N * Hs * Ws;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  if (fmt == SERL_FMT_FP16) stem_prep_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(x, static_cast<uint16_t*>(xs), N, H, W, Hs, Ws);
-  else stem_prep_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(x, static_cast<uint16_t*>(xs), N, H, W, Hs, Ws);
+  if (fmt == SERL_FMT_FP16) launch_k(stem_prep_kernel<Fp16>, blocks, 256, 0, ST(stream), x, static_cast<uint16_t*>(xs), N, H, W, Hs, Ws);
+  else launch_k(stem_prep_kernel<Bf16>, blocks, 256, 0, ST(stream), x, static_cast<uint16_t*>(xs), N, H, W, Hs, Ws);
   return check_launch("stem_prep_kernel");
 }
 
@@ -1188,9 +1197,9 @@ static int launch_pool_finish(const void* pooled, const void* side, const GnSrc&
   const size_t total = (size_t)N * 32 * 32 * 8;
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
   if (fmt == SERL_FMT_FP16)
-    pool_finish_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(static_cast<const uint16_t*>(pooled), static_cast<const uint16_t*>(side), g, static_cast<uint16_t*>(y), N);
+    launch_k(pool_finish_kernel<Fp16>, blocks, 256, 0, ST(stream), static_cast<const uint16_t*>(pooled), static_cast<const uint16_t*>(side), g, static_cast<uint16_t*>(y), N);
   else
-    pool_finish_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(static_cast<const uint16_t*>(pooled), static_cast<const uint16_t*>(side), g, static_cast<uint16_t*>(y), N);
+    launch_k(pool_finish_kernel<Bf16>, blocks, 256, 0, ST(stream), static_cast<const uint16_t*>(pooled), static_cast<const uint16_t*>(side), g, static_cast<uint16_t*>(y), N);
   return check_launch("pool_finish_kernel");
 }
 extern "C" int serl_pool_finish_h16(const void* pooled, const void* side, const float* a, const float* b, void* y, int N, int fmt, void* stream) {
@@ -1204,15 +1213,15 @@ extern "C" int serl_pool_finish_gn_h16(const void* pooled, const void* side, con
 extern "C" int serl_gn_finalize(const float* stats, const float* gamma, const float* beta, float* out_a, float* out_b, int N, int C,
                                 int HW, float eps, void* stream) {
   const int Cg = C / 4;
-  gn_finalize_kernel<<<ceil_div(N * C, 256), 256, 0, ST(stream)>>>(stats, gamma, beta, out_a, out_b, N, C, Cg, (float)HW * (float)Cg, eps);
+  launch_k(gn_finalize_kernel, ceil_div(N * C, 256), 256, 0, ST(stream), stats, gamma, beta, out_a, out_b, N, C, Cg, (float)HW * (float)Cg, eps);
   return check_launch("gn_finalize_kernel");
 }
 
 static int launch_affine_relu(void* x, const GnSrc& g, int N, int HW, int C, int fmt, void* stream) {
   size_t total = (size_t)N * HW * (C / 8);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  if (fmt == SERL_FMT_FP16) affine_relu_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(static_cast<uint16_t*>(x), g, N, HW, C);
-  else affine_relu_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(static_cast<uint16_t*>(x), g, N, HW, C);
+  if (fmt == SERL_FMT_FP16) launch_k(affine_relu_kernel<Fp16>, blocks, 256, 0, ST(stream), static_cast<uint16_t*>(x), g, N, HW, C);
+  else launch_k(affine_relu_kernel<Bf16>, blocks, 256, 0, ST(stream), static_cast<uint16_t*>(x), g, N, HW, C);
   return check_launch("affine_relu_kernel");
 }
 extern "C" int serl_affine_relu_h16(void* x, const float* a, const float* b, int N, int HW, int C, int fmt, void* stream) {
@@ -1228,8 +1237,8 @@ extern "C" int serl_maxpool_affine_h16(const void* x, const float* a, const floa
   size_t total = (size_t)N * Ho * Wo * (C / 8);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
   auto xi = static_cast<const uint16_t*>(x); auto yo = static_cast<uint16_t*>(y);
-  if (fmt == SERL_FMT_FP16) maxpool_affine_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(xi, a, b, yo, N, Hi, Wi, C, Ho, Wo);
-  else maxpool_affine_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(xi, a, b, yo, N, Hi, Wi, C, Ho, Wo);
+  if (fmt == SERL_FMT_FP16) launch_k(maxpool_affine_kernel<Fp16>, blocks, 256, 0, ST(stream), xi, a, b, yo, N, Hi, Wi, C, Ho, Wo);
+  else launch_k(maxpool_affine_kernel<Bf16>, blocks, 256, 0, ST(stream), xi, a, b, yo, N, Hi, Wi, C, Ho, Wo);
   return check_launch("maxpool_affine_kernel");
 }
 
@@ -1238,8 +1247,8 @@ static int launch_block_combine(const void* y2, const GnSrc& g2, const void* res
   size_t total = (size_t)N * HW * (C / 8);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
   auto yi = static_cast<const uint16_t*>(y2); auto ri = static_cast<const uint16_t*>(res); auto oo = static_cast<uint16_t*>(out_h16);
-  if (fmt == SERL_FMT_FP16) block_combine_kernel<Fp16><<<blocks, 256, 0, ST(stream)>>>(yi, g2, ri, gr, ar, oo, out_f32, N, HW, C);
-  else block_combine_kernel<Bf16><<<blocks, 256, 0, ST(stream)>>>(yi, g2, ri, gr, ar, oo, out_f32, N, HW, C);
+  if (fmt == SERL_FMT_FP16) launch_k(block_combine_kernel<Fp16>, blocks, 256, 0, ST(stream), yi, g2, ri, gr, ar, oo, out_f32, N, HW, C);
+  else launch_k(block_combine_kernel<Bf16>, blocks, 256, 0, ST(stream), yi, g2, ri, gr, ar, oo, out_f32, N, HW, C);
   return check_launch("block_combine_kernel");
 }
 extern "C" int serl_block_combine_h16(const void* y2, const float* a2, const float* b2, const void* res, const float* ar, const float* br,

@@ -16,6 +16,7 @@ struct GemmArgs {
 
 // C[zc](m,n) = sum_{parts} ws[part](m,n) + bias + (accumulate ? C : 0); parts of zc: reduce_z ? all Z*S : S.
 static __global__ void gemm_reduce_kernel(const GemmArgs g, int reduce_z) {
+  pdl_prologue();
   const int ZC = reduce_z ? 1 : g.Z;
   const size_t MN = (size_t)g.M * g.N, total = MN * ZC;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -35,7 +36,7 @@ static __global__ void gemm_reduce_kernel(const GemmArgs g, int reduce_z) {
 inline int launch_gemm_reduce(const GemmArgs& g, int reduce_z, cudaStream_t st) {
   size_t total = (size_t)g.M * g.N * (reduce_z ? 1 : g.Z);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
-  gemm_reduce_kernel<<<blocks, 256, 0, st>>>(g, reduce_z);
+  launch_k(gemm_reduce_kernel, blocks, 256, 0, st, g, reduce_z);
   return check_launch("gemm_reduce_kernel");
 }
 

@@ -21,6 +21,7 @@ constexpr int GSTAGES = 4;
 // 4-stage cp.async pipeline: these GEMMs are small (a few hundred CTAs of 64x64 tiles), so each CTA is bound by the
 // global->shared latency of its k-loop; with three k-blocks of loads in flight per CTA the loop runs at FMA speed.
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const GemmArgs g) {
+  pdl_prologue();
   __shared__ __align__(16) float As[GSTAGES][GK][GM + 4];
   __shared__ __align__(16) float Bs[GSTAGES][GK][GN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -142,7 +143,7 @@ extern "C" int serl_gemm_f32(const serl_gemm_desc* d, void* stream) {
   g.to_ws = (d->reduce_z || S > 1) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(ceil_div(d->M, GM), ceil_div(d->N, GN), d->Z * S);
-  gemm_f32_kernel<<<grid, 256, 0, st>>>(g);
+  launch_k(gemm_f32_kernel, grid, 256, 0, st, g);
   if (int e = check_launch("gemm_f32_kernel")) return e;
   if (g.to_ws) {
     return launch_gemm_reduce(g, d->reduce_z, st);

@@ -122,6 +122,7 @@ __device__ inline void t_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, ui
 }
 
 __global__ void __launch_bounds__(T_THREADS, 1) gemm_tf32x3_kernel(const GemmArgs g) {
+  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sOp = smem;                                     // 2 x [A_hi | A_lo | B_hi | B_lo]
@@ -314,7 +315,7 @@ extern "C" int serl_gemm_tf32x3(const serl_gemm_desc* d, void* stream) {
   g.to_ws = (d->reduce_z || S > 1) ? 1 : 0;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(ceil_div(d->M, TM), ceil_div(d->N, TN), d->Z * S);
-  gemm_tf32x3_kernel<<<grid, T_THREADS, T_SMEM, st>>>(g);
+  launch_k(gemm_tf32x3_kernel, grid, T_THREADS, T_SMEM, st, g);
   if (int e = check_launch("gemm_tf32x3_kernel")) return e;
   if (g.to_ws) return launch_gemm_reduce(g, d->reduce_z, st);
   return SERL_OK;

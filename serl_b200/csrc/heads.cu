@@ -16,6 +16,7 @@ namespace serl {
 __global__ void sle_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ kern,
                                const uint8_t* __restrict__ keep_mask, float keep, float* __restrict__ out,
                                int N, int P, int C, int ld_out) {
+  pdl_prologue();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= N * C) return;
   const int n = e / C, c = e - n * C;
@@ -42,6 +43,7 @@ __global__ void sle_fwd_kernel(const float* __restrict__ feat, const float* __re
 // ---- SLE kernel gradient: partial[chunk][p][c][f] = sum_{n in chunk} feat[n,p,c] * dout[n, c*8+f] ----
 __global__ void sle_bwd_partial_kernel(const float* __restrict__ feat, const float* __restrict__ dout,
                                        float* __restrict__ partial, int N, int P, int C, int ld_dout, int chunks) {
+  pdl_prologue();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P * C) return;
   const int p = e / C, c = e - p * C;
@@ -67,6 +69,7 @@ __global__ void sle_bwd_partial_kernel(const float* __restrict__ feat, const flo
 // block = 32 columns x 8 row-slices (coalesced 128-byte row reads), fixed-order tree over the slices: deterministic.
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, float* __restrict__ out, int groups, int rows, int D,
                                                      long long ld, int accumulate) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int cblocks = ceil_div(D, 32);
@@ -93,6 +96,7 @@ __global__ void ln_tanh_fwd_kernel(const float* __restrict__ z, int ld_z, const 
                                    const float* __restrict__ bias, int rows_per_group, int group_stride,
                                    float* __restrict__ out, int ld_out, float* __restrict__ xhat, float* __restrict__ rstd_out,
                                    int R, int D, float eps) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -120,6 +124,7 @@ __global__ void ln_tanh_bwd_kernel(const float* __restrict__ dt, int ld_dt, cons
                                    const float* __restrict__ xhat, const float* __restrict__ rstd,
                                    const float* __restrict__ scale, int rows_per_group, int group_stride,
                                    float* __restrict__ dz, float* __restrict__ dy_out, int R, int D) {
+  pdl_prologue();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= R) return;
@@ -143,6 +148,7 @@ __global__ void ln_tanh_bwd_kernel(const float* __restrict__ dt, int ld_dt, cons
 // ---- dscale[g][d] = sum_r dy*xhat ; dbias[g][d] = sum_r dy   (same 32 x 8 block shape as colsum) -----------------
 __global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restrict__ dy, const float* __restrict__ xhat,
                                                             float* __restrict__ dscale, float* __restrict__ dbias, int groups, int rows, int D) {
+  pdl_prologue();
   __shared__ float ra[8][33], rb[8][33];
   const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int cblocks = ceil_div(D, 32);
@@ -167,6 +173,7 @@ __global__ void __launch_bounds__(256) ln_param_grad_kernel(const float* __restr
 
 // ---- strided 2-D copy (concat helper) -------------------------------------------------------------
 __global__ void copy2d_kernel(const float* __restrict__ src, long long ld_src, float* __restrict__ dst, long long ld_dst, int R, int D) {
+  pdl_prologue();
   const size_t total = (size_t)R * D;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(e / D), d = (int)(e - (size_t)r * D);
@@ -182,7 +189,7 @@ using namespace serl;
 extern "C" int serl_sle_fwd(const float* feat, const float* kernel, const uint8_t* keep_mask, float keep, float* out,
                             int N, int P, int C, int F, int ld_out, void* stream) {
   if (F != 8 || (ld_out & 3)) { set_last_error("serl_sle_fwd: num_features must be 8 and ld_out %% 4 == 0"); return SERL_ERR_UNSUPPORTED; }
-  sle_fwd_kernel<<<ceil_div(N * C, 128), 128, 0, ST(stream)>>>(feat, kernel, keep_mask, keep, out, N, P, C, ld_out);
+  launch_k(sle_fwd_kernel, ceil_div(N * C, 128), 128, 0, ST(stream), feat, kernel, keep_mask, keep, out, N, P, C, ld_out);
   return check_launch("sle_fwd_kernel");
 }
 
@@ -194,22 +201,22 @@ extern "C" int serl_sle_bwd_kernel_grad(const float* feat, const float* dout, fl
   while (chunks > 1 && per * chunks > workspace_bytes) chunks >>= 1;
   if (!workspace || per * chunks > workspace_bytes) { set_last_error("serl_sle_bwd_kernel_grad: workspace too small (%zu needed)", per); return SERL_ERR_INVALID; }
   dim3 grid(ceil_div(P * C, 128), chunks);
-  sle_bwd_partial_kernel<<<grid, 128, 0, ST(stream)>>>(feat, dout, workspace, N, P, C, ld_dout, chunks);
+  launch_k(sle_bwd_partial_kernel, grid, 128, 0, ST(stream), feat, dout, workspace, N, P, C, ld_dout, chunks);
   if (int e = check_launch("sle_bwd_partial_kernel")) return e;
   const int D = P * C * F;
-  colsum_kernel<<<ceil_div(D, 32), 256, 0, ST(stream)>>>(workspace, dkernel, 1, chunks, D, D, 0);
+  launch_k(colsum_kernel, ceil_div(D, 32), 256, 0, ST(stream), workspace, dkernel, 1, chunks, D, D, 0);
   return check_launch("colsum_kernel(sle)");
 }
 
 extern "C" int serl_colsum_f32(const float* x, float* out, int groups, int rows, int D, long long ld, int accumulate, void* stream) {
-  colsum_kernel<<<groups * ceil_div(D, 32), 256, 0, ST(stream)>>>(x, out, groups, rows, D, ld, accumulate);
+  launch_k(colsum_kernel, groups * ceil_div(D, 32), 256, 0, ST(stream), x, out, groups, rows, D, ld, accumulate);
   return check_launch("colsum_kernel");
 }
 
 extern "C" int serl_layernorm_tanh_fwd(const float* z, int ld_z, const float* scale, const float* bias, int rows_per_group,
                                        int group_stride, float* out, int ld_out, float* xhat, float* rstd, int R, int D,
                                        float eps, void* stream) {
-  ln_tanh_fwd_kernel<<<ceil_div(R, 8), 256, 0, ST(stream)>>>(z, ld_z, scale, bias, rows_per_group, group_stride, out, ld_out,
+  launch_k(ln_tanh_fwd_kernel, ceil_div(R, 8), 256, 0, ST(stream), z, ld_z, scale, bias, rows_per_group, group_stride, out, ld_out,
                                                              xhat, rstd, R, D, eps);
   return check_launch("ln_tanh_fwd_kernel");
 }
@@ -217,12 +224,12 @@ extern "C" int serl_layernorm_tanh_fwd(const float* z, int ld_z, const float* sc
 extern "C" int serl_layernorm_tanh_bwd(const float* dt, int ld_dt, const float* t, int ld_t, const float* xhat, const float* rstd,
                                        const float* scale, int rows_per_group, int group_stride, float* dz, float* dy,
                                        float* dscale, float* dbias, int R, int D, void* stream) {
-  ln_tanh_bwd_kernel<<<ceil_div(R, 8), 256, 0, ST(stream)>>>(dt, ld_dt, t, ld_t, xhat, rstd, scale, rows_per_group, group_stride,
+  launch_k(ln_tanh_bwd_kernel, ceil_div(R, 8), 256, 0, ST(stream), dt, ld_dt, t, ld_t, xhat, rstd, scale, rows_per_group, group_stride,
                                                              dz, dy, R, D);
   if (int e = check_launch("ln_tanh_bwd_kernel")) return e;
   if (dscale && dbias) {
     const int groups = R / rows_per_group;
-    ln_param_grad_kernel<<<groups * ceil_div(D, 32), 256, 0, ST(stream)>>>(dy, xhat, dscale, dbias, groups, rows_per_group, D);
+    launch_k(ln_param_grad_kernel, groups * ceil_div(D, 32), 256, 0, ST(stream), dy, xhat, dscale, dbias, groups, rows_per_group, D);
     return check_launch("ln_param_grad_kernel");
   }
   return SERL_OK;
@@ -236,13 +243,13 @@ extern "C" int serl_layernorm_param_grad(const float* dy, const float* xhat, flo
     set_last_error("serl_layernorm_param_grad: invalid arguments"); return SERL_ERR_INVALID;
   }
   const int groups = R / rows_per_group;
-  ln_param_grad_kernel<<<groups * ceil_div(D, 32), 256, 0, ST(stream)>>>(dy, xhat, dscale, dbias, groups, rows_per_group, D);
+  launch_k(ln_param_grad_kernel, groups * ceil_div(D, 32), 256, 0, ST(stream), dy, xhat, dscale, dbias, groups, rows_per_group, D);
   return check_launch("ln_param_grad_kernel");
 }
 
 extern "C" int serl_copy2d_f32(const float* src, long long ld_src, float* dst, long long ld_dst, int R, int D, void* stream) {
   size_t total = (size_t)R * D;
   int blocks = (int)((total + 255) / 256); if (blocks > 1184) blocks = 1184; if (blocks < 1) blocks = 1;
-  copy2d_kernel<<<blocks, 256, 0, ST(stream)>>>(src, ld_src, dst, ld_dst, R, D);
+  launch_k(copy2d_kernel, blocks, 256, 0, ST(stream), src, ld_src, dst, ld_dst, R, D);
   return check_launch("copy2d_kernel");
 }

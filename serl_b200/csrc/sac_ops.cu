@@ -22,6 +22,7 @@ namespace serl {
 // Key schedule.  keys[] slots (2 words each): see SERL_KEY_* in serl_b200.h.
 // ---------------------------------------------------------------------------------------------
 __global__ void rng_schedule_kernel(uint32_t* rng, uint32_t* keys, int do_aug, int do_update) {
+  pdl_prologue();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   u32x2 r{rng[0], rng[1]};
   auto put = [&](int slot, u32x2 k) { keys[2 * slot] = k.x; keys[2 * slot + 1] = k.y; };
@@ -44,12 +45,14 @@ __global__ void rng_schedule_kernel(uint32_t* rng, uint32_t* keys, int do_aug, i
 }
 
 __global__ void normal_fill_kernel(const uint32_t* key, float* out, int n) {
+  pdl_prologue();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j < n) out[j] = bits_to_normal(jax_random_bits_at(u32x2{key[0], key[1]}, (uint32_t)n, (uint32_t)j));
 }
 
 // keep-mask of camera `fold`: bernoulli(fold_in(key, fold), keep, (n,)) (repo spec, oracle/drq.py::_dropout_masks)
 __global__ void dropout_mask_kernel(const uint32_t* key, uint32_t fold, float keep, uint8_t* mask, int n) {
+  pdl_prologue();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const u32x2 k = jax_fold_in(u32x2{key[0], key[1]}, fold);
@@ -59,6 +62,7 @@ __global__ void dropout_mask_kernel(const uint32_t* key, uint32_t fold, float ke
 // jax.random.randint(key, (n,), 0, ensemble) (sac.py:152-158): k1, k2 = split(key); element j combines word j of
 // random_bits(k1, (n,)) and random_bits(k2, (n,)) exactly like jax_randint2 does for n = 2.
 __global__ void subsample_idx_kernel(const uint32_t* key, int ensemble, int32_t* out, int n) {
+  pdl_prologue();
   const int j = threadIdx.x;
   if (blockIdx.x != 0 || j >= n) return;
   const u32x2 k{key[0], key[1]};
@@ -79,6 +83,7 @@ __global__ void tanh_gaussian_fwd_kernel(const float* __restrict__ mu, const flo
                                          const float* __restrict__ eps, float std_min, float std_max,
                                          float* __restrict__ act, int ld_act, float* __restrict__ logp,
                                          float* __restrict__ u_out, float* __restrict__ std_out, int B, int A, int deterministic) {
+  pdl_prologue();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float lp = 0.f;
@@ -112,6 +117,7 @@ __global__ void __launch_bounds__(1024) critic_loss_kernel(const float* __restri
                                                            int backup_entropy, float gamma, float grad_scale,
                                                            float* __restrict__ target_q, float* __restrict__ dq,
                                                            float* __restrict__ info, int E, int B) {
+  pdl_prologue();
   __shared__ float red[64];
   float sl = 0.f, sq = 0.f, sy = 0.f, dummy = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -153,6 +159,7 @@ __global__ void __launch_bounds__(1024) actor_loss_kernel(const float* __restric
                                                           float std_min, float std_max, float grad_scale,
                                                           float* __restrict__ dmu, float* __restrict__ dlogstd,
                                                           float* __restrict__ info, int E, int B, int A) {
+  pdl_prologue();
   __shared__ float red[64];
   const float alpha = softplusf(lagrange[0]);
   float sobj = 0.f, slp = 0.f;
@@ -177,6 +184,7 @@ __global__ void __launch_bounds__(1024) actor_loss_kernel(const float* __restric
 
 // dQ seed for the actor pass: every entry -grad_scale/(E*B)
 __global__ void fill_kernel(float* x, float v, int n) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = v;
 }
@@ -185,6 +193,7 @@ __global__ void fill_kernel(float* x, float v, int n) {
 __global__ void __launch_bounds__(1024) temperature_loss_kernel(const float* __restrict__ logp, const float* __restrict__ lagrange,
                                                                 float target_entropy, float grad_scale, float* __restrict__ dlagrange,
                                                                 float* __restrict__ info, int B) {
+  pdl_prologue();
   __shared__ float red[64];
   float s = 0.f, dummy = 0.f;
   for (int b = threadIdx.x; b < B; b += blockDim.x) s += logp[b];
@@ -234,6 +243,7 @@ __device__ inline float adam_update(const AdamArgs& a, int gid, float g, float* 
 }
 
 __global__ void adam_polyak_kernel(const AdamArgs a) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
   if (i >= a.seg_end[0] && i < a.seg_end[0] + a.gap) return;   // info scalars, not parameters
@@ -249,6 +259,7 @@ __global__ void adam_polyak_kernel(const AdamArgs a) {
 }
 
 __global__ void adam_tick_kernel(const AdamArgs a) {
+  pdl_prologue();
   const int gid = threadIdx.x;
   if (gid < 3) {
     const int cnt = a.counts[gid];
@@ -263,7 +274,7 @@ using namespace serl;
 #define ST(s) static_cast<cudaStream_t>(s)
 
 extern "C" int serl_rng_schedule(uint32_t* rng_state, uint32_t* keys, int do_aug, int do_update, void* stream) {
-  rng_schedule_kernel<<<1, 32, 0, ST(stream)>>>(rng_state, keys, do_aug, do_update);
+  launch_k(rng_schedule_kernel, 1, 32, 0, ST(stream), rng_state, keys, do_aug, do_update);
   return check_launch("rng_schedule_kernel");
 }
 
@@ -287,18 +298,18 @@ extern "C" int serl_host_rng_schedule(uint32_t* rng, uint32_t* keys, int do_aug,
 }
 
 extern "C" int serl_normal_fill(const uint32_t* key, float* out, int n, void* stream) {
-  normal_fill_kernel<<<ceil_div(n, 128), 128, 0, ST(stream)>>>(key, out, n);
+  launch_k(normal_fill_kernel, ceil_div(n, 128), 128, 0, ST(stream), key, out, n);
   return check_launch("normal_fill_kernel");
 }
 
 extern "C" int serl_dropout_mask_fill(const uint32_t* key, uint32_t fold, float keep, uint8_t* mask, int n, void* stream) {
-  dropout_mask_kernel<<<ceil_div(n, 256), 256, 0, ST(stream)>>>(key, fold, keep, mask, n);
+  launch_k(dropout_mask_kernel, ceil_div(n, 256), 256, 0, ST(stream), key, fold, keep, mask, n);
   return check_launch("dropout_mask_kernel");
 }
 
 extern "C" int serl_subsample_idx(const uint32_t* key, int ensemble, int32_t* out, int n, void* stream) {
   if (n < 1 || n > 32 || ensemble < 1 || ensemble > 65535) { set_last_error("serl_subsample_idx: need 1 <= n <= 32, 1 <= ensemble < 65536"); return SERL_ERR_INVALID; }
-  subsample_idx_kernel<<<1, 32, 0, ST(stream)>>>(key, ensemble, out, n);
+  launch_k(subsample_idx_kernel, 1, 32, 0, ST(stream), key, ensemble, out, n);
   return check_launch("subsample_idx_kernel");
 }
 
@@ -306,7 +317,7 @@ extern "C" int serl_tanh_gaussian_fwd(const float* mu, const float* log_std, con
                                       float* act, int ld_act, float* logp, float* u_out, float* std_out, int B, int A,
                                       int deterministic, void* stream) {
   if (!deterministic && !eps) { set_last_error("serl_tanh_gaussian_fwd: eps required unless deterministic"); return SERL_ERR_INVALID; }
-  tanh_gaussian_fwd_kernel<<<ceil_div(B, 128), 128, 0, ST(stream)>>>(mu, log_std, eps, std_min, std_max, act, ld_act, logp, u_out,
+  launch_k(tanh_gaussian_fwd_kernel, ceil_div(B, 128), 128, 0, ST(stream), mu, log_std, eps, std_min, std_max, act, ld_act, logp, u_out,
                                                                     std_out, B, A, deterministic);
   return check_launch("tanh_gaussian_fwd_kernel");
 }
@@ -314,13 +325,13 @@ extern "C" int serl_tanh_gaussian_fwd(const float* mu, const float* log_std, con
 extern "C" int serl_critic_loss(const float* q, const float* q_next, const int32_t* sub, int n_sub, const float* rewards,
                                 const float* masks, const float* logp_next, const float* lagrange, int backup_entropy,
                                 float gamma, float grad_scale, float* target_q, float* dq, float* info, int E, int B, void* stream) {
-  critic_loss_kernel<<<1, 1024, 0, ST(stream)>>>(q, q_next, sub, n_sub, rewards, masks, logp_next, lagrange, backup_entropy, gamma,
+  launch_k(critic_loss_kernel, 1, 1024, 0, ST(stream), q, q_next, sub, n_sub, rewards, masks, logp_next, lagrange, backup_entropy, gamma,
                                                  grad_scale, target_q, dq, info, E, B);
   return check_launch("critic_loss_kernel");
 }
 
 extern "C" int serl_fill_f32(float* x, float v, int n, void* stream) {
-  fill_kernel<<<ceil_div(n, 256), 256, 0, ST(stream)>>>(x, v, n);
+  launch_k(fill_kernel, ceil_div(n, 256), 256, 0, ST(stream), x, v, n);
   return check_launch("fill_kernel");
 }
 
@@ -328,14 +339,14 @@ extern "C" int serl_actor_loss(const float* q, const float* logp, const float* l
                                const float* act, int ld_act, const float* std, const float* log_std, const float* eps,
                                float std_min, float std_max, float grad_scale, float* dmu, float* dlogstd, float* info,
                                int E, int B, int A, void* stream) {
-  actor_loss_kernel<<<1, 1024, 0, ST(stream)>>>(q, logp, lagrange, da, ld_da, act, ld_act, std, log_std, eps, std_min, std_max,
+  launch_k(actor_loss_kernel, 1, 1024, 0, ST(stream), q, logp, lagrange, da, ld_da, act, ld_act, std, log_std, eps, std_min, std_max,
                                                 grad_scale, dmu, dlogstd, info, E, B, A);
   return check_launch("actor_loss_kernel");
 }
 
 extern "C" int serl_temperature_loss(const float* logp, const float* lagrange, float target_entropy, float grad_scale,
                                      float* dlagrange, float* info, int B, void* stream) {
-  temperature_loss_kernel<<<1, 1024, 0, ST(stream)>>>(logp, lagrange, target_entropy, grad_scale, dlagrange, info, B);
+  launch_k(temperature_loss_kernel, 1, 1024, 0, ST(stream), logp, lagrange, target_entropy, grad_scale, dlagrange, info, B);
   return check_launch("temperature_loss_kernel");
 }
 
@@ -350,8 +361,8 @@ extern "C" int serl_adam_polyak(const serl_adam_desc* d, void* stream) {
   if (a.gap < 0 || a.aux_lo > a.aux_hi || (a.aux_hi > a.aux_lo && (a.aux_lo < 0 || a.aux_hi > d->seg_end[0] || a.aux_lo + a.aux_off < d->n))) {
     set_last_error("serl_adam_polyak: invalid gap / aux range"); return SERL_ERR_INVALID;
   }
-  adam_polyak_kernel<<<ceil_div(d->n, 256), 256, 0, ST(stream)>>>(a);
+  launch_k(adam_polyak_kernel, ceil_div(d->n, 256), 256, 0, ST(stream), a);
   if (int e = check_launch("adam_polyak_kernel")) return e;
-  adam_tick_kernel<<<1, 32, 0, ST(stream)>>>(a);
+  launch_k(adam_tick_kernel, 1, 32, 0, ST(stream), a);
   return check_launch("adam_tick_kernel");
 }

@@ -91,6 +91,7 @@ __device__ inline void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes
 // grid: x = band, y = (cam, which, t) flattened, z = row i.   kFast: row_bytes % 16 == 0.
 template <bool kFast>
 __global__ void __launch_bounds__(kSamplerThreads) sample_gather_crop_kernel(const SamplerArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ int s_idx, s_cy, s_cx;
@@ -240,6 +241,7 @@ __device__ inline void crop_offset_warp(const uint32_t* key, const int32_t* expl
 
 // grid: x = cam*2 + which, y = row i.
 __global__ void __launch_bounds__(kFrameThreads) sample_frames_kernel(const SamplerArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ uint64_t bar[kMaxBands];
   __shared__ int s_idx, s_cy[8], s_cx[8];
@@ -399,6 +401,7 @@ __device__ inline const T* st_row(const T* base, int k, size_t packed_elems, lon
 
 // grid: x = chunk of the frame, y = cam, z = write k.  Ordered writes: launch once per dependency level.
 __global__ void __launch_bounds__(256) replay_scatter_kernel(const ScatterArgs a) {
+  pdl_prologue();
   const serl_replay_view& rv = a.rv;
   const int k = blockIdx.z, cam = blockIdx.y;
   const int dst = *st_row(a.dst_slot, k, 1, a.row_stride), ss = *st_row(a.src_slot, k, 1, a.row_stride);
@@ -437,9 +440,11 @@ __global__ void __launch_bounds__(256) replay_scatter_kernel(const ScatterArgs a
   }
 }
 
-__global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) { if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += inc; }
+__global__ void counter_add_kernel(uint64_t* ctr, uint64_t inc) {
+  pdl_prologue(); if (threadIdx.x == 0 && blockIdx.x == 0) *ctr += inc; }
 
 __global__ void replay_set_valid_kernel(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n, int32_t* size_dev, int32_t size) {
+  pdl_prologue();
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < n) valid[slots[k]] = vals[k];
   if (k == 0 && size_dev) *size_dev = size;
@@ -499,13 +504,13 @@ extern "C" int serl_replay_sample_crop(const serl_replay_view* rv, const serl_sa
       configured = smem;
     }
     dim3 fgrid(rv->num_cams * 2, rq->batch);
-    sample_frames_kernel<<<fgrid, kFrameThreads, smem, st>>>(a);
+    launch_k(sample_frames_kernel, fgrid, kFrameThreads, smem, st, a);
     return check_launch("sample_frames_kernel");
   } else if (fast) {
     size_t smem = (size_t)kBandRows * row_bytes + 32;
-    sample_gather_crop_kernel<true><<<grid, kSamplerThreads, smem, st>>>(a);
+    launch_k(sample_gather_crop_kernel<true>, grid, kSamplerThreads, smem, st, a);
   } else {
-    sample_gather_crop_kernel<false><<<grid, kSamplerThreads, 0, st>>>(a);
+    launch_k(sample_gather_crop_kernel<false>, grid, kSamplerThreads, 0, st, a);
   }
   return check_launch("sample_gather_crop_kernel");
 }
@@ -523,24 +528,24 @@ extern "C" int serl_replay_scatter(const serl_replay_view* rv, const serl_scatte
   const size_t fb = (size_t)rv->height * rv->width * rv->channels;
   int chunks = (int)((fb / 16 + 255) / 256); if (chunks < 1) chunks = 1; if (chunks > 16) chunks = 16;
   dim3 grid(chunks, rv->num_cams > 0 ? rv->num_cams : 1, rq->n);
-  replay_scatter_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  launch_k(replay_scatter_kernel, grid, 256, 0, static_cast<cudaStream_t>(stream), a);
   return check_launch("replay_scatter_kernel");
 }
 
 extern "C" int serl_replay_set_valid(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n, void* stream) {
   if (n <= 0) return SERL_OK;
-  replay_set_valid_kernel<<<ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(valid, slots, vals, n, nullptr, 0);
+  launch_k(replay_set_valid_kernel, ceil_div(n, 128), 128, 0, static_cast<cudaStream_t>(stream), valid, slots, vals, n, nullptr, 0);
   return check_launch("replay_set_valid_kernel");
 }
 
 extern "C" int serl_replay_commit(uint8_t* valid, const int32_t* slots, const uint8_t* vals, int n, int32_t* size_dev, int32_t size, void* stream) {
   if (n < 0 || !size_dev) { set_last_error("serl_replay_commit: invalid arguments"); return SERL_ERR_INVALID; }
-  replay_set_valid_kernel<<<n > 0 ? ceil_div(n, 128) : 1, 128, 0, static_cast<cudaStream_t>(stream)>>>(valid, slots, vals, n, size_dev, size);
+  launch_k(replay_set_valid_kernel, n > 0 ? ceil_div(n, 128) : 1, 128, 0, static_cast<cudaStream_t>(stream), valid, slots, vals, n, size_dev, size);
   return check_launch("replay_set_valid_kernel");
 }
 
 extern "C" int serl_counter_add(uint64_t* counter, uint64_t inc, void* stream) {
-  counter_add_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(counter, inc);
+  launch_k(counter_add_kernel, 1, 32, 0, static_cast<cudaStream_t>(stream), counter, inc);
   return check_launch("counter_add_kernel");
 }
 

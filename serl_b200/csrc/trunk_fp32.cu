@@ -38,6 +38,7 @@ __device__ inline float conv_load_a(const ConvArgs& a, int n, int hb, int wb, in
 // kVec: Ci % 16 == 0 (a BK slice is one tap, contiguous channels) -> float4 gathers.
 template <bool kVec, bool kU8>
 __global__ void __launch_bounds__(256) conv_igemm_f32_kernel(const ConvArgs a) {
+  pdl_prologue();
   __shared__ __align__(16) float As[2][BK][BM + 4];
   __shared__ __align__(16) float Bs[2][BK][BN];
   const int tid = threadIdx.x;
@@ -124,6 +125,7 @@ __global__ void __launch_bounds__(256) conv_igemm_f32_kernel(const ConvArgs a) {
 __global__ void __launch_bounds__(512) groupnorm_f32_kernel(const float* x, float* y,
                                                             const float* __restrict__ scale, const float* __restrict__ bias,
                                                             const float* residual, int HW, int C, int G, float eps, int relu) {
+  pdl_prologue();
   __shared__ float red[64];
   const int g = blockIdx.x, n = blockIdx.y;
   const int Cg = C / G, q = Cg >> 2;                       // float4 per pixel in this group
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(512) groupnorm_f32_kernel(const float* x, floa
 // max_pool 3x3 stride 2, XLA SAME (pad low 0 / high 1 on even sizes, -inf padding).
 __global__ void maxpool3x3s2_f32_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int Hi, int Wi, int C,
                                         int Ho, int Wo, int pad_lo) {
+  pdl_prologue();
   const int c4n = C >> 2;
   size_t total = (size_t)N * Ho * Wo * c4n;
   for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
@@ -201,9 +204,9 @@ extern "C" int serl_conv2d_nhwc_f32(const void* x, int x_is_u8, const float* w, 
   long long M = (long long)N * a.Ho * a.Wo;
   dim3 grid((unsigned)ceil_div_ll(M, BM), Co / BN);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (x_is_u8) conv_igemm_f32_kernel<false, true><<<grid, 256, 0, st>>>(a);
-  else if (Ci % 16 == 0) conv_igemm_f32_kernel<true, false><<<grid, 256, 0, st>>>(a);
-  else conv_igemm_f32_kernel<false, false><<<grid, 256, 0, st>>>(a);
+  if (x_is_u8) launch_k(conv_igemm_f32_kernel<false, true>, grid, 256, 0, st, a);
+  else if (Ci % 16 == 0) launch_k(conv_igemm_f32_kernel<true, false>, grid, 256, 0, st, a);
+  else launch_k(conv_igemm_f32_kernel<false, false>, grid, 256, 0, st, a);
   return check_launch("conv_igemm_f32_kernel");
 }
 
@@ -215,7 +218,7 @@ extern "C" int serl_groupnorm_nhwc_f32(const float* x, float* y, const float* sc
     return SERL_ERR_UNSUPPORTED;
   }
   dim3 grid(groups, N);
-  groupnorm_f32_kernel<<<grid, 512, 0, static_cast<cudaStream_t>(stream)>>>(x, y, scale, bias, residual, HW, C, groups, eps, relu);
+  launch_k(groupnorm_f32_kernel, grid, 512, 0, static_cast<cudaStream_t>(stream), x, y, scale, bias, residual, HW, C, groups, eps, relu);
   return check_launch("groupnorm_f32_kernel");
 }
 
@@ -226,6 +229,6 @@ extern "C" int serl_maxpool3x3s2_nhwc_f32(const float* x, float* y, int N, int H
   int pad_lo = total_pad / 2;
   size_t total = (size_t)N * Ho * Wo * (C / 4);
   int blocks = (int)((total + 255) / 256); if (blocks > 148 * 16) blocks = 148 * 16;
-  maxpool3x3s2_f32_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, y, N, Hi, Wi, C, Ho, Wo, pad_lo);
+  launch_k(maxpool3x3s2_f32_kernel, blocks, 256, 0, static_cast<cudaStream_t>(stream), x, y, N, Hi, Wi, C, Ho, Wo, pad_lo);
   return check_launch("maxpool3x3s2_f32_kernel");
 }
