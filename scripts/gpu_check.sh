@@ -15,3 +15,20 @@ if [ "${NCU:-1}" = "1" ]; then
   echo "== ncu launch list"
   SERL_BENCH_SKIP_SINGLE=1 SERL_BENCH_SKIP_CPU=1 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c ${NCU_COUNT:-1100} --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --sustain-s 0 ${BENCH_ARGS:-} > gpurun_out/ncu_bench.log 2>&1 ; echo "ncu rc=$?"
 fi
+if [ "${AB:-1}" = "1" ]; then
+  echo "== A/B bench runs (50 steps, no single-camera / CPU legs)"
+  i=0
+  for cfg in "SERL_STEM_V2=0" "SERL_RES_CONV=1" "SERL_RES_CONV=1 SERL_RES_S2=1" "SERL_PDL=1" "SERL_RES_CONV=1 SERL_RES_S2=1 SERL_PDL=1"; do
+    i=$((i+1))
+    env $cfg SERL_BENCH_SKIP_SINGLE=1 SERL_BENCH_SKIP_CPU=1 timeout 600 python bench.py --steps 50 --warmup 3 > gpurun_out/bench_ab_$i.log 2> gpurun_out/bench_ab_$i.err
+    echo "[$cfg] rc=$? $(python -c "
+import json,sys
+try:
+    d=[json.loads(l) for l in open('gpurun_out/bench_ab_$i.log') if l.startswith('{')][-1]
+    print('value %.1f e2e %.1f trunk_ms %.3f frac %.3f samp_frac %.3f sections %s' % (d['value'], d['e2e']['value'], d['roofline']['ms_per_step'], d['roofline']['frac'], d['sampler']['frac'], {k: v for k, v in d['sections_ms'].items() if k != 'note'}))
+except Exception as e:
+    print('no line', e)
+")"
+    tail -2 gpurun_out/bench_ab_$i.err
+  done
+fi

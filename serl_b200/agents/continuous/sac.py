@@ -277,9 +277,22 @@ class SACAgent:
         return cm()
 
     def _features(self, eng: Engine):
-        if self._cfg.pixel:
-            for cam in self._cfg.cams:
+        if not self._cfg.pixel:
+            return
+        cams = self._cfg.cams
+        # cameras 1.. first, each on its own stream (fork / join = graph edges), then camera 0 on the current stream.  The fp32
+        # build shares its activation scratch between cameras and stays serial.
+        side = [c for c in cams if eng.cam_stream.get(c) is not None and self._cfg.precision != "fp32"]
+        for cam in side:
+            cs = eng.cam_stream[cam]
+            cs.fork()
+            with cs:
                 eng.trunk_forward(cam, eng.pix[cam], eng.feats[cam])
+        for cam in cams:
+            if cam not in side:
+                eng.trunk_forward(cam, eng.pix[cam], eng.feats[cam])
+        for cam in side:
+            eng.cam_stream[cam].join()
 
     def _dp(self, pmap_axis) -> bool:
         """ONE predicate for both halves of the data-parallel exchange (1/world pre-scaling in the loss kernels and the SUM

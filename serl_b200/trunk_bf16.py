@@ -151,9 +151,9 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
     """pix (N,hw,hw,3) uint8 -> feats[:N] (N,4,4,512) fp32."""
     N, hw = pix.shape[0], pix.shape[1]
     plans = engine.__dict__.setdefault("_tc_plans", {})
-    if N not in plans:
-        plans[N] = _Plan(N, hw, pix.device, engine.cfg.precision)
-    p = plans[N]
+    if (cam, N) not in plans:                                          # per camera: the cameras' trunks may run concurrently
+        plans[(cam, N)] = _Plan(N, hw, pix.device, engine.cfg.precision)
+    p = plans[(cam, N)]
     w, wp = engine.trunk[cam], packed_weights(engine, cam)
     s = hw // 2
     L.call("serl_trunk_stem_prep_h16", pix.data_ptr(), p.xs.data_ptr(), N, hw, hw, p.fmt, _s())
@@ -194,7 +194,7 @@ def forward(engine, cam: str, pix: torch.Tensor, feats: torch.Tensor):
         gB, bB = w[f"{b}/MyGroupNorm_1/scale"], w[f"{b}/MyGroupNorm_1/bias"]
         proj = stride != 1 or cin != f
         last = i == len(STAGES) - 1
-        side = engine.side[1] if (proj and USE_PROJ_SIDE_STREAM and hasattr(engine, "side")) else None
+        side = engine.proj_side.get(cam) if (proj and USE_PROJ_SIDE_STREAM and hasattr(engine, "proj_side")) else None
         res_ok = USE_RES_CONV and USE_FUSED_GN and {32: 64, 16: 128, 8: 256, 4: 512}.get(so) == f
         if res_ok and USE_RES_S2 and proj and stride == 2 and f == 2 * cin:
             gP, bP = w[f"{b}/norm_proj/scale"], w[f"{b}/norm_proj/bias"]
