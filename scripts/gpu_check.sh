@@ -6,6 +6,9 @@ nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out
 nproc > gpurun_out/nproc.txt
 if [ "${PYTEST:-1}" = "1" ]; then
 echo "== pytest gpu" ; timeout 1500 python -m pytest tests -m gpu -q --timeout=600 -p no:cacheprovider ${PYTEST_ARGS:-} > gpurun_out/pytest_gpu.log 2>&1 ; echo "pytest rc=$?" ; tail -25 gpurun_out/pytest_gpu.log
+echo "== new kernels switched on: stem v2 / fused trunk / camera streams / PDL through the trunk + agent tests"
+SERL_STEM_V2=1 timeout 900 python -m pytest tests/test_trunk_bf16_gpu.py -m gpu -q --timeout=600 -p no:cacheprovider -k "stem or trunk" > gpurun_out/pytest_stem2.log 2>&1 ; echo "stem2 rc=$?" ; tail -6 gpurun_out/pytest_stem2.log
+SERL_STEM_V2=1 SERL_RES_CONV=1 SERL_RES_S2=1 SERL_CAM_STREAMS=1 SERL_PDL=1 timeout 900 python -m pytest tests/test_b256_fp16_gpu.py tests/test_agent_gpu.py -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/pytest_allnew.log 2>&1 ; echo "allnew rc=$?" ; tail -6 gpurun_out/pytest_allnew.log
 echo "== smoke" ; timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1 ; echo "smoke rc=$?" ; tail -5 gpurun_out/smoke.log
 fi
 if [ "${BENCH:-1}" = "1" ]; then
@@ -18,7 +21,7 @@ fi
 if [ "${AB:-1}" = "1" ]; then
   echo "== A/B bench runs (50 steps, no single-camera / CPU legs)"
   i=0
-  for cfg in "SERL_STEM_V2=0" "SERL_RES_CONV=1" "SERL_RES_CONV=1 SERL_RES_S2=1" "SERL_PDL=1" "SERL_RES_CONV=1 SERL_RES_S2=1 SERL_PDL=1"; do
+  for cfg in "SERL_STEM_V2=1" "SERL_STEM_V2=1 SERL_RES_CONV=1" "SERL_STEM_V2=1 SERL_RES_CONV=1 SERL_RES_S2=1" "SERL_PDL=1" "SERL_CAM_STREAMS=1" "SERL_STEM_V2=1 SERL_RES_CONV=1 SERL_RES_S2=1 SERL_PDL=1 SERL_CAM_STREAMS=1"; do
     i=$((i+1))
     env $cfg SERL_BENCH_SKIP_SINGLE=1 SERL_BENCH_SKIP_CPU=1 timeout 600 python bench.py --steps 50 --warmup 3 > gpurun_out/bench_ab_$i.log 2> gpurun_out/bench_ab_$i.err
     echo "[$cfg] rc=$? $(python -c "
