@@ -193,7 +193,7 @@ def test_rng_kernels_match_jax_restatement():
         ops.dropout_mask_fill(ops.key_ptr(keys, L.KEY_CRITIC_NEXT), j, 0.9, mask, mask.numel())
         np.testing.assert_array_equal(mask.cpu().numpy().astype(bool), P.bernoulli(P.fold_in(k_na, j), 0.9, (mask.numel(),)))
     sub = torch.zeros(2, dtype=torch.int32, device="cuda")
-    ops.subsample_idx(ops.key_ptr(keys, L.KEY_CRITIC_SUBSAMPLE), 10, sub)
+    ops.subsample_idx(ops.key_ptr(keys, L.KEY_CRITIC_SUBSAMPLE), 10, sub, 2)
     k_sub = hk[2 * L.KEY_CRITIC_SUBSAMPLE: 2 * L.KEY_CRITIC_SUBSAMPLE + 2]
     np.testing.assert_array_equal(sub.cpu().numpy(), P.randint(k_sub, (2,), 0, 10))
 

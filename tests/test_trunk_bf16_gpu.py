@@ -383,3 +383,27 @@ def test_conv3x3s2_proj_res_matches_float64_block_head(Wo, Co, N, prec):
     gy, gr = y.float().cpu().numpy(), r.float().cpu().numpy()
     assert np.isfinite(gy).all() and np.isfinite(gr).all()
     assert rel_err(gy, ref_y.numpy()) < OUT_TOL[prec] and rel_err(gr, ref_r.numpy()) < OUT_TOL[prec]
+
+
+def test_stem_v2_runs_when_requested():
+    """SERL_STEM_V2=1 must actually run stem2_tc_kernel (the launcher falls back to v1 if the driver refuses the overlapping 5-D
+    tensor map): after a fused-stem call the library still reports v2 active."""
+    import os
+    from serl_b200 import _lib as L
+    from serl_b200 import trunk_bf16 as T
+    if os.environ.get("SERL_STEM_V2", "0") in ("", "0"):
+        pytest.skip("SERL_STEM_V2 not set")
+    lib = L.load()
+    N = 2
+    plan = T._Plan(N, 128, "cuda", "fp16")
+    w = torch.randn(7, 7, 3, 64, device="cuda") * 0.1
+    pix = torch.randint(0, 256, (N, 128, 128, 3), dtype=torch.uint8, device="cuda")
+    L.call("serl_trunk_stem_prep_h16", pix.data_ptr(), plan.xs.data_ptr(), N, 128, 128, plan.fmt, L.stream_ptr())
+    d = L.StemPoolDesc()
+    st = torch.zeros(N, 4, 2, device="cuda")
+    d.xs, d.w, d.pooled, d.side = plan.xs.data_ptr(), T.pack_stem_weight(w, torch.float16).data_ptr(), plan.pooled.data_ptr(), plan.side.data_ptr()
+    d.stats, d.error, d.neg_mask, d.N, d.fmt = st.data_ptr(), plan.error.data_ptr(), 0, N, plan.fmt
+    L.call("serl_stem_conv_pool_tc_h16", C.byref(d), L.stream_ptr())
+    torch.cuda.synchronize()
+    assert int(plan.error.item()) == 0
+    assert lib.serl_stem_v2_active() == 1, "the driver refused the overlapping 5-D tensor map: stem fell back to v1"
