@@ -9,6 +9,7 @@ echo "== pytest gpu" ; timeout 1500 python -m pytest tests -m gpu -q --timeout=6
 echo "== new kernels switched on: stem v2 / fused trunk / camera streams / PDL through the trunk + agent tests"
 SERL_STEM_V2=1 timeout 900 python -m pytest tests/test_trunk_bf16_gpu.py -m gpu -q --timeout=600 -p no:cacheprovider -k "stem or trunk" > gpurun_out/pytest_stem2.log 2>&1 ; echo "stem2 rc=$?" ; tail -6 gpurun_out/pytest_stem2.log
 SERL_STEM_V2=1 SERL_RES_CONV=1 SERL_RES_S2=1 SERL_CAM_STREAMS=1 SERL_PDL=1 timeout 900 python -m pytest tests/test_b256_fp16_gpu.py tests/test_agent_gpu.py -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/pytest_allnew.log 2>&1 ; echo "allnew rc=$?" ; tail -6 gpurun_out/pytest_allnew.log
+SERL_SAMPLER_PERSISTENT=1 timeout 900 python -m pytest tests/test_replay_device.py tests/test_agent_gpu.py -m gpu -q --timeout=600 -p no:cacheprovider > gpurun_out/pytest_psampler.log 2>&1 ; echo "persistent sampler rc=$?" ; tail -4 gpurun_out/pytest_psampler.log
 echo "== smoke" ; timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1 ; echo "smoke rc=$?" ; tail -5 gpurun_out/smoke.log
 fi
 if [ "${BENCH:-1}" = "1" ]; then
@@ -21,7 +22,7 @@ fi
 if [ "${AB:-1}" = "1" ]; then
   echo "== A/B bench runs (50 steps, no single-camera / CPU legs)"
   i=0
-  for cfg in "SERL_STEM_V2=1" "SERL_STEM_V2=1 SERL_RES_CONV=1" "SERL_STEM_V2=1 SERL_RES_CONV=1 SERL_RES_S2=1" "SERL_PDL=1" "SERL_CAM_STREAMS=1" "SERL_STEM_V2=1 SERL_RES_CONV=1 SERL_RES_S2=1 SERL_PDL=1 SERL_CAM_STREAMS=1"; do
+  for cfg in ${AB_CFGS:-"SERL_STEM_V2=1" "SERL_STEM_V2=1 SERL_RES_CONV=1" "SERL_STEM_V2=1 SERL_RES_CONV=1 SERL_RES_S2=1" "SERL_SAMPLER_PERSISTENT=1" "SERL_STEM_V2=1 SERL_RES_CONV=1 SERL_RES_S2=1 SERL_PDL=1 SERL_CAM_STREAMS=1 SERL_SAMPLER_PERSISTENT=1"}; do
     i=$((i+1))
     env $cfg SERL_BENCH_SKIP_SINGLE=1 SERL_BENCH_SKIP_CPU=1 timeout 600 python bench.py --steps 50 --warmup 3 > gpurun_out/bench_ab_$i.log 2> gpurun_out/bench_ab_$i.err
     echo "[$cfg] rc=$? $(python -c "

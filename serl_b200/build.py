@@ -49,13 +49,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     def compile_one(item):
         src, obj, st, stamp = item
-        cmd = [NVCC, *FLAGS, "-c", src, "-o", obj] + (["-Xptxas", "-v"] if verbose else [])
+        tmp = obj + ".tmp.o"                               # every file appears atomically (a repo snapshot may be taken mid-build)
+        cmd = [NVCC, *FLAGS, "-c", src, "-o", tmp] + (["-Xptxas", "-v"] if verbose else [])
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
         if verbose:
             print(r.stderr)
-        open(st, "w").write(stamp)
+        os.replace(tmp, obj)
+        open(st + ".tmp", "w").write(stamp)
+        os.replace(st + ".tmp", st)
         return src
 
     if todo:
@@ -63,10 +66,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
             for done in ex.map(compile_one, todo):
                 print("compiled", os.path.relpath(done, ROOT))
     if todo or not os.path.exists(LIB):
-        r = subprocess.run([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+        r = subprocess.run([NVCC, "-shared", "-o", LIB + ".tmp", *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
                            capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+        os.replace(LIB + ".tmp", LIB)
         print("linked", os.path.relpath(LIB, ROOT))
     return LIB
 

@@ -129,7 +129,7 @@ template <int W_> struct R3Geom {
   static constexpr int IPU = UT * G / TPI;                           // images per item: 1, 1, 4, 16
 };
 
-template <class F, int W, int BN, int VST, int WST>
+template <class F, int W, int BN, int VST, int WST, int NSTG>
 __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap wmap,
                                                                      const __grid_constant__ CUtensorMap rmap, const __grid_constant__ CUtensorMap omap,
                                                                      const C3rArgs a) {
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid
   uint8_t* sV = smem;                                    // VST variant stages
   uint8_t* sB = sV + VST * VSTAGE;                       // weight tiles
   uint8_t* sS = sB + NWB * B_STAGE;                      // 2 staging tiles
-  float* sCh = reinterpret_cast<float*>(sS + 2 * STG);   // [BN][4]: gamma, beta, residual gamma, residual beta of the item's channels
+  float* sCh = reinterpret_cast<float*>(sS + NSTG * STG);   // [BN][4]: gamma, beta, residual gamma, residual beta of the item's channels
   float* sStat = sCh + BN * 4;                           // [IPU][4 groups][4]: mean, rstd, residual mean, residual rstd
   float* sRed = sStat + IPU * 16;                        // [IPU][4 groups][2]: sum, sum of squares
   uint64_t* vfull = reinterpret_cast<uint64_t*>(sRed + IPU * 8);
@@ -159,9 +159,9 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid
   uint64_t* wempty = wfull + NWB;
   uint64_t* afull = wempty + NWB;
   uint64_t* aempty = afull + NSLOT;
-  uint64_t* sfull = aempty + NSLOT;                      // staging: residual landed (or buffer handed over)
-  uint64_t* sfree = sfull + 2;                           // staging: output store has finished reading
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sfree + 2);
+  uint64_t* sfull = aempty + NSLOT;                      // staging: buffer granted to a tile (and its residual, if any, has landed)
+  uint64_t* sready = sfull + NSTG;                       // staging: the 8 epilogue warps have written the tile's output
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sready + NSTG);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int Cg = a.Co / 4;
@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid
     for (int s = 0; s < VST; ++s) { r3_mbar_init(&vfull[s], 1); r3_mbar_init(&vempty[s], 1); }
     for (int s = 0; s < NWB; ++s) { r3_mbar_init(&wfull[s], 1); r3_mbar_init(&wempty[s], 1); }
     for (int s = 0; s < NSLOT; ++s) { r3_mbar_init(&afull[s], 1); r3_mbar_init(&aempty[s], 8); }
-    for (int s = 0; s < 2; ++s) { r3_mbar_init(&sfull[s], 1); r3_mbar_init(&sfree[s], 1); }
+    for (int s = 0; s < NSTG; ++s) { r3_mbar_init(&sfull[s], 1); r3_mbar_init(&sready[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < IPU * 8; i += blockDim.x) sRed[i] = 0.f;
@@ -202,7 +202,6 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid
     bool ok = true;
     uint32_t tc = 0;                                                     // tiles processed (TMEM slot ring position)
     uint32_t sc = 0;                                                     // staging buffers used
-    int stores_pending = 0;
     for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
       const int unit = item / a.n_tiles_n, n0 = (item % a.n_tiles_n) * BN;
       // ---------------- pass 1: statistics, tile by tile as the MMAs complete ----------------
@@ -265,8 +264,8 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid
       for (int i = et; i < IPU * 8; i += R3_EPI_THREADS) sRed[i] = 0.f;   // for the next item (next use is after >= 1 more barrier)
       // ---------------- pass 2: normalise (+ residual) (+ ReLU), tile by tile ----------------
       for (int j = 0; j < UT; ++j, ++tc, ++sc) {
-        const uint32_t slot = tc % NSLOT, sb = sc & 1u;
-        ok = ok && r3_mbar_wait(&sfull[sb], (sc >> 1) & 1u, a.error);
+        const uint32_t slot = tc % NSLOT, sb = sc % NSTG;
+        ok = ok && r3_mbar_wait(&sfull[sb], (sc / NSTG) & 1u, a.error);
         const int img_u = (TPI > 1 ? 0 : j * G) + img_l;
         // this lane's (image, group) statistics: <= 2 groups per column half
         const int g0 = (n0 + chalf * HC) / Cg;
@@ -321,27 +320,11 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncwarp();
         if (lane == 0) r3_mbar_arrive(&aempty[slot]);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // staging writes (generic proxy) -> TMA store (async proxy)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        if (et == 0) {
-          if (!a.out_f32 && ok) {
-            const int nimg = tile_img(unit, j), y0r = tile_y0(j);
-#pragma unroll
-            for (int h = 0; h < NH; ++h) r3_tma_store_4d(&omap, sS + sb * STG + h * (128 * 128), n0 + h * 64, 0, nimg, y0r);
-          }
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          if (stores_pending) {                                            // the PREVIOUS tile's store no longer reads its staging buffer
-            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-            r3_mbar_arrive(&sfree[sb ^ 1u]);
-          }
-          stores_pending = 1;
-        }
+        // staging writes (generic proxy) -> TMA store (async proxy); no CTA-wide barrier: each warp reports to the I/O thread
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) r3_mbar_arrive(&sready[sb]);
       }
-    }
-    if (et == 0 && stores_pending) {
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      r3_mbar_arrive(&sfree[(sc - 1) & 1u]);
-      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");            // global writes complete before the kernel ends
     }
   } else if (warp == 8) {
     // =============================== MMA issuer (one thread) ===============================
@@ -444,26 +427,44 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid
       }
     }
   } else {
-    // =============================== staging hand-over: residual tile by TMA (or just the free buffer) ===============================
+    // =============================== I/O thread: staging buffers, residual loads, output stores ===============================
+    // Tiles use the NSTG staging buffers round-robin.  A buffer is GRANTED to tile g (its residual tile, if the layer has one,
+    // is fetched into it by TMA: arrival completes sfull) as soon as the store of tile g - NSTG has finished reading it, i.e.
+    // up to NSTG tiles ahead of the epilogue, so the residual's L2 / HBM latency hides behind the other tiles' work; when the
+    // 8 epilogue warps have written tile s (sready) the buffer goes out as one TMA store per 64 channels.
     if (lane == 0) {
       bool ok = true;
-      uint32_t sc = 0;
-      for (int item = blockIdx.x; item < a.n_items && ok; item += gridDim.x) {
-        const int unit = item / a.n_tiles_n, n0 = (item % a.n_tiles_n) * BN;
-        for (int j = 0; j < UT && ok; ++j, ++sc) {
-          const uint32_t sb = sc & 1u;
-          ok = r3_mbar_wait(&sfree[sb], ((sc >> 1) & 1u) ^ 1u, a.error);
-          if (!ok) break;
+      int g_item = blockIdx.x, g_j = 0, s_item = blockIdx.x, s_j = 0;
+      uint32_t g = 0, sidx = 0;
+      while (s_item < a.n_items && ok) {
+        while (g_item < a.n_items && g < sidx + NSTG) {                  // grant buffers ahead
+          const uint32_t sb = g % NSTG;
+          const int unit = g_item / a.n_tiles_n, n0 = (g_item % a.n_tiles_n) * BN;
           if (a.has_res) {
             r3_mbar_expect_tx(&sfull[sb], (uint32_t)STG);
 #pragma unroll
             for (int h = 0; h < NH; ++h)
-              r3_tma_load_4d(sS + sb * STG + h * (128 * 128), &rmap, n0 + h * 64, 0, tile_img(unit, j), tile_y0(j), &sfull[sb]);
+              r3_tma_load_4d(sS + sb * STG + h * (128 * 128), &rmap, n0 + h * 64, 0, tile_img(unit, g_j), tile_y0(g_j), &sfull[sb]);
           } else {
             r3_mbar_arrive(&sfull[sb]);
           }
+          ++g;
+          if (++g_j == UT) { g_j = 0; g_item += gridDim.x; }
         }
+        const uint32_t sb = sidx % NSTG;
+        ok = r3_mbar_wait(&sready[sb], (sidx / NSTG) & 1u, a.error);
+        if (!ok) break;
+        if (!a.out_f32) {
+          const int unit = s_item / a.n_tiles_n, n0 = (s_item % a.n_tiles_n) * BN;
+#pragma unroll
+          for (int h = 0; h < NH; ++h) r3_tma_store_4d(&omap, sS + sb * STG + h * (128 * 128), n0 + h * 64, 0, tile_img(unit, s_j), tile_y0(s_j));
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the store has read the buffer: it can be granted again
+        }
+        ++sidx;
+        if (++s_j == UT) { s_j = 0; s_item += gridDim.x; }
       }
+      asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");            // global writes complete before the kernel ends
     }
   }
   __syncthreads();
@@ -814,14 +815,14 @@ static bool r3_act_map(CUtensorMap* map, CUtensorMapDataType dt, const void* ptr
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <class F, int W, int BN, int VST, int WST>
+template <class F, int W, int BN, int VST, int WST, int NSTG>
 static int launch_conv3r(const serl_conv3x3_res_desc* d, cudaStream_t st) {
   using Gm = R3Geom<W>;
   constexpr int NWB = (BN == 64) ? 9 : WST;
-  constexpr size_t smem = (size_t)VST * Gm::MT * Gm::PATCH + (size_t)NWB * BN * 128 + 2 * (size_t)(BN / 64) * 128 * 128 +
-                          (size_t)BN * 16 + (size_t)Gm::IPU * 64 + (size_t)Gm::IPU * 32 + 8 * (2 * VST + 2 * NWB + 2 * (512 / BN) + 4) + 64 + 1024;
+  constexpr size_t smem = (size_t)VST * Gm::MT * Gm::PATCH + (size_t)NWB * BN * 128 + NSTG * (size_t)(BN / 64) * 128 * 128 +
+                          (size_t)BN * 16 + (size_t)Gm::IPU * 64 + (size_t)Gm::IPU * 32 + 8 * (2 * VST + 2 * NWB + 2 * (512 / BN) + 2 * NSTG) + 64 + 1024;
   static_assert(smem <= 232448, "conv3x3_res_kernel: shared memory budget exceeded");
-  auto kern = conv3x3_res_kernel<F, W, BN, VST, WST>;
+  auto kern = conv3x3_res_kernel<F, W, BN, VST, WST, NSTG>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return check_launch("cudaFuncSetAttribute(conv3x3_res)");
@@ -935,10 +936,13 @@ extern "C" int serl_conv3x3_res_h16(const serl_conv3x3_res_desc* d, void* stream
   const int key = d->W * 10000 + d->Ci * 10 + (d->Co == d->Ci);
   if (d->H != d->W || d->Co != d->Ci) { set_last_error("serl_conv3x3_res_h16: square maps with Ci == Co only"); return SERL_ERR_UNSUPPORTED; }
   switch (key) {
-    case 32 * 10000 + 64 * 10 + 1:  return h ? launch_conv3r<R3Fp16, 32, 64, 5, 1>(d, st) : launch_conv3r<R3Bf16, 32, 64, 5, 1>(d, st);
-    case 16 * 10000 + 128 * 10 + 1: return h ? launch_conv3r<R3Fp16, 16, 128, 2, 4>(d, st) : launch_conv3r<R3Bf16, 16, 128, 2, 4>(d, st);
-    case 8 * 10000 + 256 * 10 + 1:  return h ? launch_conv3r<R3Fp16, 8, 128, 2, 4>(d, st) : launch_conv3r<R3Bf16, 8, 128, 2, 4>(d, st);
-    case 4 * 10000 + 512 * 10 + 1:  return h ? launch_conv3r<R3Fp16, 4, 128, 2, 3>(d, st) : launch_conv3r<R3Bf16, 4, 128, 2, 3>(d, st);
+    // <W, BN, variant stages, weight stages, staging buffers>.  32x32: 8 tiles per item drain back to back, so three staging
+    // buffers keep residual fetches ahead (96 + 72 + 48 KB); the 2-tile items of the smaller maps have a whole item of MMAs
+    // between drains: two buffers (80/96 + 64 + 64 KB).
+    case 32 * 10000 + 64 * 10 + 1:  return h ? launch_conv3r<R3Fp16, 32, 64, 4, 1, 3>(d, st) : launch_conv3r<R3Bf16, 32, 64, 4, 1, 3>(d, st);
+    case 16 * 10000 + 128 * 10 + 1: return h ? launch_conv3r<R3Fp16, 16, 128, 2, 4, 2>(d, st) : launch_conv3r<R3Bf16, 16, 128, 2, 4, 2>(d, st);
+    case 8 * 10000 + 256 * 10 + 1:  return h ? launch_conv3r<R3Fp16, 8, 128, 2, 4, 2>(d, st) : launch_conv3r<R3Bf16, 8, 128, 2, 4, 2>(d, st);
+    case 4 * 10000 + 512 * 10 + 1:  return h ? launch_conv3r<R3Fp16, 4, 128, 2, 3, 2>(d, st) : launch_conv3r<R3Bf16, 4, 128, 2, 3, 2>(d, st);
   }
   set_last_error("serl_conv3x3_res_h16: unsupported shape (H=W=%d, Ci=%d, Co=%d): ResNet-10 block shapes at 128x128 input only", d->W, d->Ci, d->Co);
   return SERL_ERR_UNSUPPORTED;

@@ -635,8 +635,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem2_tc_kernel(const __grid_co
   constexpr int BN = 64, W_TILE = BN * 128;
   uint8_t* sRing = smem;                                        // (S2_RING + 1) x 8 KiB, the last slot mirrors slot 0
   uint8_t* sW = sRing + (S2_RING + 1) * S2_ROW_BYTES;           // 4 x 8 KiB resident weights
-  uint8_t* sStage = sW + 4 * W_TILE;                            // 2 x 8 KiB pool staging tiles (one per epilogue group)
-  uint64_t* rfull = reinterpret_cast<uint64_t*>(sStage + 2 * ST_POOL_STAGE);
+  uint8_t* sStage = sW + 4 * W_TILE;                            // 2 groups x 2 x 8 KiB pool staging tiles
+  uint64_t* rfull = reinterpret_cast<uint64_t*>(sStage + 4 * ST_POOL_STAGE);
   uint64_t* rempty = rfull + S2_RING;
   uint64_t* afull = rempty + S2_RING;
   uint64_t* aempty = afull + S2_ACC;
@@ -669,40 +669,49 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem2_tc_kernel(const __grid_co
     // ------------------------------- epilogue: stats + fused 3x3/2 max-pool -------------------------------
     const int grp = warp >> 2, quarter = warp & 3;
     const int m = quarter * 32 + lane;                          // TMEM lane = operand row of the tile
-    uint8_t* stage = sStage + grp * ST_POOL_STAGE;
+    uint8_t* stage_base = sStage + grp * (2 * ST_POOL_STAGE);  // two staging tiles per group: ONE named barrier per tile suffices
     const int tg = threadIdx.x & 127, pj = tg >> 2, qd = tg & 3; // pool phase: pooled column, 8-channel chunk of this group's 32
     const int bar_id = 1 + grp;
+    const uint32_t nmask = (uint32_t)(a.neg_mask >> (grp * 32)); // sign of the frozen GroupNorm scale of this group's 32 channels
     uint32_t prevA[4] = {0u, 0u, 0u, 0u};
     bool ok = true;
     int ac = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int n_img = u >> 2;
+      float us[2] = {0.f, 0.f}, uss[2] = {0.f, 0.f};             // GroupNorm partial sums of the unit's 8 tiles (one image): reduced once per unit
       for (int tt = 0; tt < 8; ++tt, ++ac) {
         const int as = ac & (S2_ACC - 1);
         const int t = (u & 3) * 8 + tt;                          // tile row of the image: conv rows 2t, 2t+1
+        uint8_t* stage = stage_base + (ac & 1) * ST_POOL_STAGE;  // tile ac+2 rewrites this buffer only after barrier ac+1, i.e. after every read of tile ac
         ok = ok && tc_mbar_wait(&afull[as], (uint32_t)((ac / S2_ACC) & 1), a.error);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        uint32_t v[2][16];
+        {                                                        // both 16-column loads in flight, one wait, then hand the accumulator back
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + grp * 32);
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                       : "=r"(v[0][0]), "=r"(v[0][1]), "=r"(v[0][2]), "=r"(v[0][3]), "=r"(v[0][4]), "=r"(v[0][5]), "=r"(v[0][6]), "=r"(v[0][7]),
+                         "=r"(v[0][8]), "=r"(v[0][9]), "=r"(v[0][10]), "=r"(v[0][11]), "=r"(v[0][12]), "=r"(v[0][13]), "=r"(v[0][14]), "=r"(v[0][15])
+                       : "r"(taddr) : "memory");
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                       : "=r"(v[1][0]), "=r"(v[1][1]), "=r"(v[1][2]), "=r"(v[1][3]), "=r"(v[1][4]), "=r"(v[1][5]), "=r"(v[1][6]), "=r"(v[1][7]),
+                         "=r"(v[1][8]), "=r"(v[1][9]), "=r"(v[1][10]), "=r"(v[1][11]), "=r"(v[1][12]), "=r"(v[1][13]), "=r"(v[1][14]), "=r"(v[1][15])
+                       : "r"(taddr + 16u) : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) tc_mbar_arrive(&aempty[as]);
+        }
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
-          const int c0 = grp * 32 + h * 16;
-          uint32_t v[16];
-          tc_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * BN + c0), v);
-          if (h == 1) {                                          // this warp's last read of the accumulator: hand the stage back
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) tc_mbar_arrive(&aempty[as]);
-          }
           float s = 0.f, ss = 0.f;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) { const float f = __uint_as_float(v[j]); s += f; ss += f * f; }
-          if (!ok) { s = 0.f; ss = 0.f; }
-          s = warp_sum(s); ss = warp_sum(ss);
-          if (ok && lane == 0) { float* st = a.stats + ((size_t)n_img * 4 + c0 / 16) * 2; atomicAdd(st, s); atomicAdd(st + 1, ss); }
+          for (int j = 0; j < 16; ++j) { const float f = __uint_as_float(v[h][j]); s += f; ss += f * f; }
+          us[h] += s; uss[h] += ss;
 #pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] ^= (uint32_t)((a.neg_mask >> (c0 + j)) & 1ull) << 31;
+          for (int j = 0; j < 16; ++j) v[h][j] ^= ((nmask >> (h * 16 + j)) & 1u) << 31;
           uint32_t pk[8];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) pk[j] = F::pack(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          for (int j = 0; j < 8; ++j) pk[j] = F::pack(__uint_as_float(v[h][2 * j]), __uint_as_float(v[h][2 * j + 1]));
           uint8_t* row = stage + m * 64;
           const int sw = s2_sw(m);
           *reinterpret_cast<uint4*>(row + (((2 * h) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -737,7 +746,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem2_tc_kernel(const __grid_co
         for (int i = 0; i < 4; ++i) prevA[i] = F::max2(B[i], R1[i]);
         if (ok && tt == 7)
           *reinterpret_cast<uint4*>(a.y + ((size_t)n_img * 32 + t) * 2048 + cofs) = make_uint4(prevA[0], prevA[1], prevA[2], prevA[3]);
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");   // staging tile free for the next tile
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {                              // one reduction + one atomic pair per (warp, group) per unit
+        const float s = warp_sum(us[h]), ss = warp_sum(uss[h]);
+        if (ok && lane == 0) { float* st = a.stats + ((size_t)n_img * 4 + grp * 2 + h) * 2; atomicAdd(st, s); atomicAdd(st + 1, ss); }
       }
     }
   } else if (warp == 8) {
@@ -1084,7 +1097,7 @@ typedef CUresult (*TcEncodeTiledFn5)(CUtensorMap*, CUtensorMapDataType, cuuint32
 // Returns SERL_ERR_UNSUPPORTED (and launches nothing) if the driver refuses the overlapping-stride tensor map.
 template <class F>
 static int launch_stem2_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
-  constexpr size_t smem = (size_t)(S2_RING + 1) * S2_ROW_BYTES + 4 * 64 * 128 + 2 * ST_POOL_STAGE + 1024 + 512;
+  constexpr size_t smem = (size_t)(S2_RING + 1) * S2_ROW_BYTES + 4 * 64 * 128 + 4 * ST_POOL_STAGE + 1024 + 512;
   auto kern = stem2_tc_kernel<F>;
   static bool configured = false;
   if (!configured) {
