@@ -88,6 +88,35 @@ __device__ inline void r3_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, u
   asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// Four k-steps (UMMA_K = 16 elements = 32 B = +2 descriptor units) of one tap for one tile in ONE asm statement.
+// Why: the issue loop runs in a single thread, and ptxas turns every asm statement with a vector-register operand (the TMEM
+// address, the descriptors) into an ELECT / R2UR / branch "uniformisation" sequence in front of the UTCHMMA - measured ~200
+// cycles per MMA when every MMA is its own statement (profiles/r02_ncu_issue_bound.md), i.e. the conv kernels were ISSUE-bound
+// at 16-37 % tensor-pipe activity.  One statement per four MMAs pays that sequence once; the +2 steps are uniform-datapath adds.
+__device__ inline void r3_mma_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate_first) {
+  // executed by the WHOLE (converged) issuer warp with warp-uniform operands; one elected lane issues
+  asm volatile("{\n .reg .pred p, t, e;\n .reg .b64 a1, a2, a3, b1, b2, b3;\n"
+               " elect.sync _|e, 0xffffffff;\n"
+               " setp.ne.b32 p, %4, 0;\n setp.eq.u32 t, 0, 0;\n"
+               " add.u64 a1, %1, 2;\n add.u64 b1, %2, 2;\n add.u64 a2, %1, 4;\n add.u64 b2, %2, 4;\n add.u64 a3, %1, 6;\n add.u64 b3, %2, 6;\n"
+               " @e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+               " @e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n"
+               " @e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n"
+               " @e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first) : "memory");
+}
+// tcgen05.commit / mbarrier.arrive by one elected lane of the converged issuer warp
+__device__ inline void r3_commit_w(uint64_t* bar) {
+  asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+               " @e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(r3_smem(bar)) : "memory");
+}
+__device__ inline void r3_arrive_w(uint64_t* bar) {
+  asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n @e mbarrier.arrive.shared::cta.b64 _, [%0];\n}" ::"r"(r3_smem(bar)) : "memory");
+}
+// warp-uniform bounded wait: every lane polls, the verdict is a vote (uniform by construction)
+__device__ inline bool r3_mbar_wait_w(uint64_t* bar, uint32_t parity, int32_t* error) {
+  return __all_sync(0xffffffffu, r3_mbar_wait(bar, parity, error));
+}
 __device__ inline void r3_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(r3_smem(bar)) : "memory");
 }
@@ -327,52 +356,57 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3_res_kernel(const __grid
       }
     }
   } else if (warp == 8) {
-    // =============================== MMA issuer (one thread) ===============================
-    if (lane == 0) {
+    // =============================== MMA issuer (whole warp, converged; one elected lane issues) ===============================
+    // Every operand of the issue loop is warp-uniform and the control flow is convergent, so ptxas keeps descriptors, TMEM
+    // addresses and loop state in UNIFORM registers.  (Round 1 ran this loop inside `if (lane == 0)`: ptxas then wraps every
+    // UTCHMMA in an ELECT / R2UR / branch sequence to uniformise its vector-register operands - ~200 cycles per MMA, which is
+    // what bounded every conv kernel at 16-37 % tensor-pipe activity, profiles/r02_ncu_issue_bound.md.)
+    // The whole 512-column allocation starts at TMEM address 0 by construction (checked once below).
+    {
       const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);     // LBO=1, SBO=1024 B, version 1, SWIZZLE_128B
       const uint32_t v_lo = (r3_smem(sV) & 0x3FFFF) >> 4, b_lo = (r3_smem(sB) & 0x3FFFF) >> 4;
-      bool ok = true;
+      bool ok = __all_sync(0xffffffffu, tmem_base == 0u);
+      if (!ok && lane == 0) atomicOr(a.error, 16);
       uint32_t tc = 0, vc = 0, wc = 0;
       for (int item = blockIdx.x; item < a.n_items && ok; item += gridDim.x) {
         for (int sub = 0; sub < UT / MT && ok; ++sub) {
           for (int jj = 0; jj < MT && ok; ++jj) {                         // the sub-group's accumulators must have been drained
             const uint32_t t = tc + sub * MT + jj;
-            ok = r3_mbar_wait(&aempty[t % NSLOT], ((t / NSLOT) & 1u) ^ 1u, a.error);
+            ok = r3_mbar_wait_w(&aempty[t % NSLOT], ((t / NSLOT) & 1u) ^ 1u, a.error);
           }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           for (int cb = 0; cb < a.cblocks && ok; ++cb) {
             for (int s = 0; s < 3 && ok; ++s, ++vc) {
               const uint32_t vs = vc % VST;
-              ok = r3_mbar_wait(&vfull[vs], (vc / VST) & 1u, a.error);
+              ok = r3_mbar_wait_w(&vfull[vs], (vc / VST) & 1u, a.error);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               for (int r = 0; r < 3 && ok; ++r) {
                 uint32_t ws;
                 if (kResW) {
                   ws = (uint32_t)(r * 3 + s);
-                  if (item == (int)blockIdx.x && sub == 0) { ok = r3_mbar_wait(&wfull[ws], 0u, a.error); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+                  if (item == (int)blockIdx.x && sub == 0) { ok = r3_mbar_wait_w(&wfull[ws], 0u, a.error); asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
                 } else {
                   ws = wc % WST;
-                  ok = r3_mbar_wait(&wfull[ws], (wc / WST) & 1u, a.error);
+                  ok = r3_mbar_wait_w(&wfull[ws], (wc / WST) & 1u, a.error);
                   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
                 const uint64_t bd = desc_hi | (uint64_t)(b_lo + ws * (B_STAGE >> 4));
 #pragma unroll
                 for (int jj = 0; jj < MT; ++jj) {
                   const uint32_t t = tc + sub * MT + jj;
-                  const uint32_t tmem_d = tmem_base + (t % NSLOT) * BN;
+                  const uint32_t tmem_d = (t % NSLOT) * BN;               // TMEM base is 0
                   const uint64_t ad = desc_hi | (uint64_t)(v_lo + ((vs * VSTAGE + jj * PATCH + r * ROWB) >> 4));
-#pragma unroll
-                  for (int k = 0; k < 4; ++k) r3_mma(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((cb | s | r | k) != 0));
+                  r3_mma_x4(tmem_d, ad, bd, idesc, (uint32_t)((cb | s | r) != 0));
                 }
-                if (!kResW) { r3_commit(&wempty[ws]); ++wc; }
+                if (!kResW) { r3_commit_w(&wempty[ws]); ++wc; }
               }
-              r3_commit(&vempty[vs]);
+              r3_commit_w(&vempty[vs]);
             }
           }
           for (int jj = 0; jj < MT; ++jj) {
             const uint32_t t = tc + sub * MT + jj;
-            if (ok) r3_commit(&afull[t % NSLOT]); else r3_mbar_arrive(&afull[t % NSLOT]);
+            if (ok) r3_commit_w(&afull[t % NSLOT]); else r3_arrive_w(&afull[t % NSLOT]);
           }
         }
         tc += UT;
@@ -682,26 +716,27 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3s2_res_kernel(const __gr
       asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
   } else if (warp == 8) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // =============================== MMA issuer (whole warp, converged; one elected lane issues) ===============================
+    {
       const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
       const uint32_t v_lo = (r3_smem(sV) & 0x3FFFF) >> 4, b_lo = (r3_smem(sB) & 0x3FFFF) >> 4;
-      bool ok = true;
+      bool ok = __all_sync(0xffffffffu, tmem_base == 0u);                 // the 512-column allocation starts at TMEM address 0
+      if (!ok && lane == 0) atomicOr(a.error, 16);
       uint32_t tc = 0, vc = 0, wc = 0;
       for (int item = blockIdx.x; item < a.n_items && ok; item += gridDim.x, tc += UT) {
-        for (int jj = 0; jj < MT && ok; ++jj) ok = r3_mbar_wait(&aempty[(tc + jj) & 1u], (((tc + jj) >> 1) & 1u) ^ 1u, a.error);
+        for (int jj = 0; jj < MT && ok; ++jj) ok = r3_mbar_wait_w(&aempty[(tc + jj) & 1u], (((tc + jj) >> 1) & 1u) ^ 1u, a.error);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int cb = 0; cb < a.cblocks && ok; ++cb) {
           for (int v = 0; v < 6 && ok; ++v, ++vc) {
             const uint32_t vs = vc % VST;
-            ok = r3_mbar_wait(&vfull[vs], (vc / VST) & 1u, a.error);
+            ok = r3_mbar_wait_w(&vfull[vs], (vc / VST) & 1u, a.error);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // weight tiles served by this variant, in ring order: [tap (r=0), (projection if v == 0), tap (r=2) if the plane row p == 0]
             const int ntiles = v == 0 ? 3 : (v < 3 ? 2 : 1);
             for (int e = 0; e < ntiles && ok; ++e, ++wc) {
               const uint32_t ws = wc % WST;
-              ok = r3_mbar_wait(&wfull[ws], (wc / WST) & 1u, a.error);
+              ok = r3_mbar_wait_w(&wfull[ws], (wc / WST) & 1u, a.error);
               asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
               const bool is_proj = (v == 0 && e == 1);
               const int ro = (v == 0) ? (e == 2) : (v < 3 ? (e == 1) : 0);      // the r = 2 tap of a p == 0 plane reads plane row y' + 1
@@ -710,20 +745,16 @@ __global__ void __launch_bounds__(R3_THREADS, 1) conv3x3s2_res_kernel(const __gr
 #pragma unroll
               for (int jj = 0; jj < MT; ++jj) {
                 const uint32_t ts = (tc + jj) & 1u;
-                const uint32_t tmem_d = tmem_base + ts * 256 + (is_proj ? 128u : 0u);
+                const uint32_t tmem_d = ts * 256 + (is_proj ? 128u : 0u);   // TMEM base is 0
                 const uint64_t ad = desc_hi | (uint64_t)(v_lo + ((vs * VSTAGE + jj * PATCH + ro * ROWB) >> 4));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const uint32_t acc = is_proj ? (uint32_t)((cb | k) != 0) : (uint32_t)(!(first_conv && k == 0));
-                  r3_mma(tmem_d, ad + 2 * k, bd + 2 * k, idesc, acc);
-                }
+                r3_mma_x4(tmem_d, ad, bd, idesc, is_proj ? (uint32_t)(cb != 0) : (uint32_t)(!first_conv));
               }
-              r3_commit(&wempty[ws]);
+              r3_commit_w(&wempty[ws]);
             }
-            r3_commit(&vempty[vs]);
+            r3_commit_w(&vempty[vs]);
           }
         }
-        for (int jj = 0; jj < MT; ++jj) { if (ok) r3_commit(&afull[(tc + jj) & 1u]); else r3_mbar_arrive(&afull[(tc + jj) & 1u]); }
+        for (int jj = 0; jj < MT; ++jj) { if (ok) r3_commit_w(&afull[(tc + jj) & 1u]); else r3_arrive_w(&afull[(tc + jj) & 1u]); }
       }
     }
   } else if (warp == 9) {

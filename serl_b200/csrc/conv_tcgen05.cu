@@ -78,6 +78,24 @@ __device__ inline void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bde
   asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// four k-steps of one k-block in ONE asm statement (see r3_mma_x4 in conv3x3_res.cu: the per-statement operand
+// uniformisation, not the tensor pipe, bounded the single-thread issue loops)
+__device__ inline void tc_mma_x4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate_first) {
+  // whole (converged) issuer warp, warp-uniform operands, one elected lane issues
+  asm volatile("{\n .reg .pred p, t, e;\n .reg .b64 a1, a2, a3, b1, b2, b3;\n"
+               " elect.sync _|e, 0xffffffff;\n"
+               " setp.ne.b32 p, %4, 0;\n setp.eq.u32 t, 0, 0;\n"
+               " add.u64 a1, %1, 2;\n add.u64 b1, %2, 2;\n add.u64 a2, %1, 4;\n add.u64 b2, %2, 4;\n add.u64 a3, %1, 6;\n add.u64 b3, %2, 6;\n"
+               " @e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+               " @e tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, t;\n"
+               " @e tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, t;\n"
+               " @e tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, t;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first) : "memory");
+}
+__device__ inline void tc_commit_w(uint64_t* bar) {           // one elected lane of the converged issuer warp
+  asm volatile("{\n .reg .pred e;\n elect.sync _|e, 0xffffffff;\n"
+               " @e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ inline void tc_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -617,7 +635,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) stem_tc_kernel(const __grid_con
 // ---------------------------------------------------------------------------------------------
 constexpr int S2_RING = 16;
 constexpr int S2_ROW_BYTES = 8192;                                               // [v 4][j 16][128 B]
-constexpr int S2_ACC = 4;
+constexpr int S2_ACC = 8;                                                      // all 512 TMEM columns: the allocation starts at address 0
 constexpr int S2_UNIT_ROWS = 19;                                                 // s2d rows of an 8-tile unit (16 output rows + 3)
 
 __device__ inline void s2_tma_5d(void* smem_dst, const CUtensorMap* map, int c3, int c4, uint64_t* bar) {
@@ -754,36 +772,39 @@ __global__ void __launch_bounds__(TC_THREADS, 1) stem2_tc_kernel(const __grid_co
       }
     }
   } else if (warp == 8) {
-    // ------------------------------- MMA issuer (one thread) ------------------------------
-    if (lane == 0) {
+    // ------------------------------- MMA issuer (whole warp, converged; one elected lane issues) ------------------------------
+    // warp-uniform operands + convergent control flow keep descriptors / TMEM addresses in uniform registers (see r3_mma_x4 in
+    // conv3x3_res.cu); the 512-column TMEM allocation starts at address 0 by construction
+    {
       const uint32_t idesc = (1u << 4) | (F::kUmmaFormat << 7) | (F::kUmmaFormat << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       const uint64_t desc_hi = (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
       const uint32_t r_lo = (smem_u32(sRing) & 0x3FFFF) >> 4, w_lo = (smem_u32(sW) & 0x3FFFF) >> 4;
-      bool ok = tc_mbar_wait(wfull, 0u, a.error);
+      bool ok = __all_sync(0xffffffffu, tmem_base == 0u);
+      if (!ok && lane == 0) atomicOr(a.error, 16);
+      ok = ok && __all_sync(0xffffffffu, tc_mbar_wait(wfull, 0u, a.error));
       int ac = 0;
       uint32_t cbase = 0;                                        // ring counter of the unit's first row
       for (int u = blockIdx.x; u < n_units && ok; u += gridDim.x, cbase += S2_UNIT_ROWS) {
         for (int tt = 0; tt < 8 && ok; ++tt, ++ac) {
           const int as = ac & (S2_ACC - 1);
-          ok = tc_mbar_wait(&aempty[as], (uint32_t)((ac / S2_ACC) & 1) ^ 1u, a.error);
+          ok = __all_sync(0xffffffffu, tc_mbar_wait(&aempty[as], (uint32_t)((ac / S2_ACC) & 1) ^ 1u, a.error));
           for (int i = (tt == 0 ? 0 : 3); i < 5 && ok; ++i) {    // rows 2tt .. 2tt+4; all but the last two were waited for by earlier tiles
             const uint32_t r = cbase + 2 * tt + i;
-            ok = tc_mbar_wait(&rfull[r & (S2_RING - 1)], (r / S2_RING) & 1u, a.error);
+            ok = __all_sync(0xffffffffu, tc_mbar_wait(&rfull[r & (S2_RING - 1)], (r / S2_RING) & 1u, a.error));
           }
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t tmem_d = tmem_base + (uint32_t)(as * BN);
+          const uint32_t tmem_d = (uint32_t)(as * BN);           // TMEM base is 0
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {
             const uint32_t slot = (cbase + 2 * tt + kb) & (S2_RING - 1);    // rows (slot, slot + 1): slot + 1 == S2_RING is the mirror of slot 0
             const uint64_t ad = desc_hi | (uint64_t)(r_lo + slot * (S2_ROW_BYTES >> 4));
             const uint64_t bd = desc_hi | (uint64_t)(w_lo + (uint32_t)kb * (W_TILE >> 4));
-#pragma unroll
-            for (int k = 0; k < TC_BK / 16; ++k) tc_mma_bf16(tmem_d, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((kb | k) != 0));
+            tc_mma_x4(tmem_d, ad, bd, idesc, (uint32_t)(kb != 0));
           }
           // rows 2tt, 2tt+1 are not read by later tiles (the unit's last tile also releases its three tail rows)
           const int nrel = tt == 7 ? 5 : 2;
-          for (int i = 0; i < nrel; ++i) tc_commit(&rempty[(cbase + 2 * tt + i) & (S2_RING - 1)]);
-          if (ok) tc_commit(&afull[as]); else tc_mbar_arrive(&afull[as]);
+          for (int i = 0; i < nrel; ++i) tc_commit_w(&rempty[(cbase + 2 * tt + i) & (S2_RING - 1)]);
+          tc_commit_w(&afull[as]);
         }
       }
     }
