@@ -1200,10 +1200,10 @@ extern "C" int serl_conv2d_tc_h16(const serl_conv_tc_desc* d, void* stream) {
   return d->fmt == SERL_FMT_FP16 ? conv_tc_dispatch<Fp16>(d, a, ST(stream)) : conv_tc_dispatch<Bf16>(d, a, ST(stream));
 }
 
-static int g_stem_v2 = -1;                                    // -1: read SERL_STEM_V2 at the first call
+static int g_stem_v2 = -1;                                    // -1: read SERL_STEM_V2 at the first call (default on; SERL_STEM_V2=0 selects round 1's stem)
 /* 1 if the fused stem runs (will run) the TMA-im2col kernel stem2_tc_kernel, 0 for round 1's stem_tc_kernel<., true> */
 extern "C" int serl_stem_v2_active(void) {
-  if (g_stem_v2 < 0) { const char* e = getenv("SERL_STEM_V2"); g_stem_v2 = (e && atoi(e) != 0) ? 1 : 0; }
+  if (g_stem_v2 < 0) { const char* e = getenv("SERL_STEM_V2"); g_stem_v2 = (e && atoi(e) == 0) ? 0 : 1; }
   return g_stem_v2;
 }
 
@@ -1218,9 +1218,9 @@ extern "C" int serl_stem_conv_pool_tc_h16(const serl_stem_pool_desc* d, void* st
   a.N = d->N; a.Hi = 67; a.Wi = 67; a.Ci = 12; a.Co = 64; a.kh = 4; a.kw = 4; a.stride = 1; a.pad = 0;
   a.Ho = 64; a.Wo = 64; a.M = d->N * 64 * 64; a.Cg = 16; a.num_kb = 4; a.cblocks = 1;
   { static int dbg = -1; if (dbg < 0) { const char* e = getenv("SERL_TC_DEBUG"); dbg = e ? atoi(e) : 0; } a.debug = dbg; }
-  // v2 (TMA-built im2col, row ring) with SERL_STEM_V2=1 unless the driver refuses its tensor map; v1 (shared->shared im2col) otherwise
+  // v2 (TMA-built im2col, row ring; default) unless SERL_STEM_V2=0 or the driver refuses its tensor map; v1 (shared->shared im2col) otherwise
   int& v2 = g_stem_v2;
-  if (v2 < 0) { const char* e = getenv("SERL_STEM_V2"); v2 = (e && atoi(e) != 0) ? 1 : 0; }
+  if (v2 < 0) { const char* e = getenv("SERL_STEM_V2"); v2 = (e && atoi(e) == 0) ? 0 : 1; }
   if (v2 && !a.debug) {
     const int rc = d->fmt == SERL_FMT_FP16 ? launch_stem2_tc<Fp16>(a, d->fmt, ST(stream)) : launch_stem2_tc<Bf16>(a, d->fmt, ST(stream));
     if (rc != SERL_ERR_UNSUPPORTED) return rc;

@@ -93,7 +93,7 @@ class Engine:
         # for the block's projection conv.  At batch 256 the persistent conv kernels fill the GPU and the passes serialise; at
         # the small per-rank batches of data-parallel runs (32 rows per rank on 8 GPUs) a trunk kernel covers a fraction of the
         # SMs and the cameras overlap.
-        self.cam_stream = {c: (L.new_side_stream(dev, streams_on and os.environ.get("SERL_CAM_STREAMS", "0") != "0") if j > 0 else None)
+        self.cam_stream = {c: (L.new_side_stream(dev, streams_on and os.environ.get("SERL_CAM_STREAMS", "1") != "0") if j > 0 else None)
                            for j, c in enumerate(cfg.cams)}
         self.proj_side = {c: L.new_side_stream(dev, streams_on and os.environ.get("SERL_PROJ_SIDE", "1") != "0") for c in cfg.cams}
         self.ws_side = [ops.Workspace(ws_bytes, device, gemm_impl) for _ in range(2)]

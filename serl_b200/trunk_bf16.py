@@ -38,11 +38,11 @@ GN_EPS = 1e-5
 # Stride-1 3x3 convs with GroupNorm (+ residual) (+ ReLU) inside the conv kernel (conv3x3_res.cu): an image's accumulators stay
 # in tensor memory until its statistics are complete, so neither the raw conv output nor a normalisation pass touches HBM
 # (no affine_relu after ResNetBlock_0/Conv_0, no block_combine after any Conv_1).  SERL_RES_CONV=0 selects round 1's path.
-USE_RES_CONV = os.environ.get("SERL_RES_CONV", "0") != "0"
+USE_RES_CONV = os.environ.get("SERL_RES_CONV", "1") != "0"
 
 # Head of ResNetBlock_1..3 (stride-2 3x3 conv + GN + ReLU AND the 1x1 stride-2 projection + GN) in one kernel
 # (conv3x3s2_res_kernel): no separate projection conv, no affine_relu pass.  Needs USE_RES_CONV.  SERL_RES_S2=0 keeps round 1's kernels.
-USE_RES_S2 = os.environ.get("SERL_RES_S2", "0") != "0"
+USE_RES_S2 = os.environ.get("SERL_RES_S2", "1") != "0"
 
 # The 1x1 / stride-2 projection conv of a block only depends on the block input: run it on a side stream next to the
 # conv -> GroupNorm+ReLU -> conv chain (joined before the residual add).
