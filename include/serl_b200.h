@@ -196,6 +196,70 @@ int serl_gemm_f32(const serl_gemm_desc* d, void* stream);
  * per k-step accumulated in fp32 TMEM ("3xTF32": fp32-class accuracy, ~2^-22 per product).  Heads of the 16-bit builds. */
 int serl_gemm_tf32x3(const serl_gemm_desc* d, void* stream);
 
+/* Heads of the 16-bit builds, round 2: single-pass TF32 GEMM (tcgen05 kind::tf32, operands by TMA straight from the fp32
+ * tensors: X @ W, dZ @ W^T and X^T @ dZ of a Dense layer all read the row-major arrays in place) with fused epilogues.
+ * Replaces, per launch, Dense (+ bias) [+ LayerNorm + tanh [+ value head | + policy heads + tanh-Gaussian sample]] of
+ * networks/mlp.py:22-31, networks/actor_critic_nets.py:57-73,178-227,230-272, vision/resnet_v1.py:371-374.
+ * C[z](m, n) = sum_k A[z](m, k) B[z](k, n); element strides in floats; per operand one of its two strides must be 1 and the
+ * other a multiple of 4, base pointers 16-byte aligned (TMA), z stride 0 = the operand is shared by the Z members.
+ * Up to SERL_TGEMM_MAX_PROBLEMS problems (same M, N, K, operand layouts and epilogue) per launch. */
+#define SERL_TGEMM_MAX_PROBLEMS 6
+#define SERL_TGEMM_EPI_STORE 0            /* C = acc + bias (+ C)                                                        */
+#define SERL_TGEMM_EPI_LN_TANH 1          /* N == 256: C = tanh(LayerNorm(acc + bias) * scale + ln_bias); optional xhat, rstd */
+#define SERL_TGEMM_EPI_LN_TANH_HEAD 2     /* ... and head_out[m, :head_n] = C[m, :] @ head_w (256, head_n) + head_b        */
+#define SERL_TGEMM_EPI_LN_TANH_POLICY 3   /* ... two heads (means, log-stds) -> clipped std, u = mu + std * noise, act = tanh(u), logp */
+typedef struct serl_tgemm_problem {
+  const float* A; const float* B;
+  int64_t sAz, sAm, sAk, sBz, sBk, sBn;
+  int32_t Z;
+  float* C; int64_t sCz; int32_t ldc;            /* may be NULL for the LayerNorm epilogues (activation not kept)          */
+  const float* bias; int64_t sBiasZ;
+  const float* ln_scale; const float* ln_bias; int64_t sLnZ;
+  float* xhat; float* rstd; int64_t sXhatZ, sRstdZ;   /* optional saves for the backward pass: xhat (M, 256), rstd (M)     */
+  const float* head_w; const float* head_b; int64_t sHeadWz, sHeadBz;
+  float* head_out; int64_t sHeadOutZ; int32_t ld_head;  /* HEAD: (M, head_n) with row stride ld_head; POLICY: means (M, A)   */
+  const float* head_w2; const float* head_b2; float* head_out2;   /* POLICY: log-std head and its raw output (M, A)        */
+  const float* noise; float* act; int32_t ld_act; float* logp; float* u_out; float* std_out;   /* POLICY (Z == 1)          */
+} serl_tgemm_problem;
+typedef struct serl_tgemm_desc {
+  const serl_tgemm_problem* problems; int32_t num_problems;   /* HOST array                                                */
+  int32_t M, N, K;
+  int32_t epilogue, head_n;
+  int32_t accumulate, reduce_z, splits;          /* splits: 0 = automatic k-split (one problem per launch when > 1)        */
+  float ln_eps, std_min, std_max; int32_t deterministic;
+  float* workspace; size_t workspace_bytes;      /* k-split / reduce_z partials                                           */
+  int32_t* error;                                /* device int32, OR-ed with 32 if a pipeline barrier timed out             */
+} serl_tgemm_desc;
+int serl_tgemm_tf32(const serl_tgemm_desc* d, void* stream);
+
+/* Batched companions of serl_tgemm_tf32 (csrc/heads_fused.cu): one launch over every problem of a step. */
+#define SERL_HEADS_MAX_PROBLEMS 8
+typedef struct serl_sle_problem {             /* SpatialLearnedEmbeddings (+ Dropout keep mask), vision/resnet_v1.py:81-116,352 */
+  const float* feat; const float* kernel; const uint8_t* keep_mask; float* out; int32_t ld_out;
+} serl_sle_problem;
+int serl_sle_fwd_multi(const serl_sle_problem* problems /*host*/, int num_problems, float keep, int N, int P, int C, int F, void* stream);
+typedef struct serl_enc_finish_problem {      /* out = tanh(LayerNorm(z + bias) * scale + ln_bias), z from k-split partials or a small dense */
+  const float* partials; int32_t S;           /* (S, rows, D) partial products of serl_tgemm_tf32, or NULL                      */
+  const float* x; int32_t ld_x; const float* w; int32_t K;   /* else z = x (rows, K) @ w (K, D): the proprio Dense, encoding.py:65 */
+  const float* bias; const float* ln_scale; const float* ln_bias;
+  float* out; int32_t ld_out; float* xhat; float* rstd; int32_t D;   /* D <= 256                                                  */
+} serl_enc_finish_problem;
+int serl_enc_finish(const serl_enc_finish_problem* problems /*host*/, int num_problems, int rows, float eps, void* stream);
+typedef struct serl_ln_bwd_problem {          /* LayerNorm + tanh backward; upstream gradient dt (+ dt2), or dq[row] * head_w[group][d] */
+  const float* dt; int32_t ld_dt; const float* dt2; int32_t ld_dt2; const float* dq; const float* head_w; int64_t head_w_stride;
+  const float* t; int32_t ld_t; const float* xhat; const float* rstd; const float* scale; int32_t rows_per_group; int64_t group_stride;
+  float* dz; float* dy; int32_t R, D;
+} serl_ln_bwd_problem;
+int serl_layernorm_tanh_bwd_multi(const serl_ln_bwd_problem* problems /*host*/, int num_problems, void* stream);
+#define SERL_SMALL_GRAD_MAX_JOBS 12
+#define SERL_SMALL_GRAD_COLSUM 0              /* out_a[g][d] = sum_r x[g*rows + r][d]                     (bias gradients)         */
+#define SERL_SMALL_GRAD_LN 1                  /* out_a = sum_r x*y (scale), out_b = sum_r x (bias)        (x = dy, y = xhat)        */
+#define SERL_SMALL_GRAD_HEAD 2                /* out_a[g][d] = sum_r x[r][d] * y[r], out_b[g] = sum_r y[r] (x = h, y = dq: value head) */
+typedef struct serl_small_grad_job {
+  int32_t kind; const float* x; int64_t ld_x; const float* y; int64_t ld_y; float* out_a; float* out_b; int32_t groups, rows, D;
+} serl_small_grad_job;
+int serl_small_grads(const serl_small_grad_job* jobs /*host*/, int num_jobs, void* stream);
+
 /* SpatialLearnedEmbeddings (vision/resnet_v1.py:81-116) + Dropout (resnet_v1.py:352) */
 int serl_sle_fwd(const float* feat, const float* kernel, const uint8_t* keep_mask, float keep, float* out,
                  int N, int P, int C, int F, int ld_out, void* stream);

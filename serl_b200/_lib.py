@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libserl_b200.so")
 MAX_CAMS = 4
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 (KEY_CROP_OBS, KEY_CROP_NEXT, KEY_CRITIC_NEXT, KEY_CRITIC_SUBSAMPLE, KEY_ACTOR_DROPOUT, KEY_ACTOR_SAMPLE,
  KEY_TEMP_NEXT) = range(7)
@@ -50,6 +50,45 @@ class GemmDesc(C.Structure):
                 ("M", i32), ("N", i32), ("K", i32), ("Z", i32),
                 ("sAz", i64), ("sAm", i64), ("sAk", i64), ("sBz", i64), ("sBk", i64), ("sBn", i64), ("sCz", i64),
                 ("sBiasZ", i64), ("ldc", i32), ("accumulate", i32), ("reduce_z", i32)]
+
+
+class TgemmProblem(C.Structure):
+    _fields_ = [("A", vp), ("B", vp), ("sAz", i64), ("sAm", i64), ("sAk", i64), ("sBz", i64), ("sBk", i64), ("sBn", i64), ("Z", i32),
+                ("C", vp), ("sCz", i64), ("ldc", i32), ("bias", vp), ("sBiasZ", i64), ("ln_scale", vp), ("ln_bias", vp), ("sLnZ", i64),
+                ("xhat", vp), ("rstd", vp), ("sXhatZ", i64), ("sRstdZ", i64), ("head_w", vp), ("head_b", vp), ("sHeadWz", i64),
+                ("sHeadBz", i64), ("head_out", vp), ("sHeadOutZ", i64), ("ld_head", i32), ("head_w2", vp), ("head_b2", vp),
+                ("head_out2", vp), ("noise", vp), ("act", vp), ("ld_act", i32), ("logp", vp), ("u_out", vp), ("std_out", vp)]
+
+
+class TgemmDesc(C.Structure):
+    _fields_ = [("problems", C.POINTER(TgemmProblem)), ("num_problems", i32), ("M", i32), ("N", i32), ("K", i32), ("epilogue", i32),
+                ("head_n", i32), ("accumulate", i32), ("reduce_z", i32), ("splits", i32), ("ln_eps", f32), ("std_min", f32),
+                ("std_max", f32), ("deterministic", i32), ("workspace", vp), ("workspace_bytes", C.c_size_t), ("error", vp)]
+
+
+class SleProblem(C.Structure):
+    _fields_ = [("feat", vp), ("kernel", vp), ("keep_mask", vp), ("out", vp), ("ld_out", i32)]
+
+
+class EncFinishProblem(C.Structure):
+    _fields_ = [("partials", vp), ("S", i32), ("x", vp), ("ld_x", i32), ("w", vp), ("K", i32), ("bias", vp), ("ln_scale", vp), ("ln_bias", vp),
+                ("out", vp), ("ld_out", i32), ("xhat", vp), ("rstd", vp), ("D", i32)]
+
+
+class LnBwdProblem(C.Structure):
+    _fields_ = [("dt", vp), ("ld_dt", i32), ("dt2", vp), ("ld_dt2", i32), ("dq", vp), ("head_w", vp), ("head_w_stride", i64),
+                ("t", vp), ("ld_t", i32), ("xhat", vp), ("rstd", vp), ("scale", vp), ("rows_per_group", i32), ("group_stride", i64),
+                ("dz", vp), ("dy", vp), ("R", i32), ("D", i32)]
+
+
+class SmallGradJob(C.Structure):
+    _fields_ = [("kind", i32), ("x", vp), ("ld_x", i64), ("y", vp), ("ld_y", i64), ("out_a", vp), ("out_b", vp), ("groups", i32),
+                ("rows", i32), ("D", i32)]
+
+
+SMALL_GRAD_COLSUM, SMALL_GRAD_LN, SMALL_GRAD_HEAD = range(3)
+TGEMM_STORE, TGEMM_LN_TANH, TGEMM_LN_TANH_HEAD, TGEMM_LN_TANH_POLICY = range(4)
+TGEMM_MAX_PROBLEMS = 6
 
 
 class ConvTcDesc(C.Structure):
@@ -116,6 +155,11 @@ _PROTOS = {
     "serl_block_combine_h16": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_gemm_f32": [C.POINTER(GemmDesc), vp],
     "serl_gemm_tf32x3": [C.POINTER(GemmDesc), vp],
+    "serl_tgemm_tf32": [C.POINTER(TgemmDesc), vp],
+    "serl_sle_fwd_multi": [C.POINTER(SleProblem), C.c_int, f32, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "serl_enc_finish": [C.POINTER(EncFinishProblem), C.c_int, C.c_int, f32, vp],
+    "serl_layernorm_tanh_bwd_multi": [C.POINTER(LnBwdProblem), C.c_int, vp],
+    "serl_small_grads": [C.POINTER(SmallGradJob), C.c_int, vp],
     "serl_sle_fwd": [vp, vp, vp, f32, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_sle_bwd_kernel_grad": [vp, vp, vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_layernorm_tanh_fwd": [vp, C.c_int, vp, vp, C.c_int, C.c_int, vp, C.c_int, vp, vp, C.c_int, C.c_int, f32, vp],

@@ -42,7 +42,7 @@ bool pdl_enabled() {
 }  // namespace serl
 
 extern "C" const char* serl_last_error(void) { return serl::g_err; }
-extern "C" int serl_version(void) { return 2; }
+extern "C" int serl_version(void) { return 3; }
 extern "C" unsigned long long serl_launch_count(void) { return serl::launch_count(); }
 extern "C" int serl_set_pdl(int enabled) { serl::g_pdl = enabled ? 1 : 0; return SERL_OK; }
 extern "C" int serl_device_sm_count(int device) {

@@ -194,3 +194,33 @@ def adam_polyak(params, target, m, v, grad, seg_end: Sequence[int], live: Sequen
     d.b1, d.b2, d.eps, d.tau, d.polyak = b1, b2, eps, float(tau), int(polyak)
     d.lr_out = _p(lr_out)
     L.call("serl_adam_polyak", C.byref(d), _s())
+
+
+# ---- single-pass TF32 GEMM with TMA-fed operands and fused epilogues (heads of the 16-bit builds) -------------------
+def tgemm_problem(A, B, *, sAm, sAk, sBk, sBn, Z=1, sAz=0, sBz=0, C_=None, sCz=0, ldc=0, bias=None, sBiasZ=0, ln_scale=None,
+                  ln_bias=None, sLnZ=0, xhat=None, rstd=None, sXhatZ=0, sRstdZ=0, head_w=None, head_b=None, sHeadWz=0, sHeadBz=0,
+                  head_out=None, sHeadOutZ=0, ld_head=1, head_w2=None, head_b2=None, head_out2=None, noise=None, act=None, ld_act=0,
+                  logp=None, u_out=None, std_out=None):
+    """One problem of a serl_tgemm_tf32 launch; every operand is a device ADDRESS (int) or None, strides in floats."""
+    p = L.TgemmProblem()
+    p.A, p.B, p.sAz, p.sAm, p.sAk, p.sBz, p.sBk, p.sBn, p.Z = A, B, sAz, sAm, sAk, sBz, sBk, sBn, Z
+    p.C, p.sCz, p.ldc, p.bias, p.sBiasZ = C_, sCz, ldc, bias, sBiasZ
+    p.ln_scale, p.ln_bias, p.sLnZ, p.xhat, p.rstd, p.sXhatZ, p.sRstdZ = ln_scale, ln_bias, sLnZ, xhat, rstd, sXhatZ, sRstdZ
+    p.head_w, p.head_b, p.sHeadWz, p.sHeadBz, p.head_out, p.sHeadOutZ, p.ld_head = head_w, head_b, sHeadWz, sHeadBz, head_out, sHeadOutZ, ld_head
+    p.head_w2, p.head_b2, p.head_out2 = head_w2, head_b2, head_out2
+    p.noise, p.act, p.ld_act, p.logp, p.u_out, p.std_out = noise, act, ld_act, logp, u_out, std_out
+    return p
+
+
+def tgemm(ws: Optional[Workspace], problems, M, N, K, *, epilogue=L.TGEMM_STORE, head_n=0, accumulate=False, reduce_z=False, splits=0,
+          ln_eps=1e-6, std_min=1e-5, std_max=5.0, deterministic=False, error=None):
+    """C[z] = A[z] @ B[z] on the tensor cores (TF32, fp32 accumulate) for up to 6 problems of one shape; see include/serl_b200.h."""
+    arr = (L.TgemmProblem * len(problems))(*problems)
+    d = L.TgemmDesc()
+    d.problems, d.num_problems, d.M, d.N, d.K = arr, len(problems), M, N, K
+    d.epilogue, d.head_n, d.accumulate, d.reduce_z, d.splits = epilogue, head_n, int(accumulate), int(reduce_z), splits
+    d.ln_eps, d.std_min, d.std_max, d.deterministic = float(ln_eps), float(std_min), float(std_max), int(deterministic)
+    if ws is not None:
+        d.workspace, d.workspace_bytes = ws.buf.data_ptr(), ws.nbytes
+    d.error = _p(error)
+    L.call("serl_tgemm_tf32", C.byref(d), _s())
