@@ -207,6 +207,7 @@ int serl_gemm_tf32x3(const serl_gemm_desc* d, void* stream);
 #define SERL_TGEMM_EPI_STORE 0            /* C = acc + bias (+ C)                                                        */
 #define SERL_TGEMM_EPI_LN_TANH 1          /* N == 256: C = tanh(LayerNorm(acc + bias) * scale + ln_bias); optional xhat, rstd */
 #define SERL_TGEMM_EPI_LN_TANH_HEAD 2     /* ... and head_out[m, :head_n] = C[m, :] @ head_w (256, head_n) + head_b        */
+#define SERL_TGEMM_EPI_PARTIAL 4          /* k-split partial products left in the workspace [(member * splits + s)][M][N] for serl_enc_finish */
 #define SERL_TGEMM_EPI_LN_TANH_POLICY 3   /* ... two heads (means, log-stds) -> clipped std, u = mu + std * noise, act = tanh(u), logp */
 typedef struct serl_tgemm_problem {
   const float* A; const float* B;
@@ -233,7 +234,7 @@ typedef struct serl_tgemm_desc {
 int serl_tgemm_tf32(const serl_tgemm_desc* d, void* stream);
 
 /* Batched companions of serl_tgemm_tf32 (csrc/heads_fused.cu): one launch over every problem of a step. */
-#define SERL_HEADS_MAX_PROBLEMS 8
+#define SERL_HEADS_MAX_PROBLEMS 12
 typedef struct serl_sle_problem {             /* SpatialLearnedEmbeddings (+ Dropout keep mask), vision/resnet_v1.py:81-116,352 */
   const float* feat; const float* kernel; const uint8_t* keep_mask; float* out; int32_t ld_out;
 } serl_sle_problem;

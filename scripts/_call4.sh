@@ -1,0 +1,15 @@
+set -u
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_fused_heads_gpu.py tests/test_tgemm_gpu.py -m gpu -q -x -s --timeout=600 -p no:cacheprovider > gpurun_out/pytest_fused.log 2>&1; echo "fused rc=$?"; grep -E "step|passed|failed|Error|error|assert" gpurun_out/pytest_fused.log | tail -30
+timeout 900 python -m pytest tests/test_b256_fp16_gpu.py tests/test_agent_gpu.py tests/test_dp_gpu.py -m gpu -q --timeout=600 -p no:cacheprovider 2>&1 | tail -8
+for cfg in SERL_FUSED_HEADS=1 SERL_FUSED_HEADS=0; do
+env $cfg SERL_BENCH_SKIP_SINGLE=1 SERL_BENCH_SKIP_CPU=1 timeout 600 python bench.py --steps 50 --warmup 3 > gpurun_out/bench4.log 2> gpurun_out/bench4.err
+echo "[$cfg] rc=$? $(python -c "
+import json
+try:
+    d=[json.loads(l) for l in open('gpurun_out/bench4.log') if l.startswith('{')][-1]
+    print('value %.1f sus %.1f e2e %.1f launches %d trunk_ms %.3f frac %.3f sections %s' % (d['value'], d['sustained']['value'], d['e2e']['value'], d['gpu_launches'], d['roofline']['ms_per_step'], d['roofline']['frac'], {k: v for k, v in d['sections_ms'].items() if k != 'note'}))
+except Exception as e:
+    print('no line', e)
+")"; tail -3 gpurun_out/bench4.err
+done

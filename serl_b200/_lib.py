@@ -87,7 +87,7 @@ class SmallGradJob(C.Structure):
 
 
 SMALL_GRAD_COLSUM, SMALL_GRAD_LN, SMALL_GRAD_HEAD = range(3)
-TGEMM_STORE, TGEMM_LN_TANH, TGEMM_LN_TANH_HEAD, TGEMM_LN_TANH_POLICY = range(4)
+TGEMM_STORE, TGEMM_LN_TANH, TGEMM_LN_TANH_HEAD, TGEMM_LN_TANH_POLICY, TGEMM_PARTIAL = range(5)
 TGEMM_MAX_PROBLEMS = 6
 
 

@@ -366,6 +366,8 @@ class SACAgent:
         for eng in self._engines.values():
             if int(eng.status.item()):
                 raise L.SerlError("replay draw failed: no valid slot within the redraw budget")
+            if getattr(eng, "fused", None) is not None:
+                eng.fused.check_error()
 
     def update_high_utd(self, batch, *, utd_ratio: int, pmap_axis: Optional[str] = None, _augment: bool = False):
         """sac.py:544-596: utd_ratio critic updates on consecutive minibatches, then one actor+temperature update

@@ -7,7 +7,7 @@
 //     (both MN-major) - forward, input gradient and weight gradient of a Dense layer (networks/mlp.py:22-31 and its jax.grad
 //     transposes) - all read the same row-major fp32 arrays the rest of the step uses;
 //   * one CTA per 128 x 256 output tile (x k-split x batch member): warp 0 = TMA producer, warp 1 = MMA issuer (whole warp
-//     converged, one elected lane issues, uniform-register operands), warps 2-5 = epilogue (TMEM lane = output row);
+//     converged, one elected lane issues, uniform-register operands), warps 2-9 = epilogue (TMEM lane = output row, two warps per lane quarter);
 //   * fused epilogues: bias; bias + LayerNorm(eps 1e-6, fast variance) + tanh with the statistics the backward pass needs
 //     (an output row is one TMEM lane, so the row reductions are thread-local); + the value head (Q = h . w + b,
 //     networks/actor_critic_nets.py:64-72) or the policy's mean / log-std heads with the tanh-Gaussian sample and its
@@ -24,7 +24,8 @@ namespace serl {
 
 constexpr int TG_BM = 128, TG_BN = 256, TG_BK = 32;           // 32 fp32 = 128 B = one swizzle row
 constexpr int TG_STAGES = 4;
-constexpr int TG_THREADS = 192;
+constexpr int TG_THREADS = 320;                               // TMA warp + MMA warp + 8 epilogue warps
+constexpr int TG_EPI_THREADS = 256;
 constexpr int TG_MAXG = SERL_TGEMM_MAX_PROBLEMS;
 constexpr int TG_A_STAGE = TG_BM * 128, TG_B_STAGE = TG_BN * 128, TG_STAGE = TG_A_STAGE + TG_B_STAGE;
 constexpr int TG_MAXHEAD = 8;
@@ -102,6 +103,8 @@ __device__ inline void tg_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the special-function unit (ex2.approx + rcp.approx): absolute error < 3e-7, exact limits
+__device__ inline float tg_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f); }
 __device__ inline float tg_softplus(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
 
 __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_constant__ TgMaps maps, const __grid_constant__ TgArgs a) {
@@ -196,34 +199,41 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
     }
     if (ok && nk > 0) tg_commit_w(done); else tg_arrive_w(done);
   } else {
-    // =============================== epilogue: thread = output row (TMEM lane) ===============================
-    const int et = threadIdx.x - 64;                                     // 0..127
+    // =============================== epilogue: 8 warps, thread = (output row = TMEM lane, column half) ===============================
+    // Two warps per TMEM lane quarter, 128 columns each: with one warp per scheduler the dependent chains of the LayerNorm /
+    // tanh arithmetic ran at a fraction of the issue rate; the two halves of a row meet through shared memory.
+    const int et = threadIdx.x - 64;                                     // 0..255
     const int q = warp & 3;                                              // TMEM lane quarter this warp may access
+    const int hh = (warp - 2) >> 2;                                      // column half
     const int row = q * 32 + lane, m = m0 + row;
-    const bool ln = a.epi != SERL_TGEMM_EPI_STORE;
+    const int c_lo = hh * (TG_BN / 2), c_hi = c_lo + TG_BN / 2;
+    const bool ln = a.epi >= SERL_TGEMM_EPI_LN_TANH && a.epi <= SERL_TGEMM_EPI_LN_TANH_POLICY;
     // stage the epilogue vectors while the main loop runs
     if (!a.to_ws) {
       const float* bias = g.bias ? g.bias + z * g.sBiasZ : nullptr;
-      for (int c = et; c < TG_BN; c += 128) {
+      for (int c = et; c < TG_BN; c += TG_EPI_THREADS) {
         const int n = n0 + c;
         sBias[c] = (bias && n < a.N) ? bias[n] : 0.f;
         if (ln) { sLs[c] = g.ln_scale[z * g.sLnZ + n]; sLb[c] = g.ln_bias[z * g.sLnZ + n]; }
       }
-      if (a.epi >= SERL_TGEMM_EPI_LN_TANH_HEAD) {
+      if (ln && a.epi >= SERL_TGEMM_EPI_LN_TANH_HEAD) {
         const float* hw = g.head_w + z * g.sHeadWz;
-        for (int i = et; i < TG_BN * a.head_n; i += 128) sHw[i] = hw[i];
+        for (int i = et; i < TG_BN * a.head_n; i += TG_EPI_THREADS) sHw[i] = hw[i];
         if (et < a.head_n) sHb[et] = g.head_b ? g.head_b[z * g.sHeadBz + et] : 0.f;
         if (a.epi == SERL_TGEMM_EPI_LN_TANH_POLICY) {
-          for (int i = et; i < TG_BN * a.head_n; i += 128) sHw2[i] = g.head_w2[i];
+          for (int i = et; i < TG_BN * a.head_n; i += TG_EPI_THREADS) sHw2[i] = g.head_w2[i];
           if (et < a.head_n) sHb[8 + et] = g.head_b2 ? g.head_b2[et] : 0.f;
         }
       }
     }
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+    asm volatile("bar.sync 1, 256;" ::: "memory");
     const bool ok = tg_wait(done, 0u, a.error);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tbase = tmem_d + ((uint32_t)(q * 32) << 16);
     const bool have = ok && nk > 0;
+    // after `done` every MMA has read its operands and every TMA load has landed: the operand stages are free scratch
+    float* sPart = reinterpret_cast<float*>(sOp);                        // [2 halves][128 rows][2]: sum, sum of squares
+    float* sHeadPart = sPart + 2 * TG_BM * 2;                            // [128 rows][16]: half 1's head partial sums
     if (a.to_ws || !ln) {
       float* dst; long long ld;
       if (a.to_ws) { dst = a.ws + ((size_t)blockIdx.z * a.M) * a.N; ld = a.N; }
@@ -231,8 +241,8 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
       const bool vec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) && (ld % 4 == 0);
       const bool acc = !a.to_ws && a.accumulate;
 #pragma unroll 1
-      for (int c = 0; c < TG_BN; c += 32) {
-        if (n0 + c >= a.N) break;                                        // uniform
+      for (int c = c_lo; c < c_hi; c += 32) {
+        if (n0 + c >= a.N) break;                                        // warp-uniform
         float v[32];
         if (have) tg_ld32(tbase + (uint32_t)c, v);
         else {
@@ -262,14 +272,22 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
         }
       }
     } else {
-      // ---- bias + LayerNorm + tanh (N == 256: the whole row is this thread's) ----
+      // ---- bias + LayerNorm + tanh (N == 256: a row = this thread's 128 columns + its partner's) ----
       float s = 0.f, ss = 0.f;
 #pragma unroll 1
-      for (int c = 0; c < TG_BN; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         float v[32];
         tg_ld32(tbase + (uint32_t)c, v);
 #pragma unroll
         for (int i = 0; i < 32; ++i) { const float x = v[i] + sBias[c + i]; s += x; ss += x * x; }
+      }
+      *reinterpret_cast<float2*>(sPart + (hh * TG_BM + row) * 2) = make_float2(s, ss);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      {
+        const float2 o = *reinterpret_cast<const float2*>(sPart + ((hh ^ 1) * TG_BM + row) * 2);
+        // fixed summation order (half 0 + half 1) so that both threads of a row hold bit-identical statistics
+        const float2 p0 = hh ? o : make_float2(s, ss), p1 = hh ? make_float2(s, ss) : o;
+        s = p0.x + p1.x; ss = p0.y + p1.y;
       }
       const float mean = s * (1.f / TG_BN);
       const float var = fmaxf(ss * (1.f / TG_BN) - mean * mean, 0.f);
@@ -281,7 +299,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
       float* xrow = g.xhat ? g.xhat + z * g.sXhatZ + (size_t)m * TG_BN : nullptr;
       const bool valid = have && m < a.M;
 #pragma unroll 1
-      for (int c = 0; c < TG_BN; c += 32) {
+      for (int c = c_lo; c < c_hi; c += 32) {
         float v[32];
         tg_ld32(tbase + (uint32_t)c, v);
         float h[32];
@@ -289,7 +307,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
         for (int i = 0; i < 32; ++i) {
           const float xh = (v[i] + sBias[c + i] - mean) * rstd;
           v[i] = xh;
-          h[i] = tanhf(fmaf(xh, sLs[c + i], sLb[c + i]));
+          h[i] = tg_tanh(fmaf(xh, sLs[c + i], sLb[c + i]));
         }
         if (valid) {
           if (hrow) {
@@ -316,8 +334,20 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
           }
         }
       }
-      if (valid) {
-        if (g.rstd) g.rstd[z * g.sRstdZ + m] = rstd;
+      if (valid && g.rstd && hh == 0) g.rstd[z * g.sRstdZ + m] = rstd;
+      if (a.epi >= SERL_TGEMM_EPI_LN_TANH_HEAD) {
+        // half 1 hands its partial head sums to half 0, which finishes the row
+        if (hh == 1) {
+#pragma unroll
+          for (int j = 0; j < 2 * TG_MAXHEAD; ++j) sHeadPart[row * 16 + j] = hacc[j];
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (hh == 0) {
+#pragma unroll
+          for (int j = 0; j < 2 * TG_MAXHEAD; ++j) hacc[j] += sHeadPart[row * 16 + j];
+        }
+      }
+      if (valid && hh == 0) {
         if (a.epi == SERL_TGEMM_EPI_LN_TANH_HEAD) {
           float* o = g.head_out + z * g.sHeadOutZ + (size_t)m * g.ld_head;
 #pragma unroll
@@ -410,9 +440,11 @@ extern "C" int serl_tgemm_tf32(const serl_tgemm_desc* d, void* stream) {
     }
     attr_done = true;
   }
-  const bool ln = d->epilogue != SERL_TGEMM_EPI_STORE;
+  const bool ln = d->epilogue >= SERL_TGEMM_EPI_LN_TANH && d->epilogue <= SERL_TGEMM_EPI_LN_TANH_POLICY;
+  const bool partial = d->epilogue == SERL_TGEMM_EPI_PARTIAL;
+  if (d->epilogue < 0 || d->epilogue > SERL_TGEMM_EPI_PARTIAL) { set_last_error("serl_tgemm_tf32: unknown epilogue %d", d->epilogue); return SERL_ERR_INVALID; }
   if (ln && (d->N != TG_BN || d->reduce_z || d->splits > 1)) { set_last_error("serl_tgemm_tf32: LayerNorm epilogues need N == 256, no k-split, no reduce_z"); return SERL_ERR_UNSUPPORTED; }
-  if (d->epilogue >= SERL_TGEMM_EPI_LN_TANH_HEAD && (d->head_n < 1 || d->head_n > TG_MAXHEAD)) { set_last_error("serl_tgemm_tf32: head_n in [1, 8]"); return SERL_ERR_UNSUPPORTED; }
+  if (ln && d->epilogue >= SERL_TGEMM_EPI_LN_TANH_HEAD && (d->head_n < 1 || d->head_n > TG_MAXHEAD)) { set_last_error("serl_tgemm_tf32: head_n in [1, 8]"); return SERL_ERR_UNSUPPORTED; }
   TgMaps maps;
   TgArgs a{};
   a.G = d->num_problems; a.M = d->M; a.N = d->N; a.K = d->K; a.epi = d->epilogue; a.accumulate = d->accumulate; a.head_n = d->head_n;
@@ -435,9 +467,9 @@ extern "C" int serl_tgemm_tf32(const serl_tgemm_desc* d, void* stream) {
     g.noise = p.noise; g.act = p.act; g.logp = p.logp; g.u_out = p.u_out; g.std_out = p.std_out;
     g.sCz = p.sCz; g.sBiasZ = p.sBiasZ; g.sLnZ = p.sLnZ; g.sXhatZ = p.sXhatZ; g.sRstdZ = p.sRstdZ; g.sHeadWz = p.sHeadWz; g.sHeadBz = p.sHeadBz;
     g.sHeadOutZ = p.sHeadOutZ; g.ldc = p.ldc; g.ld_head = p.ld_head; g.ld_act = p.ld_act; g.z0 = ztotal; g.Z = p.Z;
-    if (!d->reduce_z && !p.C && !ln) { set_last_error("serl_tgemm_tf32: problem %d: C required", i); return SERL_ERR_INVALID; }
+    if (!d->reduce_z && !p.C && !ln && !partial) { set_last_error("serl_tgemm_tf32: problem %d: C required", i); return SERL_ERR_INVALID; }
     if (ln && (!p.ln_scale || !p.ln_bias)) { set_last_error("serl_tgemm_tf32: problem %d: LayerNorm scale / bias required", i); return SERL_ERR_INVALID; }
-    if (d->epilogue >= SERL_TGEMM_EPI_LN_TANH_HEAD && (!p.head_w || !p.head_out)) { set_last_error("serl_tgemm_tf32: problem %d: head_w / head_out required", i); return SERL_ERR_INVALID; }
+    if (ln && d->epilogue >= SERL_TGEMM_EPI_LN_TANH_HEAD && (!p.head_w || !p.head_out)) { set_last_error("serl_tgemm_tf32: problem %d: head_w / head_out required", i); return SERL_ERR_INVALID; }
     if (d->epilogue == SERL_TGEMM_EPI_LN_TANH_POLICY && (!p.head_w2 || !p.act || (!d->deterministic && !p.noise) || p.Z != 1)) {
       set_last_error("serl_tgemm_tf32: problem %d: policy epilogue needs head_w2, act, noise and Z == 1", i); return SERL_ERR_INVALID;
     }
@@ -451,7 +483,14 @@ extern "C" int serl_tgemm_tf32(const serl_tgemm_desc* d, void* stream) {
     else if (tiles < 74 && d->K >= 512) { S = 148 / tiles; if (S > d->K / 128) S = d->K / 128; if (S < 1) S = 1; }
   }
   const size_t part = (size_t)d->M * d->N * sizeof(float);
-  if (d->reduce_z || S > 1) {
+  if (partial) {
+    // the caller reduces: partial products of split s of member zz (counted across the problems) at workspace[(zz * S + s)][M][N]
+    S = d->splits > 0 ? d->splits : 1;
+    if (d->reduce_z || !d->workspace) { set_last_error("serl_tgemm_tf32: the PARTIAL epilogue needs a workspace and no reduce_z"); return SERL_ERR_INVALID; }
+    const int kc = ceil_div(ceil_div(d->K, S), TG_BK) * TG_BK;
+    if (ceil_div(d->K, kc) != S) { set_last_error("serl_tgemm_tf32: %d splits of K = %d leave empty splits", S, d->K); return SERL_ERR_INVALID; }
+    if (part * (size_t)ztotal * S > d->workspace_bytes) { set_last_error("serl_tgemm_tf32: PARTIAL needs %zu workspace bytes", part * (size_t)ztotal * S); return SERL_ERR_INVALID; }
+  } else if (d->reduce_z || S > 1) {
     if (d->num_problems != 1) { set_last_error("serl_tgemm_tf32: k-split / reduce_z launches take one problem"); return SERL_ERR_UNSUPPORTED; }
     while (S > 1 && part * (size_t)ztotal * S > d->workspace_bytes) --S;
     if (!d->workspace || part * (size_t)ztotal * S > d->workspace_bytes) {
@@ -462,13 +501,13 @@ extern "C" int serl_tgemm_tf32(const serl_tgemm_desc* d, void* stream) {
   a.kchunk = ceil_div(ceil_div(d->K, S), TG_BK) * TG_BK;
   S = ceil_div(d->K, a.kchunk);
   a.S = S;
-  a.to_ws = (d->reduce_z || S > 1) ? 1 : 0;
+  a.to_ws = (partial || d->reduce_z || S > 1) ? 1 : 0;
   a.ws = d->workspace;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   dim3 grid(ceil_div(d->M, TG_BM), ceil_div(d->N, TG_BN), ztotal * S);
   launch_k(tgemm_tf32_kernel, grid, TG_THREADS, TG_SMEM, st, maps, a);
   if (int e = check_launch("tgemm_tf32_kernel")) return e;
-  if (a.to_ws) {
+  if (a.to_ws && !partial) {
     const serl_tgemm_problem& p = d->problems[0];
     GemmArgs r{};
     r.C = p.C; r.bias = p.bias; r.ws = d->workspace; r.M = d->M; r.N = d->N; r.K = d->K; r.Z = p.Z; r.S = S;

@@ -147,6 +147,10 @@ class Engine:
         self.info_hist = torch.zeros(INFO_GAP, dtype=f32, device=device)
         self.lr_info = torch.zeros(4, dtype=f32, device=device)
         self.launches = 0
+        # 16-bit builds, pixel agent: the critic step runs on the fused head kernels (heads_fused.py: TF32 GEMMs with TMA-fed
+        # operands and LayerNorm / head epilogues, batched problems); SERL_FUSED_HEADS=0 keeps the per-op chain below.
+        from . import heads_fused
+        self.fused = heads_fused.FusedCritic(self) if (heads_fused.enabled(cfg) and (dev.type == "cuda" or os.environ.get("SERL_FUSED_HEADS") == "force")) else None
 
     # ------------------------------------------------------------------------------------------
     def P(self, buf, path):
@@ -408,6 +412,8 @@ class Engine:
 
     def critic_loss_and_grads(self, keys, grad_scale=1.0, explicit=None):
         """sac.py:134-191 + its gradient w.r.t. group-0 parameters (written to store.grad)."""
+        if self.fused is not None:
+            return self.fused.critic_loss_and_grads(keys, grad_scale=grad_scale, explicit=explicit)
         cfg, B, E, st = self.cfg, self.B, self.cfg.ensemble, self.store
         obs_rows, next_rows = slice(0, B), slice(B, 2 * B)
         # three independent forward branches:

@@ -224,3 +224,50 @@ def tgemm(ws: Optional[Workspace], problems, M, N, K, *, epilogue=L.TGEMM_STORE,
         d.workspace, d.workspace_bytes = ws.buf.data_ptr(), ws.nbytes
     d.error = _p(error)
     L.call("serl_tgemm_tf32", C.byref(d), _s())
+
+
+def tgemm_splits(K: int, want: int) -> int:
+    """Largest S <= want such that S k-splits of whole 32-wide k-blocks cover K with no empty split."""
+    for S in range(max(want, 1), 0, -1):
+        kc = -(-(-(-K // S)) // 32) * 32
+        if -(-K // kc) == S:
+            return S
+    return 1
+
+
+def sle_fwd_multi(problems, keep, N, P, C_):
+    """problems: (feat, kernel, keep_mask | None, out, ld_out) device addresses; one launch."""
+    arr = (L.SleProblem * len(problems))()
+    for q, (feat, kern, mask, out, ld) in zip(arr, problems):
+        q.feat, q.kernel, q.keep_mask, q.out, q.ld_out = feat, kern, mask, out, ld
+    L.call("serl_sle_fwd_multi", arr, len(problems), float(keep), N, P, C_, 8, _s())
+
+
+def enc_finish(problems, rows, eps=1e-6):
+    """problems: dicts with partials+S or x+ld_x+w+K, and bias, ln_scale, ln_bias, out, ld_out, D, optional xhat, rstd."""
+    arr = (L.EncFinishProblem * len(problems))()
+    for q, p in zip(arr, problems):
+        q.partials, q.S, q.x, q.ld_x, q.w, q.K = p.get("partials"), p.get("S", 0), p.get("x"), p.get("ld_x", 0), p.get("w"), p.get("K", 0)
+        q.bias, q.ln_scale, q.ln_bias, q.out, q.ld_out = p["bias"], p["ln_scale"], p["ln_bias"], p["out"], p["ld_out"]
+        q.xhat, q.rstd, q.D = p.get("xhat"), p.get("rstd"), p["D"]
+    L.call("serl_enc_finish", arr, len(problems), rows, float(eps), _s())
+
+
+def ln_tanh_bwd_multi(problems):
+    """problems: dicts with dt+ld_dt (or dq+head_w[+head_w_stride]), optional dt2+ld_dt2, t, ld_t, xhat, rstd, scale,
+    rows_per_group, group_stride, dz, optional dy, R, D."""
+    arr = (L.LnBwdProblem * len(problems))()
+    for q, p in zip(arr, problems):
+        q.dt, q.ld_dt, q.dt2, q.ld_dt2 = p.get("dt"), p.get("ld_dt", 0), p.get("dt2"), p.get("ld_dt2", 0)
+        q.dq, q.head_w, q.head_w_stride = p.get("dq"), p.get("head_w"), p.get("head_w_stride", 0)
+        q.t, q.ld_t, q.xhat, q.rstd, q.scale = p["t"], p["ld_t"], p["xhat"], p["rstd"], p["scale"]
+        q.rows_per_group, q.group_stride, q.dz, q.dy, q.R, q.D = p["rows_per_group"], p.get("group_stride", 0), p["dz"], p.get("dy"), p["R"], p["D"]
+    L.call("serl_layernorm_tanh_bwd_multi", arr, len(problems), _s())
+
+
+def small_grads(jobs):
+    """jobs: (kind, x, ld_x, y | None, ld_y, out_a, out_b | None, groups, rows, D)."""
+    arr = (L.SmallGradJob * len(jobs))()
+    for q, (kind, x, ld_x, y, ld_y, out_a, out_b, groups, rows, D) in zip(arr, jobs):
+        q.kind, q.x, q.ld_x, q.y, q.ld_y, q.out_a, q.out_b, q.groups, q.rows, q.D = kind, x, ld_x, y, ld_y, out_a, out_b, groups, rows, D
+    L.call("serl_small_grads", arr, len(jobs), _s())

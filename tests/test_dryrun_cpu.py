@@ -166,10 +166,35 @@ def test_bf16_trunk_call_sequence(dry):
                            precision="bf16")
     del dry[:]
     agent.update_critics(rb.sample(4, pack_obs_and_next_obs=True))
-    # 12 convs: the stem (fused with its max-pool), 5 stride-1 3x3 convs (shifted-window kernel), 6 strided / 1x1 convs
+    # 12 convs in 9 launches: the stem (fused with its max-pool), 5 stride-1 3x3 convs with GroupNorm (+ residual) + ReLU inside
+    # (conv3x3_res), 3 stage heads = stride-2 3x3 conv + 1x1 projection + both GroupNorms in one kernel (conv3x3s2_res)
     assert dry.count("serl_stem_conv_pool_tc_h16") == 1 and dry.count("serl_pool_finish_gn_h16") == 1
-    assert dry.count("serl_conv3x3s1_tc_h16") == 5 and dry.count("serl_conv2d_tc_h16") == 6 and dry.count("serl_conv2d_nhwc_f32") == 0
-    # GroupNorm affines are derived inside the consumers from the conv sums: no finalize launches
-    assert dry.count("serl_gn_finalize") == 0 and dry.count("serl_block_combine_gn_h16") == 4 and dry.count("serl_affine_relu_gn_h16") == 4
+    assert dry.count("serl_conv3x3_res_h16") == 5 and dry.count("serl_conv3x3s2_res_h16") == 3
+    assert dry.count("serl_conv3x3s1_tc_h16") == 0 and dry.count("serl_conv2d_tc_h16") == 0 and dry.count("serl_conv2d_nhwc_f32") == 0
+    # no GroupNorm / residual pass of its own
+    assert dry.count("serl_gn_finalize") == 0 and dry.count("serl_block_combine_gn_h16") == 0 and dry.count("serl_affine_relu_gn_h16") == 0
     assert dry.count("serl_trunk_stem_prep_h16") == 1 and dry.count("serl_maxpool_affine_h16") == 0
     assert dry.count("serl_gemm_tf32x3") > 0 and dry.count("serl_gemm_f32") == 0      # 16-bit builds: tensor-core heads
+
+
+def test_fused_heads_call_sequence(dry, monkeypatch):
+    """Host logic of the fused critic step (heads_fused.py) on the dry device: launch counts per kernel family for two cameras."""
+    monkeypatch.setenv("SERL_FUSED_HEADS", "force")
+    from serl_b200.utils.launcher import make_drq_agent
+    cams = ("front", "wrist")
+    rb = _ring(cams, 64, 128)
+    trs = random_transitions(np.random.default_rng(0), 40, cams, 128)
+    for tr in trs:
+        rb.insert(tr)
+    agent = make_drq_agent(1, trs[0]["observations"], trs[0]["actions"], image_keys=cams, encoder_type="resnet-pretrained", device="cpu",
+                           precision="fp16")
+    del dry[:]
+    agent.update_critics(rb.sample(4, pack_obs_and_next_obs=True))
+    # forward: 1 SLE + 1 k-split GEMM + 1 finish for the 3 passes x 2 cameras, 2 policy GEMMs, 2 critic GEMMs (online + target per layer);
+    # backward: dh1, d enc, dW2, dW1, encoder dW, d SLE
+    assert dry.count("serl_sle_fwd_multi") == 1 and dry.count("serl_enc_finish") == 1 and dry.count("serl_sle_fwd") == 0
+    assert dry.count("serl_tgemm_tf32") == 1 + 2 + 2 + 6
+    assert dry.count("serl_layernorm_tanh_bwd_multi") == 3 and dry.count("serl_small_grads") == 2
+    assert dry.count("serl_layernorm_tanh_fwd") == 0 and dry.count("serl_colsum_f32") == 0
+    assert dry.count("serl_gemm_tf32x3") == 1                                  # the (S, 64) proprio weight gradient: fan-in not TMA-addressable
+    assert dry.count("serl_critic_loss") == 1 and dry.count("serl_adam_polyak") == 1

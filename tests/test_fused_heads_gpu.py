@@ -1,0 +1,85 @@
+"""GPU: the fused critic step of the 16-bit builds (serl_b200/heads_fused.py: TF32 tensor-core GEMMs with TMA-fed operands and
+LayerNorm / head epilogues, batched problems) against (a) the float64 oracle and (b) the per-op chain it replaces
+(SERL_FUSED_HEADS=0: 3xTF32 GEMMs + separate LayerNorm / reduction kernels) on the same state and batch.
+Bars: north_star's 1e-2 for the 16-bit builds on Q / TD target / loss; every gradient leaf within 2e-2 of its own max of the
+oracle's (fp16 trunk + TF32 heads) and within 1e-2 of the unfused chain's (TF32 vs 3xTF32 heads, same trunk)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import fake_env, oracle_cfg_from_agent, oracle_state_from_agent, random_transitions, rel_err, to_numpy_tree
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(cams, seed=42, cap=200, n_fill=260):
+    from serl_b200.utils.launcher import make_drq_agent, make_replay_buffer
+    env = fake_env(cams)
+    rb = make_replay_buffer(env, capacity=cap, type="memory_efficient_replay_buffer", image_keys=list(cams), seed=3)
+    trs = random_transitions(np.random.default_rng(seed), n_fill, cams)
+    for tr in trs:
+        rb.insert(tr)
+    agent = make_drq_agent(seed, trs[0]["observations"], trs[0]["actions"], image_keys=cams, encoder_type="resnet-pretrained", precision="fp16")
+    g = torch.Generator(device="cuda").manual_seed(0)             # biases / LayerNorm offsets off their zero init: every gradient path live
+    st = agent._store
+    st.params.add_(torch.randn(st.n, device="cuda", generator=g) * 0.05)
+    st.target.copy_(st.params + torch.randn(st.n, device="cuda", generator=g) * 0.005)
+    st.version += 1
+    lam = st.leaf["modules_temperature/lagrange"].offset
+    st.params[lam] = -4.0
+    st.target[lam] = -4.0
+    return agent, rb
+
+
+@pytest.mark.parametrize("cams,B", [(("front", "wrist"), 12), (("front",), 160)])
+def test_fused_critic_step_matches_oracle_and_unfused_chain(cams, B, monkeypatch):
+    from oracle import drq as O
+    from oracle.replay import unpack
+    agent, rb = _setup(cams)
+    monkeypatch.setenv("SERL_FUSED_HEADS", "0")
+    ref_agent, _ = _setup(cams)
+    ref_agent._engine(B)                                              # the engine (and its head path) is built on first use
+    monkeypatch.delenv("SERL_FUSED_HEADS")
+    ocfg = oracle_cfg_from_agent(agent)
+    it = rb.get_iterator(sample_args={"batch_size": B, "pack_obs_and_next_obs": True})
+    for step in range(3):                                            # eager, capture + replay, replay
+        ostate = oracle_state_from_agent(agent) if B <= 16 else None
+        ref_agent._store.params.copy_(agent._store.params); ref_agent._store.target.copy_(agent._store.target)
+        ref_agent._store.m.copy_(agent._store.m); ref_agent._store.v.copy_(agent._store.v); ref_agent._store.counts.copy_(agent._store.counts)
+        ref_agent.state._rng.copy_(agent.state._rng)
+        batch = next(it)
+        bd = {k: v for k, v in batch.to_dict().items() if k != "_indices"}
+        agent, info = agent.update_critics(batch)
+        eng = agent._engines[B]
+        assert eng.fused is not None
+        ref_agent, rinfo = ref_agent.update_critics(bd)               # same rows as an explicit dict batch (no augmentation difference: same keys)
+        reng = ref_agent._engines[B]
+        assert reng.fused is None
+        for cam in cams:
+            assert torch.equal(eng.pix[cam], reng.pix[cam])
+        assert rel_err(eng.q.cpu().numpy(), reng.q.cpu().numpy().astype(np.float64)) < 5e-3
+        assert rel_err(eng.target_q.cpu().numpy(), reng.target_q.cpu().numpy().astype(np.float64)) < 5e-3
+        st, rst = agent._store, ref_agent._store
+        worst = ("", 0.0)
+        for leaf in st.spec:
+            if leaf.group != 0:
+                continue
+            got, ref = st.view(st.grad, leaf.path).cpu().numpy(), rst.view(rst.grad, leaf.path).cpu().numpy().astype(np.float64)
+            e = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-12)
+            worst = max(worst, (leaf.path, e), key=lambda t: t[1])
+            assert e < 1e-2, (leaf.path, e)
+        print(f"step {step}: fused vs per-op chain: worst gradient leaf {worst[0]} {worst[1]:.2e}")
+        if ostate is not None:
+            host = unpack(to_numpy_tree(bd))
+            oinfo = O.update_critics(ostate, ocfg, host)
+            assert rel_err(eng.q.cpu().numpy(), oinfo["critic"]["_q"].numpy()) < 1e-2
+            assert rel_err(eng.target_q.cpu().numpy(), oinfo["critic"]["_target_q"].numpy()) < 1e-2
+            assert abs(float(info["critic"]["critic_loss"]) - oinfo["critic"]["critic_loss"]) < 1e-2 * max(abs(oinfo["critic"]["critic_loss"]), 1e-6)
+            if step == 0:
+                for leaf in st.spec:
+                    if leaf.group != 0:
+                        continue
+                    ref = oinfo["_grads"]["critic"][leaf.path].numpy()
+                    got = st.view(st.grad, leaf.path).cpu().numpy()
+                    assert np.abs(got - ref).max() <= 2e-2 * max(np.abs(ref).max(), 1e-8), leaf.path
+    agent.check_status()
