@@ -185,7 +185,13 @@ class OracleFrameRing:
             "masks": self.masks[indx],
             "dones": self.dones[indx],
         }
-        win = indx[:, None] - T + np.arange(T + 1)[None, :]          # slots idx-T .. idx
+        # (:148-151) obs_pixels = sliding_window_view(frames, T + 1, axis=0)[indx - T]: the window axis has capacity - T entries and a
+        # NEGATIVE index (a valid slot idx < T: the first transition of an episode whose filler frame landed on the last slots of the
+        # ring) selects from its end, numpy-style - the reference returns slots capacity-T-1+(idx-T+1) .. , not the ring-wrapped
+        # window.  Restated literally (pinned by tests/golden/replay_wrap_first.npz, generated by the real class).
+        w0 = indx - T
+        w0 = np.where(w0 < 0, w0 + (self.capacity - T), w0)
+        win = w0[:, None] + np.arange(T + 1)[None, :]                  # slots of window w0
         for k in self.image_keys:
             out["observations"][k] = self.frames[k][win]              # (B, T+1, H, W, C)
         return out

@@ -62,6 +62,8 @@ class DrQAgent(SACAgent):
         def body(batch, graph_mode):
             ops.rng_schedule(self.state._rng, self._keys, True, True)    # split(rng,3) then update's split(rng,4)
             eng.launches += 1
+            if getattr(eng, "fused", None) is not None and self.explicit_randomness is None:
+                eng.fused.prefetch_rng(self._keys)
             with self._section("sample_crop"):
                 self._load_batch(eng, batch, augment=True, keys=self._keys, graph_mode=graph_mode)
             with self._section("trunk"):

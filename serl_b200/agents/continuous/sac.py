@@ -14,6 +14,7 @@ dropout and action sampling in `_compute_next_actions`, ALL three Adam txs tick 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, FrozenSet, Optional, Sequence
 
 import numpy as np
@@ -27,6 +28,9 @@ from ...engine import AgentConfig, Engine
 from ...params import ParamStore, init_trainable, init_trunk, trainable_spec, trunk_spec
 
 ALL_NETS = frozenset({"actor", "critic", "temperature"})
+
+
+_HEADS_PDL = os.environ.get("SERL_HEADS_PDL", "0") not in ("", "0")
 
 
 def _dist():
@@ -315,6 +319,11 @@ class SACAgent:
         dp = self._dp(pmap_axis)
         gscale = 1.0 / _dist().get_world_size() if dp else 1.0
         at = "actor" in nets or "temperature" in nets
+        # programmatic dependent launch for the ~40-launch heads chain only (SERL_HEADS_PDL=1): the next kernel's CTAs become
+        # resident and run their set-up while the current one drains; the trunk's one-CTA-per-SM kernels gain nothing from it
+        heads_pdl = _HEADS_PDL and torch.device(self.device).type == "cuda"
+        if heads_pdl:
+            L.call("serl_set_pdl", 1)
         with self._section("heads"):
             if "critic" in nets:
                 eng.critic_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl)
@@ -322,6 +331,8 @@ class SACAgent:
                 # any subset is legal (sac.py:270-277): a network that is not updated contributes a zero gradient, its tx still ticks
                 eng.actor_temp_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl, do_actor="actor" in nets,
                                               do_temperature="temperature" in nets)
+        if heads_pdl:
+            L.call("serl_set_pdl", int(os.environ.get("SERL_PDL", "0") not in ("", "0")))
         if dp and nets:
             # [group 0 | critic infos] and/or [actor, temperature infos | groups 1, 2 | aux]: one contiguous range either way
             with self._section("allreduce"):

@@ -129,24 +129,44 @@ __global__ void __launch_bounds__(256) ln_tanh_bwd_multi_kernel(const __grid_con
   }
 }
 
-// ---- column reductions: block = 32 columns x 8 row-slices, fixed-order tree (deterministic) --------------------------------
+// ---- column reductions: block = 32 columns x 32 row-slices, four rows in flight per thread, fixed-order tree (deterministic) ----
 struct SmallGradArgs { serl_small_grad_job j[SERL_SMALL_GRAD_MAX_JOBS]; int J; };
 
-__global__ void __launch_bounds__(256) small_grads_kernel(const __grid_constant__ SmallGradArgs a) {
+__global__ void __launch_bounds__(1024) small_grads_kernel(const __grid_constant__ SmallGradArgs a) {
   pdl_prologue();
-  __shared__ float ra[8][33], rb[8][33];
+  __shared__ float ra[32][33], rb[32][33];
   const serl_small_grad_job& q = a.j[blockIdx.z];
   const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int g = blockIdx.y, d = blockIdx.x * 32 + cx;
   if (g >= q.groups || blockIdx.x * 32 >= q.D) return;            // uniform per block
   float sa = 0.f, sb = 0.f;
   if (d < q.D) {
-    for (int r = sl; r < q.rows; r += 8) {
-      const size_t row = (size_t)g * q.rows + r;
-      const float x = q.x[row * q.ld_x + d];
-      if (q.kind == SERL_SMALL_GRAD_COLSUM) sa += x;
-      else if (q.kind == SERL_SMALL_GRAD_LN) { sa += x * q.y[row * q.ld_y + d]; sb += x; }
-      else { const float w = q.y[row]; sa += x * w; sb += w; }     // SERL_SMALL_GRAD_HEAD: x = h (rows, D), y = dq (rows)
+    const float* xp = q.x + (size_t)g * q.rows * q.ld_x + d;
+    if (q.kind == SERL_SMALL_GRAD_COLSUM) {
+      int r = sl;
+      for (; r + 96 < q.rows; r += 128) {
+        const float x0 = xp[(size_t)r * q.ld_x], x1 = xp[(size_t)(r + 32) * q.ld_x], x2 = xp[(size_t)(r + 64) * q.ld_x], x3 = xp[(size_t)(r + 96) * q.ld_x];
+        sa += x0; sa += x1; sa += x2; sa += x3;
+      }
+      for (; r < q.rows; r += 32) sa += xp[(size_t)r * q.ld_x];
+    } else if (q.kind == SERL_SMALL_GRAD_LN) {
+      const float* yp = q.y + (size_t)g * q.rows * q.ld_y + d;
+      int r = sl;
+      for (; r + 96 < q.rows; r += 128) {
+        const float x0 = xp[(size_t)r * q.ld_x], x1 = xp[(size_t)(r + 32) * q.ld_x], x2 = xp[(size_t)(r + 64) * q.ld_x], x3 = xp[(size_t)(r + 96) * q.ld_x];
+        const float y0 = yp[(size_t)r * q.ld_y], y1 = yp[(size_t)(r + 32) * q.ld_y], y2 = yp[(size_t)(r + 64) * q.ld_y], y3 = yp[(size_t)(r + 96) * q.ld_y];
+        sa = fmaf(x0, y0, sa); sb += x0; sa = fmaf(x1, y1, sa); sb += x1; sa = fmaf(x2, y2, sa); sb += x2; sa = fmaf(x3, y3, sa); sb += x3;
+      }
+      for (; r < q.rows; r += 32) { const float x = xp[(size_t)r * q.ld_x]; sa = fmaf(x, yp[(size_t)r * q.ld_y], sa); sb += x; }
+    } else {                                                      // SERL_SMALL_GRAD_HEAD: x = h (rows, D), y = dq (rows)
+      const float* yp = q.y + (size_t)g * q.rows;
+      int r = sl;
+      for (; r + 96 < q.rows; r += 128) {
+        const float x0 = xp[(size_t)r * q.ld_x], x1 = xp[(size_t)(r + 32) * q.ld_x], x2 = xp[(size_t)(r + 64) * q.ld_x], x3 = xp[(size_t)(r + 96) * q.ld_x];
+        const float w0 = yp[r], w1 = yp[r + 32], w2 = yp[r + 64], w3 = yp[r + 96];
+        sa = fmaf(x0, w0, sa); sb += w0; sa = fmaf(x1, w1, sa); sb += w1; sa = fmaf(x2, w2, sa); sb += w2; sa = fmaf(x3, w3, sa); sb += w3;
+      }
+      for (; r < q.rows; r += 32) { const float w = yp[r]; sa = fmaf(xp[(size_t)r * q.ld_x], w, sa); sb += w; }
     }
   }
   ra[sl][cx] = sa; rb[sl][cx] = sb;
@@ -154,7 +174,7 @@ __global__ void __launch_bounds__(256) small_grads_kernel(const __grid_constant_
   if (sl == 0 && d < q.D) {
     float ta = ra[0][cx], tb = rb[0][cx];
 #pragma unroll
-    for (int k = 1; k < 8; ++k) { ta += ra[k][cx]; tb += rb[k][cx]; }
+    for (int k = 1; k < 32; ++k) { ta += ra[k][cx]; tb += rb[k][cx]; }
     q.out_a[(size_t)g * q.D + d] = ta;
     if (q.out_b && q.kind == SERL_SMALL_GRAD_LN) q.out_b[(size_t)g * q.D + d] = tb;
     if (q.out_b && q.kind == SERL_SMALL_GRAD_HEAD && d == 0) q.out_b[g] = tb;
@@ -223,6 +243,6 @@ extern "C" int serl_small_grads(const serl_small_grad_job* jobs, int num_jobs, v
     gmax = q.groups > gmax ? q.groups : gmax; dmax = q.D > dmax ? q.D : dmax;
   }
   a.J = num_jobs;
-  launch_k(small_grads_kernel, dim3(ceil_div(dmax, 32), gmax, num_jobs), 256, 0, ST(stream), a);
+  launch_k(small_grads_kernel, dim3(ceil_div(dmax, 32), gmax, num_jobs), 1024, 0, ST(stream), a);
   return check_launch("small_grads_kernel");
 }

@@ -150,7 +150,11 @@ __global__ void __launch_bounds__(kSamplerThreads) sample_gather_crop_kernel(con
 
   // ---- frame band: slot idx - T + t + which, rows clamp(y + cy - pad) ---------------------------
   const size_t frame_bytes = (size_t)H * row_bytes;
-  const int slot = idx - T + t + which;
+  // window idx - T of numpy's sliding_window_view over the (capacity) slot axis; the reference indexes it with idx - T as is, so a
+  // valid slot idx < T (first transition of an episode whose filler frame sits at the END of the ring) gets numpy's negative-index
+  // window = the LAST one, slots capacity-T-1 .. capacity-1 (memory_efficient_replay_buffer.py:148-151; pinned by tests/golden/replay_wrap_first.npz)
+  const int w0 = idx - T + ((idx - T) < 0 ? rv.capacity - T : 0);
+  const int slot = w0 + t + which;
   const uint8_t* src = rv.frames[cam] + (size_t)slot * frame_bytes;
   uint8_t* dst = (which ? a.next_pix[cam] : a.obs_pix[cam]) + ((size_t)g * H + y0) * row_bytes;
   const int dy = cy - a.padding;
@@ -300,7 +304,8 @@ __global__ void __launch_bounds__(kFrameThreads) sample_frames_kernel(const Samp
     const int cy = s_cy[t], cx = s_cx[t];
     const int dy = cy - a.padding, sh = (cx - a.padding) * C;
     if (threadIdx.x == 0) {                                // one TMA bulk copy per band, each with its own mbarrier
-      const uint8_t* fsrc = rv.frames[cam] + (size_t)(idx - T + t + which) * frame_bytes;
+      const int w0 = idx - T + ((idx - T) < 0 ? rv.capacity - T : 0);                 // negative window index: numpy semantics (see sample_gather_crop_kernel)
+      const uint8_t* fsrc = rv.frames[cam] + (size_t)(w0 + t + which) * frame_bytes;
       for (int band = 0; band < nb; ++band) {
         const int y0 = band * kBandRows, rows = min(kBandRows, H - y0);
         const int r_lo = min(max(y0 + dy, 0), H - 1), r_hi = min(max(y0 + rows - 1 + dy, 0), H - 1);
@@ -493,7 +498,7 @@ __global__ void __launch_bounds__(kFrameThreads, 2) sample_frames_persistent_ker
       return;
     }
     const int dy = s_cy[k] - a.padding;
-    const uint8_t* fsrc = rv.frames[cam] + (size_t)(idx - 1 + which) * frame_bytes;
+    const uint8_t* fsrc = rv.frames[cam] + (size_t)((idx > 0 ? idx - 1 : rv.capacity - 2) + which) * frame_bytes;   // idx == 0: numpy's window -1
     (void)i;
     for (int band = 0; band < nb; ++band) {
       const int y0 = band * kBandRows, rows = min(kBandRows, H - y0);

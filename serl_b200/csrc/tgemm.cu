@@ -108,7 +108,6 @@ __device__ inline float tg_tanh(float x) { return 1.f - __fdividef(2.f, __expf(2
 __device__ inline float tg_softplus(float x) { return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x))); }
 
 __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_constant__ TgMaps maps, const __grid_constant__ TgArgs a) {
-  pdl_prologue();
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sOp = smem;                                                   // TG_STAGES x [A 16 KB | B 32 KB]
@@ -150,6 +149,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = *tmem_slot;
+  // Programmatic dependent launch: everything above (barriers, tensor-memory allocation, descriptor prefetch) touches no data
+  // of the previous kernel and overlaps its tail; nothing below starts before that kernel has completed.
+  pdl_prologue();
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -234,6 +236,30 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
     // after `done` every MMA has read its operands and every TMA load has landed: the operand stages are free scratch
     float* sPart = reinterpret_cast<float*>(sOp);                        // [2 halves][128 rows][2]: sum, sum of squares
     float* sHeadPart = sPart + 2 * TG_BM * 2;                            // [128 rows][16]: half 1's head partial sums
+    // Output rows leave through a per-warp staging tile (32 rows x 32 columns, 16-byte chunks XOR-swizzled by row): a thread owns
+    // a ROW of the accumulator, so direct stores put the 32 lanes of an instruction on 32 different lines (measured: the
+    // epilogue's time was these stores); staged, one instruction writes 4 rows x 128 contiguous bytes.
+    float* sTile = reinterpret_cast<float*>(sOp + 16384) + (warp - 2) * 2048;   // two tiles per warp: activation | xhat
+    const int row_w = m0 + q * 32;                                       // first global row of this warp
+    auto stage = [&](float* tile, const float (&v)[32]) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(tile + lane * 32 + ((j ^ (lane & 7)) << 2)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    };
+    auto flush = [&](const float* tile, float* gbase, long long ld, int col, bool acc, bool live) {
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3), j = lane & 7;
+        float4 o = *reinterpret_cast<const float4*>(tile + rr * 32 + ((j ^ (rr & 7)) << 2));
+        if (live && row_w + rr < a.M) {
+          float4* p = reinterpret_cast<float4*>(gbase + (size_t)(row_w + rr) * ld + col + 4 * j);
+          if (acc) { const float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+          *p = o;
+        }
+      }
+      __syncwarp();
+    };
     if (a.to_ws || !ln) {
       float* dst; long long ld;
       if (a.to_ws) { dst = a.ws + ((size_t)blockIdx.z * a.M) * a.N; ld = a.N; }
@@ -249,24 +275,20 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (m < a.M) {
+        if (vec && n0 + c + 32 <= a.N) {                                 // warp-uniform
+          if (!a.to_ws) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] += sBias[c + i];
+          }
+          stage(sTile, v);
+          flush(sTile, dst, ld, n0 + c, acc, true);
+        } else if (m < a.M) {
           float* rowp = dst + (size_t)m * ld + n0 + c;
-          if (vec && n0 + c + 32 <= a.N) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 o = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-              if (!a.to_ws) { o.x += sBias[c + 4 * i]; o.y += sBias[c + 4 * i + 1]; o.z += sBias[c + 4 * i + 2]; o.w += sBias[c + 4 * i + 3]; }
-              float4* p = reinterpret_cast<float4*>(rowp + 4 * i);
-              if (acc) { const float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-              *p = o;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              if (n0 + c + i < a.N) {
-                float o = v[i] + (a.to_ws ? 0.f : sBias[c + i]);
-                rowp[i] = acc ? rowp[i] + o : o;
-              }
+          for (int i = 0; i < 32; ++i) {
+            if (n0 + c + i < a.N) {
+              float o = v[i] + (a.to_ws ? 0.f : sBias[c + i]);
+              rowp[i] = acc ? rowp[i] + o : o;
             }
           }
         }
@@ -295,8 +317,9 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
       float hacc[2 * TG_MAXHEAD];
 #pragma unroll
       for (int i = 0; i < 2 * TG_MAXHEAD; ++i) hacc[i] = 0.f;
-      float* hrow = g.C ? g.C + z * g.sCz + (size_t)m * g.ldc : nullptr;
-      float* xrow = g.xhat ? g.xhat + z * g.sXhatZ + (size_t)m * TG_BN : nullptr;
+      float* hbase = g.C ? g.C + z * g.sCz : nullptr;
+      float* xbase = g.xhat ? g.xhat + z * g.sXhatZ : nullptr;
+      const bool hvec = hbase && ((reinterpret_cast<uintptr_t>(hbase) & 15) == 0) && (g.ldc % 4 == 0);
       const bool valid = have && m < a.M;
 #pragma unroll 1
       for (int c = c_lo; c < c_hi; c += 32) {
@@ -309,16 +332,14 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tgemm_tf32_kernel(const __grid_
           v[i] = xh;
           h[i] = tg_tanh(fmaf(xh, sLs[c + i], sLb[c + i]));
         }
-        if (valid) {
-          if (hrow) {
+        if (hbase) {
+          if (hvec) { stage(sTile, h); flush(sTile, hbase, g.ldc, c, false, have); }
+          else if (valid) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(hrow + c)[i] = make_float4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
-          }
-          if (xrow) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) reinterpret_cast<float4*>(xrow + c)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 32; ++i) hbase[(size_t)m * g.ldc + c + i] = h[i];
           }
         }
+        if (xbase) { stage(sTile + 1024, v); flush(sTile + 1024, xbase, TG_BN, c, false, have); }
         if (a.epi >= SERL_TGEMM_EPI_LN_TANH_HEAD) {
 #pragma unroll
           for (int j = 0; j < TG_MAXHEAD; ++j) {

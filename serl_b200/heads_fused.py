@@ -45,8 +45,26 @@ class FusedCritic:
         self.S = ops.tgemm_splits(4096, max(1, min(148 // tiles, 32)))
         self.ws_enc = ops.Workspace(nprob * self.S * B * 256 * 4, dev)
         self.error = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._rng_prefetched = False
 
     # ------------------------------------------------------------------------------------------------------------
+    def _fill_rng(self, keys):
+        eng = self.eng
+        cfg, B, A = eng.cfg, eng.B, eng.cfg.action_dim
+        ops.normal_fill(ops.key_ptr(keys, L.KEY_CRITIC_NEXT), eng.eps, B * A)
+        for j, cam in enumerate(cfg.cams):
+            ops.dropout_mask_fill(ops.key_ptr(keys, L.KEY_CRITIC_NEXT), j, 0.9, eng.masks_u8[cam], B * 4096)
+        eng.launches += 1 + len(cfg.cams)
+
+    def prefetch_rng(self, keys):
+        """The critic step's noise and dropout masks only depend on the key schedule: fill them on side stream 1 right after
+        rng_schedule, next to the sampler and the trunk (joined at the top of critic_loss_and_grads)."""
+        s1 = self.eng.side[1]
+        s1.fork()
+        with s1:
+            self._fill_rng(keys)
+        self._rng_prefetched = True
+
     def critic_loss_and_grads(self, keys, grad_scale=1.0, explicit=None):
         eng = self.eng
         cfg, B, E, A, st = eng.cfg, eng.B, eng.cfg.ensemble, eng.cfg.action_dim, eng.store
@@ -56,11 +74,11 @@ class FusedCritic:
         obs_rows, next_rows = slice(0, B), slice(B, 2 * B)
         err = self.error
         # ---- randomness of the policy pass on s' (dropout masks + sample noise; sac.py:122-128) ----
-        if explicit is None:
-            ops.normal_fill(ops.key_ptr(keys, L.KEY_CRITIC_NEXT), eng.eps, B * A)
-            for j, cam in enumerate(cfg.cams):
-                ops.dropout_mask_fill(ops.key_ptr(keys, L.KEY_CRITIC_NEXT), j, 0.9, eng.masks_u8[cam], B * 4096)
-            eng.launches += 1 + ncam
+        if self._rng_prefetched:
+            eng.side[1].join()                                       # filled on side stream 1 while the sampler and the trunk ran
+            self._rng_prefetched = False
+        elif explicit is None:
+            self._fill_rng(keys)
         else:
             eng.eps.copy_(explicit["critic"]["eps"])
             for cam in cfg.cams:

@@ -180,6 +180,45 @@ def make_case(name, *, cap, T, ncam, H, W, S, A, n_insert, mean_ep, seed, n_batc
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+def make_wrap_first_case(name="wrap_first", *, cap=10, T=1, H=3, W=2, S=2, A=2, first_ep=8, second_ep=3):
+    """A valid slot idx < T: an episode that ends on slot cap-2 puts the next episode's filler frame on slot cap-1 and its first
+    transition on slot 0.  The reference gathers obs_pixels[indx - T] from a sliding-window view, so idx = 0 reads window -1 =
+    slots cap-2, cap-1 (numpy negative index), not the ring-wrapped pair (memory_efficient_replay_buffer.py:148-151)."""
+    gym = _GYM
+    from serl_launcher.data.memory_efficient_replay_buffer import MemoryEfficientReplayBuffer
+    obs_space = gym.spaces.Dict({"cam0": gym.spaces.Box(0, 255, shape=(T, H, W, 3), dtype=np.uint8),
+                                 "state": gym.spaces.Box(-np.inf, np.inf, shape=(T, S), dtype=np.float32)})
+    buf = MemoryEfficientReplayBuffer(obs_space, gym.spaces.Box(-1, 1, shape=(A,), dtype=np.float32), cap, pixel_keys=("cam0",))
+    rng = np.random.default_rng(7)
+    ins = dict(frames=[], nframes=[], state=[], nstate=[], actions=[], rewards=[], masks=[], dones=[])
+    for n in (first_ep, second_ep):
+        cur = {"cam0": rng.integers(0, 256, (T, H, W, 3), dtype=np.uint8), "state": rng.standard_normal((T, S)).astype(np.float32)}
+        for i in range(n):
+            nxt = {"cam0": np.concatenate([cur["cam0"][1:], rng.integers(0, 256, (1, H, W, 3), dtype=np.uint8)]),
+                   "state": rng.standard_normal((T, S)).astype(np.float32)}
+            tr = dict(observations={k: v.copy() for k, v in cur.items()}, next_observations={k: v.copy() for k, v in nxt.items()},
+                      actions=rng.uniform(-1, 1, A).astype(np.float32), rewards=np.float32(rng.random()), masks=np.float32(1.0), dones=bool(i == n - 1))
+            ins["frames"].append(cur["cam0"]); ins["nframes"].append(nxt["cam0"]); ins["state"].append(cur["state"]); ins["nstate"].append(nxt["state"])
+            ins["actions"].append(tr["actions"]); ins["rewards"].append(tr["rewards"]); ins["masks"].append(tr["masks"]); ins["dones"].append(tr["dones"])
+            buf.insert(tr)
+            cur = nxt
+    assert buf._is_correct_index[0], "the case must make slot 0 valid"
+    stream = [0, 1, 2, cap - 2, 0]
+    buf._np_random = ScriptedStream(stream)
+    batch = buf.sample(len(stream), pack_obs_and_next_obs=True).unfreeze()
+    dd = buf.dataset_dict
+    flat = {"meta": np.array([cap, T, 1, H, W, S, A, first_ep + second_ep, len(stream), 1], dtype=np.int64), "stream": np.array(stream),
+            "valid": buf._is_correct_index.copy(), "size": np.int64(len(buf)), "cursor": np.int64(buf._insert_index),
+            "frames_cam0": dd["observations"]["cam0"].copy(), "pix_cam0": batch["observations"]["cam0"],
+            "state": batch["observations"]["state"], "next_state": batch["next_observations"]["state"], "actions": batch["actions"]}
+    for k in ("state", "nstate", "actions", "rewards", "masks", "dones"):
+        flat[f"in_{k}"] = np.stack(ins[k])
+    flat["in_frames_cam0"], flat["in_nframes_cam0"] = np.stack(ins["frames"]), np.stack(ins["nframes"])
+    path = os.path.join(HERE, f"replay_{name}.npz")
+    np.savez_compressed(path, **flat)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 if __name__ == "__main__":
     _GYM = _install_stubs()
     sys.path.insert(0, REF)
@@ -187,3 +226,4 @@ if __name__ == "__main__":
     make_case("t1_cam1", cap=37, T=1, ncam=1, H=6, W=5, S=3, A=2, n_insert=150, mean_ep=7, seed=1, n_batches=2, B=16)
     make_case("t2_cam2", cap=53, T=2, ncam=2, H=4, W=4, S=2, A=3, n_insert=230, mean_ep=9, seed=2, n_batches=2, B=16)
     make_case("t1_cam2_long", cap=64, T=1, ncam=2, H=4, W=6, S=7, A=4, n_insert=400, mean_ep=25, seed=3, n_batches=2, B=32)
+    make_wrap_first_case()

@@ -8,7 +8,8 @@ import pytest
 
 from oracle import replay as R
 
-GOLD = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "replay_*.npz")))
+GOLD = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "replay_*.npz")) if not p.endswith("replay_wrap_first.npz"))
+WRAP_FIRST = os.path.join(os.path.dirname(__file__), "golden", "replay_wrap_first.npz")
 
 
 def _reference_index_protocol(stream, pos, B, size, valid):
@@ -51,7 +52,6 @@ def test_ring_matches_reference(path):
                 assert pos == int(g[f"{tag}_b{b}/pos0"])
                 idx, pos = _reference_index_protocol(stream, pos, B, ring.size, ring.valid)
                 assert pos == int(g[f"{tag}_b{b}/pos1"])
-                assert (idx >= T).all()      # valid slots always have a full window
                 out = ring.gather_packed(idx)
                 for c in cams:
                     np.testing.assert_array_equal(out["observations"][c], g[f"{tag}_b{b}/pix_{c}"])
@@ -60,6 +60,28 @@ def test_ring_matches_reference(path):
                 np.testing.assert_array_equal(out["next_observations"]["state"], g[f"{tag}_b{b}/next_state"])
                 for k in ("actions", "rewards", "masks", "dones"):
                     np.testing.assert_array_equal(out[k], g[f"{tag}_b{b}/{k}"])
+
+
+def test_valid_slot_below_T_reads_numpys_negative_window_like_the_reference():
+    """An episode whose filler frame lands on the LAST slot puts its first (valid) transition on slot 0; the reference gathers
+    sliding_window_view(frames)[idx - T], so idx = 0 returns window -1 = slots capacity-2, capacity-1 (fixture from the real class)."""
+    g = np.load(WRAP_FIRST)
+    cap, T, ncam, H, W, S, A, n_insert, B, _ = g["meta"].tolist()
+    ring = R.OracleFrameRing(cap, ["cam0"], (H, W, 3), T, S, A)
+    for i in range(n_insert):
+        ring.insert(dict(observations={"cam0": g["in_frames_cam0"][i], "state": g["in_state"][i]},
+                         next_observations={"cam0": g["in_nframes_cam0"][i], "state": g["in_nstate"][i]},
+                         actions=g["in_actions"][i], rewards=g["in_rewards"][i], masks=g["in_masks"][i], dones=g["in_dones"][i]))
+    np.testing.assert_array_equal(ring.valid, g["valid"])
+    assert ring.valid[0] and ring.size == int(g["size"]) and ring.cursor == int(g["cursor"])
+    np.testing.assert_array_equal(ring.frames["cam0"], g["frames_cam0"])
+    idx = g["stream"].astype(np.int64) % ring.size
+    assert ring.valid[idx].all() and (idx < T).any()
+    out = ring.gather_packed(idx)
+    np.testing.assert_array_equal(out["observations"]["cam0"], g["pix_cam0"])
+    np.testing.assert_array_equal(out["observations"]["cam0"][0], ring.frames["cam0"][[cap - 2, cap - 1]])
+    np.testing.assert_array_equal(out["observations"]["state"], g["state"])
+    np.testing.assert_array_equal(out["next_observations"]["state"], g["next_state"])
 
 
 def test_philox4x32_10_kat():

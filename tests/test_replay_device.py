@@ -68,6 +68,30 @@ def test_sample_indices_and_gather_bit_exact(cams, cap, hw, T):
         np.testing.assert_array_equal(d["dones"].cpu().numpy(), ref["dones"])
 
 
+def test_valid_slot_zero_gathers_the_reference_window_in_bounds():
+    """A valid slot idx < T (episode filler on the last slot, first transition on slot 0): the sampler must read the window the
+    reference reads (slots capacity-2, capacity-1: numpy's negative window index) - and nothing in front of the frame buffer
+    (compute-sanitizer caught the round-1 kernel reading slot -1)."""
+    cams, cap, hw = ("front",), 10, 128
+    dev, ora = _mk(cams, cap, hw, seed=5)
+    rng = np.random.default_rng(3)
+    for n in (8, 3):
+        for i, tr in enumerate(random_transitions(rng, n, cams, hw, mean_ep=10 ** 9)):
+            tr["dones"] = bool(i == n - 1)
+            tr["masks"] = np.float32(1.0)
+            dev.insert(tr)
+            ora.insert(tr)
+    dev.flush()
+    assert ora.valid[0] and bool(dev.valid[0].item())
+    idx = np.array([0, 1, 2, cap - 2, 0, 0], np.int32)
+    part = dict(ring=dev, seed=5, step=0, batch=len(idx), indx=torch.as_tensor(idx).cuda())
+    d = dev._gather_dict(part, True)
+    ref = ora.gather_packed(idx.astype(np.int64))
+    np.testing.assert_array_equal(d["observations"]["front"].cpu().numpy(), ref["observations"]["front"])
+    np.testing.assert_array_equal(d["observations"]["front"].cpu().numpy()[0], ora.frames["front"][[cap - 2, cap - 1]])
+    np.testing.assert_array_equal(d["observations"]["state"].cpu().numpy(), ref["observations"]["state"])
+
+
 def _crop_call(dev, part, B, key_obs, key_next, T=1, expl=None):
     from serl_b200 import _lib as L
     cams, (H, W, Cc) = dev.cams, dev.frame_shape
