@@ -154,9 +154,13 @@ def trunk_traffic(args):
 def workload_config(args):
     rl = (f" = {args.batch // 2} online + {args.batch - args.batch // 2} demo (50/50 RLPD, demo ring of 20 trajectories)" if args.rlpd else "")
     name = "BASELINE configs[2]" if (args.cams == 2 and args.rlpd) else ("BASELINE configs[1]" if args.cams == 1 and not args.rlpd else "custom")
+    if args.cams == 2 and args.batch == 2048:
+        name = "BASELINE configs[3] (dual camera, batch 2048, replay 200k sharded over the ranks)"
     return {"workload": f"{name}: async_drq_sim, {args.cams}x 128x128x3 camera(s), batch {args.batch} (global){rl}, replay {args.capacity} in HBM, "
                         "critic grad step incl. sampling + DrQ shift", "global_batch": args.batch, "cams": args.cams, "rlpd": bool(args.rlpd),
             "replay_capacity": args.capacity, "parallelism": f"dp{args.gpus}", "precision": args.precision,
+            "step_pipeline": ("on: sampler + frozen trunk of step i+1 overlap heads / all-reduce / Adam of step i (agent.pipeline_critic_steps; "
+                              "the next batch is drawn one call early, like the reference iterator's queue)" if os.environ.get("SERL_PIPELINE", "1") != "0" else "off"),
             "arithmetic": ("frozen ResNet-10 trunk: 16-bit operands on tcgen05 tensor cores with fp32 accumulation; trainable heads, losses, "
                            "Adam in fp32" if args.precision != "fp32" else "everything fp32 (CUDA cores): the 1e-5 parity build"),
             "l2": "inputs exceed L2: each step gathers fresh random frames from a multi-GB replay"}
@@ -250,6 +254,8 @@ class Workload:
         self.agent = make_drq_agent(42, self.transitions[0]["observations"], self.transitions[0]["actions"], image_keys=cams,
                                     encoder_type="resnet-pretrained", precision=args.precision)
         self.agent.data_parallel = world > 1
+        # cross-step pipeline (serl_b200/agents/continuous/drq.py): sampler + frozen trunk of step i+1 next to heads + Adam of step i
+        self.agent.pipeline_critic_steps = os.environ.get("SERL_PIPELINE", "1") != "0"
         if rlpd:                                                       # async_drq_sim.py:275-277: batch_size // 2 from each buffer
             half = self.B // 2
             self.demo = make_replay_buffer(env, capacity=20 * 101, type="memory_efficient_replay_buffer", image_keys=list(cams),
@@ -301,7 +307,7 @@ class Workload:
 def measure_single_camera(args, steps=100):
     """Supplementary measurement on BASELINE configs[1]: single camera, whole batch from one 100k ring."""
     w = Workload(args, 1, False, 100_000, args.batch)
-    for _ in range(5):
+    for _ in range(11):
         w.agent.update_critics(w.next_batch())
     ms = w.timed_steps(steps) / steps
     dt, h2d, d2h = w.e2e_steps(steps)
@@ -334,7 +340,10 @@ def run_b200(args):
     ev = lambda: torch.cuda.Event(enable_timing=True)
     clocks = ClockSampler(local)
     clocks.start()
-    for _ in range(max(args.warmup, 3)):
+    # W warm-up steps; the step has up to four CUDA-graph variants (serial; pipeline start "W"; steady state "P" on either engine of the
+    # ping-pong pair), each run eagerly once and captured on its second use: a few more untimed steps so that the timed region only replays
+    settle = 6 if agent.pipeline_critic_steps else 0
+    for _ in range(max(args.warmup, 3) + settle):
         agent.update_critics(w.next_batch())
     launches0 = agent.kernel_launches
     w0 = time.time()
@@ -424,7 +433,7 @@ def run_b200(args):
             "e2e": {"value": args.steps / (e2e_ms / 1e3), "unit": "steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "sustained": {"value": n_sus / (ms_sus / 1e3), "unit": "steps/s", "steps": n_sus, "seconds": ms_sus / 1e3,
                           "note": "same loop, run for >= --sustain-s seconds right after the K timed steps; the clock samples cover both"},
-            "gpu_launches": launches, "cuda_graph": True, "replicas_identical": replicas_identical,
+            "gpu_launches": launches, "cuda_graph": True, "replicas_identical": replicas_identical, "untimed_graph_settle_steps": settle,
             "sections_ms": {**{k: round(v, 4) for k, v in sec.items()},
                             "note": "eagerly launched steps, CUDA events per section, mean over steps, max over ranks; heads = encoder heads + critic / policy MLPs + losses + backward"},
             "roofline": {"kernel": TRUNK_KERNELS[args.precision != "fp32"], "bound": "tensor",

@@ -16,7 +16,7 @@ import re
 import sys
 from collections import OrderedDict, defaultdict
 
-TRUNK = re.compile(r"stem2?_tc_kernel|conv3x3_tc_kernel|conv3x3_res_kernel|conv_tc_kernel|stem_prep_kernel|pool_finish_kernel|affine_relu_kernel|"
+TRUNK = re.compile(r"stem2?_tc_kernel|conv3x3_tc_kernel|conv3x3_res_kernel|conv3x3s2_res_kernel|conv_tc_kernel|stem_prep_kernel|pool_finish_kernel|affine_relu_kernel|"
                    r"block_combine_kernel|gn_finalize_kernel|maxpool_affine_kernel|conv_igemm_f32|groupnorm_f32|maxpool3x3s2_f32|FillFunctor<float>")
 
 
@@ -46,8 +46,9 @@ def load(path):
 
 
 def last_step(launches):
-    starts = [i for i, l in enumerate(launches) if "rng_schedule_kernel" in l["name"] and i + 1 < len(launches)
-              and ("sample_" in launches[i + 1]["name"])]
+    # (the critic step's noise / dropout fills are prefetched right after the key schedule: the sampler follows within a few launches)
+    starts = [i for i, l in enumerate(launches) if "rng_schedule_kernel" in l["name"]
+              and any("sample_" in x["name"] for x in launches[i + 1:i + 6])]
     if len(starts) < 2:
         raise SystemExit(f"need two step boundaries, found {len(starts)}")
     return launches[starts[-2]:starts[-1]]

@@ -53,6 +53,17 @@ class SACAgent:
         self.explicit_randomness = None     # tests: dict with eps / dropout / subsample (and crop offsets)
         self.use_cuda_graphs = True         # replay the whole step as one CUDA graph from its 3rd identical call on
         self.section_events = None          # bench: list collecting (name, start event, end event) of eagerly launched steps
+        # Cross-step pipeline (DrQ pixel agent, opt-in): the frozen encoder of step i+1 does not depend on the parameters step i
+        # updates, so `update_critics` can run sampler + trunk of the NEXT sequential batch next to the heads / Adam of the current
+        # one (drq.py::_update_critics_pipelined).  The next batch is then drawn one call early - like the reference iterator's
+        # `queue_size=2` prefetch (data/replay_buffer.py:77-90) - and a call that does not continue the sequence falls back.
+        self.pipeline_critic_steps = False
+        self._pipe = None
+        self._eng_pair: Dict[int, list] = {}
+        self._keys_pair = [self._keys, torch.zeros_like(self._keys)]
+        self._rng_look = torch.zeros(2, dtype=torch.uint32, device=device)
+        self._pipe_stream = None
+        self._last_engine = None
         self._graphs = {}
         self._graphs_version = store.version   # captured graphs bake parameter-derived state (packed trunk weights, stem sign mask)
         self._launch_adj = 0                # graph capture / replay correction of the library's launch counter
@@ -116,8 +127,9 @@ class SACAgent:
         """Drops every captured CUDA graph (and the packed 16-bit trunk weights derived from the fp32 ones): called when
         parameters were written from outside the step (`state.replace(params=...)`, checkpoint restore)."""
         self._graphs.clear()
+        self._pipe = None
         self._graphs_version = self._store.version
-        for eng in self._engines.values():
+        for eng in list(self._engines.values()) + [e for pair in self._eng_pair.values() for e in pair]:
             eng.__dict__.pop("_tc_weights", None)
 
     # ---- engines ---------------------------------------------------------------------------------
@@ -148,6 +160,8 @@ class SACAgent:
         attributes); 2nd: capture + replay; later: replay only."""
         if self._graphs_version != self._store.version:          # TrainState.replace(params=...) since the last capture
             self.invalidate_graphs()
+        self._pipe = None                                        # any step outside the pipelined path consumes the key chain: prefetch is stale
+        self._keys = self._keys_pair[0]
         if key is None:
             return body(batch, False)
         entry = self._graphs.get(key)
@@ -213,18 +227,31 @@ class SACAgent:
             ident = torch.full((B, 2), 4, dtype=torch.int32, device=self.device)
             expl = (ident, ident)
         row = 0
-        for part in batch.parts:
+        # RLPD (concat_batches of an online and a demo handle): the parts gather disjoint output rows from different rings, so the
+        # second part's launch runs on side stream 0 next to the first (each launch alone is one partial wave of CTAs: latency-bound)
+        side = eng.side[0] if (graph_mode and len(batch.parts) == 2 and batch.parts[0]["ring"] is not batch.parts[1]["ring"]) else None
+        for pi, part in enumerate(batch.parts):
             ring = part["ring"]
             if cfg.pixel and ring.T != 1:
                 raise NotImplementedError("the trunk kernels take one frame per observation (obs_horizon=1), like every SERL example")
-            ring.launch_sample(part, out, crop_total=B, out_row_offset=row, key_obs=ops.key_ptr(keys, L.KEY_CROP_OBS),
-                               key_next=ops.key_ptr(keys, L.KEY_CROP_NEXT), explicit_off=expl,
-                               step_dev=ring.step_dev if graph_mode else None, record_event=not graph_mode)
-            eng.launches += 1
-            if graph_mode:
-                ops.counter_add(ring.step_dev, 1)
+            on_side = side is not None and pi == 1
+            if on_side:
+                side.fork()
+                side.__enter__()
+            try:
+                ring.launch_sample(part, out, crop_total=B, out_row_offset=row, key_obs=ops.key_ptr(keys, L.KEY_CROP_OBS),
+                                   key_next=ops.key_ptr(keys, L.KEY_CROP_NEXT), explicit_off=expl,
+                                   step_dev=ring.step_dev if graph_mode else None, record_event=not graph_mode)
                 eng.launches += 1
+                if graph_mode:
+                    ops.counter_add(ring.step_dev, 1)
+                    eng.launches += 1
+            finally:
+                if on_side:
+                    side.__exit__(None, None, None)
             row += part["batch"]
+        if side is not None:
+            side.join()
 
     def _handle_from_dict(self, batch: dict) -> BatchHandle:
         """Host / device dict in the reference layout -> a temporary HBM ring + explicit indices."""
@@ -374,7 +401,7 @@ class SACAgent:
         pass   # draw failures are surfaced lazily by check_status() to avoid a sync per step
 
     def check_status(self):
-        for eng in self._engines.values():
+        for eng in list(self._engines.values()) + [pair[1] for pair in self._eng_pair.values()]:
             if int(eng.status.item()):
                 raise L.SerlError("replay draw failed: no valid slot within the redraw budget")
             if getattr(eng, "fused", None) is not None:

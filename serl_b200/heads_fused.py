@@ -63,7 +63,12 @@ class FusedCritic:
         s1.fork()
         with s1:
             self._fill_rng(keys)
-        self._rng_prefetched = True
+        self._rng_prefetched = "side"
+
+    def fill_rng_now(self, keys):
+        """Same fills on the CURRENT stream, ahead of the step that consumes them (cross-step pipeline, drq.py)."""
+        self._fill_rng(keys)
+        self._rng_prefetched = "done"
 
     def critic_loss_and_grads(self, keys, grad_scale=1.0, explicit=None):
         eng = self.eng
@@ -75,8 +80,9 @@ class FusedCritic:
         err = self.error
         # ---- randomness of the policy pass on s' (dropout masks + sample noise; sac.py:122-128) ----
         if self._rng_prefetched:
-            eng.side[1].join()                                       # filled on side stream 1 while the sampler and the trunk ran
-            self._rng_prefetched = False
+            if self._rng_prefetched == "side":
+                eng.side[1].join()                                   # filled on side stream 1 while the sampler and the trunk ran
+            self._rng_prefetched = False                             # ("done": filled in stream order by the step pipeline)
         elif explicit is None:
             self._fill_rng(keys)
         else:

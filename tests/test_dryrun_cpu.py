@@ -198,3 +198,35 @@ def test_fused_heads_call_sequence(dry, monkeypatch):
     assert dry.count("serl_layernorm_tanh_fwd") == 0 and dry.count("serl_colsum_f32") == 0
     assert dry.count("serl_gemm_tf32x3") == 1                                  # the (S, 64) proprio weight gradient: fan-in not TMA-addressable
     assert dry.count("serl_critic_loss") == 1 and dry.count("serl_adam_polyak") == 1
+
+
+def test_pipelined_update_critics_call_sequence(dry):
+    """Host logic of the cross-step pipeline: the first call of a handle sequence runs two front ends (its own + the next step's),
+    every following sequential call runs one (the next step's) next to its heads; a call that breaks the sequence starts over."""
+    from serl_b200.utils.launcher import make_drq_agent
+    cams = ("front",)
+    rb = _ring(cams, 64, 128)
+    trs = random_transitions(np.random.default_rng(0), 40, cams, 128)
+    for tr in trs:
+        rb.insert(tr)
+    agent = make_drq_agent(1, trs[0]["observations"], trs[0]["actions"], image_keys=cams, encoder_type="resnet-pretrained", device="cpu",
+                           precision="fp16")
+    agent.pipeline_critic_steps = True
+    agent._graph_key = lambda tag, batch: ("dry",)                  # the dry device cannot capture graphs: pipelined path, eager bodies
+    agent.use_cuda_graphs = False
+    it = rb.get_iterator(sample_args={"batch_size": 4, "pack_obs_and_next_obs": True})
+    counts = []
+    for _ in range(3):
+        del dry[:]
+        agent.update_critics(next(it))
+        counts.append((dry.count("serl_replay_sample_crop"), dry.count("serl_stem_conv_pool_tc_h16"), dry.count("serl_critic_loss"), dry.count("serl_rng_schedule")))
+    assert counts == [(2, 2, 1, 2), (1, 1, 1, 1), (1, 1, 1, 1)]
+    assert agent.state.step == 3
+    next(it)                                                        # skip a handle: the prefetched batch is not the next one
+    del dry[:]
+    agent.update_critics(next(it))
+    assert dry.count("serl_replay_sample_crop") == 2 and dry.count("serl_critic_loss") == 1
+    del dry[:]
+    agent.update_high_utd(next(it), utd_ratio=1)                    # another entry point drops the prefetch
+    agent.update_critics(next(it))
+    assert dry.count("serl_replay_sample_crop") == 1 + 2
