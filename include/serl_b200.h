@@ -239,6 +239,11 @@ typedef struct serl_sle_problem {             /* SpatialLearnedEmbeddings (+ Dro
   const float* feat; const float* kernel; const uint8_t* keep_mask; float* out; int32_t ld_out;
 } serl_sle_problem;
 int serl_sle_fwd_multi(const serl_sle_problem* problems /*host*/, int num_problems, float keep, int N, int P, int C, int F, void* stream);
+typedef struct serl_sle_bwd_problem {         /* SLE kernel gradient: dkernel[p,c,f] = sum_n feat[n,p,c] * dout[n, c*8+f]              */
+  const float* feat; const float* dout; int32_t ld_dout; float* dkernel;
+} serl_sle_bwd_problem;
+int serl_sle_bwd_multi(const serl_sle_bwd_problem* problems /*host*/, int num_problems, float* workspace, size_t workspace_bytes,
+                       int N, int P, int C, int F, void* stream);
 typedef struct serl_enc_finish_problem {      /* out = tanh(LayerNorm(z + bias) * scale + ln_bias), z from k-split partials or a small dense */
   const float* partials; int32_t S;           /* (S, rows, D) partial products of serl_tgemm_tf32, or NULL                      */
   const float* x; int32_t ld_x; const float* w; int32_t K;   /* else z = x (rows, K) @ w (K, D): the proprio Dense, encoding.py:65 */
@@ -250,6 +255,7 @@ typedef struct serl_ln_bwd_problem {          /* LayerNorm + tanh backward; upst
   const float* dt; int32_t ld_dt; const float* dt2; int32_t ld_dt2; const float* dq; const float* head_w; int64_t head_w_stride;
   const float* t; int32_t ld_t; const float* xhat; const float* rstd; const float* scale; int32_t rows_per_group; int64_t group_stride;
   float* dz; float* dy; int32_t R, D;
+  int32_t dt_parts; int64_t dt_part_stride;   /* > 1: dt is the sum of dt_parts arrays (ensemble partials of serl_tgemm_tf32's PARTIAL epilogue) */
 } serl_ln_bwd_problem;
 int serl_layernorm_tanh_bwd_multi(const serl_ln_bwd_problem* problems /*host*/, int num_problems, void* stream);
 #define SERL_SMALL_GRAD_MAX_JOBS 12
@@ -288,6 +294,13 @@ int serl_critic_loss(const float* q, const float* q_next, const int32_t* sub, in
 int serl_actor_loss(const float* q, const float* logp, const float* lagrange, const float* da, int ld_da, const float* act,
                     int ld_act, const float* std, const float* log_std, const float* eps, float std_min, float std_max,
                     float grad_scale, float* dmu, float* dlogstd, float* info /*3*/, int E, int B, int A, void* stream);
+/* Behaviour cloning (agents/continuous/bc.py:36-76, launcher policy utils/launcher.py:26-47: Dense -> tanh, no LayerNorm):
+ * element-wise tanh forward / backward, and loss = -mean_b log N(a_b; mu_b, diag(clip(exp(log_std_b))^2)) with its gradients
+ * w.r.t. mu / log_std (scaled by grad_scale / B) and info = {actor_loss, mse} * grad_scale. */
+int serl_tanh_fwd(const float* z, float* out, int n, void* stream);
+int serl_tanh_bwd(const float* dt, const float* t, float* dz, int n, void* stream);
+int serl_bc_loss(const float* mu, const float* log_std, const float* actions, float std_min, float std_max, float grad_scale,
+                 float* dmu, float* dlogstd, float* info /*2*/, int B, int A, void* stream);
 int serl_temperature_loss(const float* logp, const float* lagrange, float target_entropy, float grad_scale,
                           float* dlagrange, float* info /*1*/, int B, void* stream);
 

@@ -70,6 +70,10 @@ class SleProblem(C.Structure):
     _fields_ = [("feat", vp), ("kernel", vp), ("keep_mask", vp), ("out", vp), ("ld_out", i32)]
 
 
+class SleBwdProblem(C.Structure):
+    _fields_ = [("feat", vp), ("dout", vp), ("ld_dout", i32), ("dkernel", vp)]
+
+
 class EncFinishProblem(C.Structure):
     _fields_ = [("partials", vp), ("S", i32), ("x", vp), ("ld_x", i32), ("w", vp), ("K", i32), ("bias", vp), ("ln_scale", vp), ("ln_bias", vp),
                 ("out", vp), ("ld_out", i32), ("xhat", vp), ("rstd", vp), ("D", i32)]
@@ -78,7 +82,7 @@ class EncFinishProblem(C.Structure):
 class LnBwdProblem(C.Structure):
     _fields_ = [("dt", vp), ("ld_dt", i32), ("dt2", vp), ("ld_dt2", i32), ("dq", vp), ("head_w", vp), ("head_w_stride", i64),
                 ("t", vp), ("ld_t", i32), ("xhat", vp), ("rstd", vp), ("scale", vp), ("rows_per_group", i32), ("group_stride", i64),
-                ("dz", vp), ("dy", vp), ("R", i32), ("D", i32)]
+                ("dz", vp), ("dy", vp), ("R", i32), ("D", i32), ("dt_parts", i32), ("dt_part_stride", i64)]
 
 
 class SmallGradJob(C.Structure):
@@ -157,6 +161,7 @@ _PROTOS = {
     "serl_gemm_tf32x3": [C.POINTER(GemmDesc), vp],
     "serl_tgemm_tf32": [C.POINTER(TgemmDesc), vp],
     "serl_sle_fwd_multi": [C.POINTER(SleProblem), C.c_int, f32, C.c_int, C.c_int, C.c_int, C.c_int, vp],
+    "serl_sle_bwd_multi": [C.POINTER(SleBwdProblem), C.c_int, vp, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, vp],
     "serl_enc_finish": [C.POINTER(EncFinishProblem), C.c_int, C.c_int, f32, vp],
     "serl_layernorm_tanh_bwd_multi": [C.POINTER(LnBwdProblem), C.c_int, vp],
     "serl_small_grads": [C.POINTER(SmallGradJob), C.c_int, vp],
@@ -172,6 +177,9 @@ _PROTOS = {
     "serl_critic_loss": [vp, vp, vp, C.c_int, vp, vp, vp, vp, C.c_int, f32, f32, vp, vp, vp, C.c_int, C.c_int, vp],
     "serl_actor_loss": [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp, vp, vp, f32, f32, f32, vp, vp, vp, C.c_int, C.c_int,
                         C.c_int, vp],
+    "serl_tanh_fwd": [vp, vp, C.c_int, vp],
+    "serl_tanh_bwd": [vp, vp, vp, C.c_int, vp],
+    "serl_bc_loss": [vp, vp, vp, f32, f32, f32, vp, vp, vp, C.c_int, C.c_int, vp],
     "serl_temperature_loss": [vp, vp, f32, f32, vp, vp, C.c_int, vp],
     "serl_adam_polyak": [C.POINTER(AdamDesc), vp],
 }

@@ -42,6 +42,16 @@ bool pdl_enabled() {
 }  // namespace serl
 
 extern "C" const char* serl_last_error(void) { return serl::g_err; }
+namespace serl {
+int balanced_grid(int items, int sms) {
+  static int full = -1;
+  if (full < 0) { const char* e = getenv("SERL_FULL_GRID"); full = (e && atoi(e) != 0) ? 1 : 0; }
+  if (items <= sms || full) return items < sms ? items : sms;
+  const int waves = (items + sms - 1) / sms;
+  return (items + waves - 1) / waves;
+}
+}  // namespace serl
+
 extern "C" int serl_version(void) { return 3; }
 extern "C" unsigned long long serl_launch_count(void) { return serl::launch_count(); }
 extern "C" int serl_set_pdl(int enabled) { serl::g_pdl = enabled ? 1 : 0; return SERL_OK; }

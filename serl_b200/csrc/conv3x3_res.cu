@@ -882,7 +882,7 @@ static int launch_conv3r(const serl_conv3x3_res_desc* d, cudaStream_t st) {
   a.has_res = d->res != nullptr; a.relu = d->relu; a.eps = d->eps;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  const int grid = a.n_items < sms ? a.n_items : sms;
+  const int grid = balanced_grid(a.n_items, sms);
   launch_k(kern, grid, R3_THREADS, smem, st, xmap, wmap, rmap, omap, a);
   return check_launch("conv3x3_res_kernel");
 }
@@ -932,7 +932,7 @@ static int launch_conv3s2(const serl_conv3x3s2_res_desc* d, cudaStream_t st) {
   a.n_items = ((d->N + IPU - 1) / IPU) * a.n_tiles_n; a.eps = d->eps;
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  const int grid = a.n_items < sms ? a.n_items : sms;
+  const int grid = balanced_grid(a.n_items, sms);
   launch_k(kern, grid, R3_THREADS, smem, st, xmap, wmap, pmap, omap, rmap, a);
   return check_launch("conv3x3s2_res_kernel");
 }

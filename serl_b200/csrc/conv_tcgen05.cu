@@ -1152,7 +1152,7 @@ static int launch_stem2_tc(const ConvTcArgs& a, int fmt, cudaStream_t st) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const int units = a.N * 4;
-  const int grid = units < sms ? units : sms;                   // persistent, one CTA per SM
+  const int grid = balanced_grid(units, sms);                   // persistent, one CTA per SM
   launch_k(kern, grid, TC_THREADS, smem, st, wmap, xmap, a);
   return check_launch("stem2_tc_kernel");
 }

@@ -43,6 +43,46 @@ __global__ void sle_fwd_multi_kernel(const __grid_constant__ SleMultiArgs a) {
   *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
 }
 
+// ---- SLE kernel gradient, P problems: partial[problem][chunk][p][c][f] = sum_{n in chunk} feat[n,p,c] * dout[n, c*8+f] ----------
+struct SleBwdArgs { serl_sle_bwd_problem p[SERL_HEADS_MAX_PROBLEMS]; float* partial; int P, N, Pp, C, chunks; };
+
+__global__ void sle_bwd_partial_multi_kernel(const __grid_constant__ SleBwdArgs a) {
+  pdl_prologue();
+  const serl_sle_bwd_problem& q = a.p[blockIdx.z];
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= a.Pp * a.C) return;
+  const int p = e / a.C, c = e - p * a.C;
+  const int ch = blockIdx.y;
+  const int per = ceil_div(a.N, a.chunks);
+  const int n0 = ch * per, n1 = min(a.N, n0 + per);
+  float acc[8];
+#pragma unroll
+  for (int f = 0; f < 8; ++f) acc[f] = 0.f;
+  for (int n = n0; n < n1; ++n) {
+    const float v = q.feat[((size_t)n * a.Pp + p) * a.C + c];
+    const float4 d0 = *reinterpret_cast<const float4*>(q.dout + (size_t)n * q.ld_dout + c * 8);
+    const float4 d1 = *reinterpret_cast<const float4*>(q.dout + (size_t)n * q.ld_dout + c * 8 + 4);
+    acc[0] = fmaf(v, d0.x, acc[0]); acc[1] = fmaf(v, d0.y, acc[1]); acc[2] = fmaf(v, d0.z, acc[2]); acc[3] = fmaf(v, d0.w, acc[3]);
+    acc[4] = fmaf(v, d1.x, acc[4]); acc[5] = fmaf(v, d1.y, acc[5]); acc[6] = fmaf(v, d1.z, acc[6]); acc[7] = fmaf(v, d1.w, acc[7]);
+  }
+  float* o = a.partial + (((size_t)blockIdx.z * a.chunks + ch) * a.Pp * a.C + e) * 8;
+  *reinterpret_cast<float4*>(o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  *reinterpret_cast<float4*>(o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
+// dkernel[problem][d] = sum_chunk partial[problem][chunk][d]: thread per 4 elements, fixed order
+__global__ void sle_bwd_reduce_multi_kernel(const __grid_constant__ SleBwdArgs a) {
+  pdl_prologue();
+  const serl_sle_bwd_problem& q = a.p[blockIdx.y];
+  const size_t D4 = (size_t)a.Pp * a.C * 2;                         // float4 elements
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D4) return;
+  const float4* src = reinterpret_cast<const float4*>(a.partial) + (size_t)blockIdx.y * a.chunks * D4 + i;
+  float4 s = src[0];
+  for (int ch = 1; ch < a.chunks; ++ch) { const float4 v = src[(size_t)ch * D4]; s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w; }
+  reinterpret_cast<float4*>(q.dkernel)[i] = s;
+}
+
 // ---- encoder finish: warp per row ---------------------------------------------------------------------------------------
 struct EncFinishArgs { serl_enc_finish_problem p[SERL_HEADS_MAX_PROBLEMS]; int P, rows; float eps; };
 
@@ -111,7 +151,12 @@ __global__ void __launch_bounds__(256) ln_tanh_bwd_multi_kernel(const __grid_con
     dy[j] = 0.f; xh[j] = 0.f;
     if (d < D) {
       const float tv = q.t[(size_t)row * q.ld_t + d];
-      float dt = q.dq ? dqv * hw[d] : q.dt[(size_t)row * q.ld_dt + d];
+      float dt;
+      if (q.dq) dt = dqv * hw[d];
+      else {
+        dt = q.dt[(size_t)row * q.ld_dt + d];
+        for (int pp = 1; pp < q.dt_parts; ++pp) dt += q.dt[(size_t)pp * q.dt_part_stride + (size_t)row * q.ld_dt + d];   // fixed order
+      }
       if (q.dt2) dt += q.dt2[(size_t)row * q.ld_dt2 + d];
       dy[j] = dt * (1.f - tv * tv);
       xh[j] = q.xhat[(size_t)row * D + d];
@@ -196,6 +241,27 @@ extern "C" int serl_sle_fwd_multi(const serl_sle_problem* problems, int num_prob
   a.P = num_problems; a.N = N; a.Pp = P; a.C = C; a.keep = keep;
   launch_k(sle_fwd_multi_kernel, dim3(ceil_div(N * C, 128), num_problems), 128, 0, ST(stream), a);
   return check_launch("sle_fwd_multi_kernel");
+}
+
+extern "C" int serl_sle_bwd_multi(const serl_sle_bwd_problem* problems, int num_problems, float* workspace, size_t workspace_bytes,
+                                  int N, int P, int C, int F, void* stream) {
+  if (!problems || num_problems < 1 || num_problems > SERL_HEADS_MAX_PROBLEMS || F != 8) { set_last_error("serl_sle_bwd_multi: 1..%d problems, num_features 8", SERL_HEADS_MAX_PROBLEMS); return SERL_ERR_INVALID; }
+  SleBwdArgs a{};
+  for (int i = 0; i < num_problems; ++i) {
+    a.p[i] = problems[i];
+    if (!a.p[i].feat || !a.p[i].dout || !a.p[i].dkernel || (a.p[i].ld_dout & 3) || (reinterpret_cast<uintptr_t>(a.p[i].dkernel) & 15)) {
+      set_last_error("serl_sle_bwd_multi: problem %d invalid", i); return SERL_ERR_INVALID;
+    }
+  }
+  int chunks = N >= 64 ? 16 : 1;
+  const size_t per = (size_t)P * C * F * sizeof(float) * num_problems;
+  while (chunks > 1 && per * chunks > workspace_bytes) chunks >>= 1;
+  if (!workspace || per * chunks > workspace_bytes) { set_last_error("serl_sle_bwd_multi: workspace too small (%zu needed)", per); return SERL_ERR_INVALID; }
+  a.partial = workspace; a.P = num_problems; a.N = N; a.Pp = P; a.C = C; a.chunks = chunks;
+  launch_k(sle_bwd_partial_multi_kernel, dim3(ceil_div(P * C, 128), chunks, num_problems), 128, 0, ST(stream), a);
+  if (int e = check_launch("sle_bwd_partial_multi_kernel")) return e;
+  launch_k(sle_bwd_reduce_multi_kernel, dim3(ceil_div(P * C * 2, 256), num_problems), 256, 0, ST(stream), a);
+  return check_launch("sle_bwd_reduce_multi_kernel");
 }
 
 extern "C" int serl_enc_finish(const serl_enc_finish_problem* problems, int num_problems, int rows, float eps, void* stream) {

@@ -258,6 +258,47 @@ __global__ void adam_polyak_kernel(const AdamArgs a) {
   if (a.polyak) a.target[i] = pn * a.tau + a.target[i] * (1.f - a.tau);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Behaviour cloning (agents/continuous/bc.py:36-76): Dense -> tanh layers of the launcher's BC policy (MLP without LayerNorm,
+// utils/launcher.py:26-47) and the loss  -mean_b log N(a_b; mu_b, diag(std_b^2)),  std = clip(exp(log_std), std_min, std_max).
+// ---------------------------------------------------------------------------------------------
+__global__ void tanh_fwd_kernel(const float* __restrict__ z, float* __restrict__ out, int n) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = tanhf(z[i]);
+}
+__global__ void tanh_bwd_kernel(const float* __restrict__ dt, const float* __restrict__ t, float* __restrict__ dz, int n) {
+  pdl_prologue();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float tv = t[i]; dz[i] = dt[i] * (1.f - tv * tv); }
+}
+// info[0] = actor_loss, info[1] = mse (both * grad_scale: see critic_loss_kernel); one CTA
+__global__ void __launch_bounds__(1024) bc_loss_kernel(const float* __restrict__ mu, const float* __restrict__ log_std, const float* __restrict__ act,
+                                                       float std_min, float std_max, float grad_scale, float* __restrict__ dmu,
+                                                       float* __restrict__ dls, float* __restrict__ info, int B, int A) {
+  pdl_prologue();
+  __shared__ float red[64];
+  float sl = 0.f, sm = 0.f;
+  const float inv = grad_scale / (float)B;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    float lp = 0.f, se = 0.f;
+    for (int j = 0; j < A; ++j) {
+      const float m = mu[b * A + j], ls = log_std[b * A + j], a = act[b * A + j];
+      const float raw = expf(ls);
+      const float sd = fminf(fmaxf(raw, std_min), std_max);
+      const float d = a - m, z = d / sd;
+      lp += -0.5f * z * z - logf(sd) - 0.918938533204672742f;
+      se += d * d;
+      dmu[b * A + j] = -(d / (sd * sd)) * inv;                                   // d(-logp)/dmu
+      const float dsd = -(d * d / (sd * sd * sd) - 1.f / sd) * inv;               // d(-logp)/dstd
+      dls[b * A + j] = (raw > std_min && raw < std_max) ? dsd * raw : 0.f;       // clip passes the gradient strictly inside only
+    }
+    sl -= lp; sm += se;
+  }
+  block_sum2(sl, sm, red);
+  if (threadIdx.x == 0) { info[0] = sl * inv; info[1] = sm * inv; }
+}
+
 __global__ void adam_tick_kernel(const AdamArgs a) {
   pdl_prologue();
   const int gid = threadIdx.x;
@@ -348,6 +389,21 @@ extern "C" int serl_temperature_loss(const float* logp, const float* lagrange, f
                                      float* dlagrange, float* info, int B, void* stream) {
   launch_k(temperature_loss_kernel, 1, 1024, 0, ST(stream), logp, lagrange, target_entropy, grad_scale, dlagrange, info, B);
   return check_launch("temperature_loss_kernel");
+}
+
+extern "C" int serl_tanh_fwd(const float* z, float* out, int n, void* stream) {
+  launch_k(tanh_fwd_kernel, ceil_div(n, 256), 256, 0, ST(stream), z, out, n);
+  return check_launch("tanh_fwd_kernel");
+}
+extern "C" int serl_tanh_bwd(const float* dt, const float* t, float* dz, int n, void* stream) {
+  launch_k(tanh_bwd_kernel, ceil_div(n, 256), 256, 0, ST(stream), dt, t, dz, n);
+  return check_launch("tanh_bwd_kernel");
+}
+extern "C" int serl_bc_loss(const float* mu, const float* log_std, const float* actions, float std_min, float std_max, float grad_scale,
+                            float* dmu, float* dlogstd, float* info, int B, int A, void* stream) {
+  if (!mu || !log_std || !actions || !dmu || !dlogstd || !info || B < 1 || A < 1) { set_last_error("serl_bc_loss: invalid arguments"); return SERL_ERR_INVALID; }
+  launch_k(bc_loss_kernel, 1, 1024, 0, ST(stream), mu, log_std, actions, std_min, std_max, grad_scale, dmu, dlogstd, info, B, A);
+  return check_launch("bc_loss_kernel");
 }
 
 extern "C" int serl_adam_polyak(const serl_adam_desc* d, void* stream) {

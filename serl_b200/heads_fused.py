@@ -54,6 +54,9 @@ class FusedCritic:
         ops.normal_fill(ops.key_ptr(keys, L.KEY_CRITIC_NEXT), eng.eps, B * A)
         for j, cam in enumerate(cfg.cams):
             ops.dropout_mask_fill(ops.key_ptr(keys, L.KEY_CRITIC_NEXT), j, 0.9, eng.masks_u8[cam], B * 4096)
+        if cfg.subsample is not None:                                 # the TD target's ensemble subsample (sac.py:152-158) is key-only too
+            ops.subsample_idx(ops.key_ptr(keys, L.KEY_CRITIC_SUBSAMPLE), cfg.ensemble, eng.sub, cfg.subsample)
+            eng.launches += 1
         eng.launches += 1 + len(cfg.cams)
 
     def prefetch_rng(self, keys):
@@ -149,10 +152,7 @@ class FusedCritic:
         # ---- TD target, loss, dQ (sac.py:134-191) ----
         n_sub = 0
         if cfg.subsample is not None:
-            if explicit is None:
-                ops.subsample_idx(ops.key_ptr(keys, L.KEY_CRITIC_SUBSAMPLE), E, eng.sub, cfg.subsample)
-                eng.launches += 1
-            else:
+            if explicit is not None:                                 # (drawn with the other key-only randomness otherwise: _fill_rng)
                 eng.sub.copy_(explicit["critic"]["subsample"])
             n_sub = cfg.subsample
         ops.critic_loss(eng.q, eng.q_next, eng.sub, n_sub, eng.rewards, eng.masks, eng.logp, P(Pm, "modules_temperature/lagrange"),
@@ -198,23 +198,25 @@ class FusedCritic:
                 (L.SMALL_GRAD_HEAD, cm.h2.data_ptr(), 256, eng.dq.data_ptr(), 1, P(G, "modules_critic/Dense_0/kernel"), P(G, "modules_critic/Dense_0/bias"), 1, R, 256),
             ])
         # d enc = sum_e dz1[e] @ W1[e][:F]^T  (the input is broadcast over the ensemble; only the encoder columns are needed)
-        ops.tgemm(eng.ws, [ops.tgemm_problem(dz1.data_ptr(), P(Pm, f"{c}/Dense_0/kernel"), sAm=256, sAk=1, sBk=1, sBn=256, Z=E, sAz=B * 256, sBz=FA * 256,
-                                             C_=eng.dX.data_ptr(), sCz=0, ldc=FA)], B, F, 256, reduce_z=True, error=err)
-        eng.launches += 9
+        # (the E partial products stay in the workspace; the encoder heads' LayerNorm backward sums them while it reads them)
+        ops.tgemm(eng.ws, [ops.tgemm_problem(dz1.data_ptr(), P(Pm, f"{c}/Dense_0/kernel"), sAm=256, sAk=1, sBk=1, sBn=256, Z=E, sAz=B * 256, sBz=FA * 256)],
+                  B, F, 256, epilogue=L.TGEMM_PARTIAL, splits=1, error=err)
+        dXp, parts = eng.ws.buf, dict(dt_parts=E, dt_part_stride=B * F)
+        eng.launches += 8
         # ---- trainable encoder heads ----
         off = 256 * ncam
         lnb, wg, dsle, jobs = [], [], [], []
         for j, cam in enumerate(cfg.cams):
             p = f"{ENC}/encoder_{cam}"
             dez, dey = eng.d_enc_z[cam], eng.d_enc_y[cam]
-            lnb.append(dict(dt=ops.at(eng.dX, 256 * j), ld_dt=FA, t=ops.at(eng.Xc, 256 * j), ld_t=FA, xhat=eng.enc_xhat[cam].data_ptr(),
+            lnb.append(dict(dt=ops.at(dXp, 256 * j), ld_dt=F, **parts, t=ops.at(eng.Xc, 256 * j), ld_t=FA, xhat=eng.enc_xhat[cam].data_ptr(),
                             rstd=eng.enc_rstd[cam].data_ptr(), scale=P(Pm, f"{p}/LayerNorm_0/scale"), rows_per_group=B, group_stride=0,
                             dz=dez.data_ptr(), dy=dey.data_ptr(), R=B, D=256))
             wg.append(ops.tgemm_problem(eng.sle_saved[cam].data_ptr(), dez.data_ptr(), sAm=1, sAk=4096, sBk=256, sBn=1, C_=P(G, f"{p}/Dense_0/kernel"), ldc=256))
             dsle.append(ops.tgemm_problem(dez.data_ptr(), P(Pm, f"{p}/Dense_0/kernel"), sAm=256, sAk=1, sBk=1, sBn=256, C_=self.d_sle[cam].data_ptr(), ldc=4096))
             jobs.append((L.SMALL_GRAD_COLSUM, dez.data_ptr(), 256, None, 0, P(G, f"{p}/Dense_0/bias"), None, 1, B, 256))
             jobs.append((L.SMALL_GRAD_LN, dey.data_ptr(), 256, eng.enc_xhat[cam].data_ptr(), 256, P(G, f"{p}/LayerNorm_0/scale"), P(G, f"{p}/LayerNorm_0/bias"), 1, B, 256))
-        lnb.append(dict(dt=ops.at(eng.dX, off), ld_dt=FA, t=ops.at(eng.Xc, off), ld_t=FA, xhat=eng.enc_xhat_p.data_ptr(), rstd=eng.enc_rstd_p.data_ptr(),
+        lnb.append(dict(dt=ops.at(dXp, off), ld_dt=F, **parts, t=ops.at(eng.Xc, off), ld_t=FA, xhat=eng.enc_xhat_p.data_ptr(), rstd=eng.enc_rstd_p.data_ptr(),
                         scale=P(Pm, f"{ENC}/LayerNorm_0/scale"), rows_per_group=B, group_stride=0, dz=eng.d_enc_zp.data_ptr(), dy=eng.d_enc_yp.data_ptr(), R=B, D=64))
         jobs.append((L.SMALL_GRAD_COLSUM, eng.d_enc_zp.data_ptr(), 64, None, 0, P(G, f"{ENC}/Dense_0/bias"), None, 1, B, 64))
         jobs.append((L.SMALL_GRAD_LN, eng.d_enc_yp.data_ptr(), 64, eng.enc_xhat_p.data_ptr(), 64, P(G, f"{ENC}/LayerNorm_0/scale"), P(G, f"{ENC}/LayerNorm_0/bias"), 1, B, 64))
@@ -225,9 +227,8 @@ class FusedCritic:
             ops.small_grads(jobs)
             ops.dense_bwd_weight(wss, eng.state_o.data_ptr(), cfg.state_in, eng.d_enc_zp.data_ptr(), 64, P(G, f"{ENC}/Dense_0/kernel"), B, cfg.state_in, 64)
         ops.tgemm(eng.ws, dsle, B, 4096, 256, splits=1, error=err)
-        for cam in cfg.cams:
-            ops.sle_bwd_kernel_grad(eng.ws, eng.feats[cam][slice(0, B)], self.d_sle[cam].data_ptr(), 4096,
-                                    P(G, f"{ENC}/encoder_{cam}/SpatialLearnedEmbeddings_0/kernel"))
+        ops.sle_bwd_multi(eng.ws, [(eng.feats[cam][slice(0, B)].data_ptr(), self.d_sle[cam].data_ptr(), 4096,
+                                    P(G, f"{ENC}/encoder_{cam}/SpatialLearnedEmbeddings_0/kernel")) for cam in cfg.cams], B, 16, 512)
         side.join()
         eng.launches += 6 + 2 * ncam
 

@@ -243,6 +243,14 @@ def sle_fwd_multi(problems, keep, N, P, C_):
     L.call("serl_sle_fwd_multi", arr, len(problems), float(keep), N, P, C_, 8, _s())
 
 
+def sle_bwd_multi(ws: Workspace, problems, N, P, C_):
+    """problems: (feat, dout, ld_dout, dkernel) device addresses; SLE kernel gradients of all cameras in two launches."""
+    arr = (L.SleBwdProblem * len(problems))()
+    for q, (feat, dout, ld, dk) in zip(arr, problems):
+        q.feat, q.dout, q.ld_dout, q.dkernel = feat, dout, ld, dk
+    L.call("serl_sle_bwd_multi", arr, len(problems), ws.buf.data_ptr(), ws.nbytes, N, P, C_, 8, _s())
+
+
 def enc_finish(problems, rows, eps=1e-6):
     """problems: dicts with partials+S or x+ld_x+w+K, and bias, ln_scale, ln_bias, out, ld_out, D, optional xhat, rstd."""
     arr = (L.EncFinishProblem * len(problems))()
@@ -262,6 +270,7 @@ def ln_tanh_bwd_multi(problems):
         q.dq, q.head_w, q.head_w_stride = p.get("dq"), p.get("head_w"), p.get("head_w_stride", 0)
         q.t, q.ld_t, q.xhat, q.rstd, q.scale = p["t"], p["ld_t"], p["xhat"], p["rstd"], p["scale"]
         q.rows_per_group, q.group_stride, q.dz, q.dy, q.R, q.D = p["rows_per_group"], p.get("group_stride", 0), p["dz"], p.get("dy"), p["R"], p["D"]
+        q.dt_parts, q.dt_part_stride = p.get("dt_parts", 1), p.get("dt_part_stride", 0)
     L.call("serl_layernorm_tanh_bwd_multi", arr, len(problems), _s())
 
 

@@ -1,13 +1,23 @@
 """Launcher factories with the reference's names and hyper-parameters (utils/launcher.py:50-116,201-272):
-`make_sac_agent`, `make_drq_agent`, `make_replay_buffer`, `make_trainer_config`, `make_wandb_logger`.
+`make_bc_agent`, `make_sac_agent`, `make_drq_agent`, `make_replay_buffer`, `make_trainer_config`, `make_wandb_logger`.
 """
 from __future__ import annotations
 
 from typing import Optional
 
+from ..agents.continuous.bc import BCAgent
 from ..agents.continuous.drq import DrQAgent
 from ..agents.continuous.sac import SACAgent
 from ..data.data_store import MemoryEfficientReplayBufferDataStore, ReplayBufferDataStore
+
+
+def make_bc_agent(seed, sample_obs, sample_action, image_keys=("image",), encoder_type="small", precision="fp32", device=None):
+    """utils/launcher.py:26-47."""
+    return BCAgent.create(
+        seed, sample_obs, sample_action,
+        network_kwargs={"activations": "tanh", "use_layer_norm": False, "hidden_dims": [256, 256]},
+        policy_kwargs={"tanh_squash_distribution": False, "std_parameterization": "exp", "std_min": 1e-5, "std_max": 5},
+        use_proprio=True, encoder_type=encoder_type, image_keys=image_keys, precision=precision, device=device)
 
 
 def make_sac_agent(seed, sample_obs, sample_action, discount=0.99, device=None):

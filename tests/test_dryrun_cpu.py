@@ -230,3 +230,31 @@ def test_pipelined_update_critics_call_sequence(dry):
     agent.update_high_utd(next(it), utd_ratio=1)                    # another entry point drops the prefetch
     agent.update_critics(next(it))
     assert dry.count("serl_replay_sample_crop") == 1 + 2
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+def test_bc_agent_call_sequence(dry, precision):
+    """Host logic of BCAgent.update / sample_actions: one trunk pass per camera, the image heads are forward-only
+    (stop_gradient), the proprio encoder and the tanh MLP (no LayerNorm) are differentiated, one Adam."""
+    from serl_b200.utils.launcher import make_bc_agent
+    cams = ("front", "wrist")
+    trs = random_transitions(np.random.default_rng(0), 6, cams, 128)
+    agent = make_bc_agent(1, trs[0]["observations"], trs[0]["actions"], image_keys=cams, encoder_type="resnet-pretrained", device="cpu", precision=precision)
+    batch = {"observations": {**{c: np.stack([t["observations"][c] for t in trs]) for c in cams}, "state": np.stack([t["observations"]["state"] for t in trs])},
+             "actions": np.stack([t["actions"] for t in trs]).astype(np.float32)}
+    rng0 = agent.state.rng
+    del dry[:]
+    agent, info = agent.update(batch)
+    assert set(info) == {"actor_loss", "mse"} and agent.state.step == 1 and not np.array_equal(agent.state.rng, rng0)
+    assert dry.count("serl_sle_fwd") == 2 and dry.count("serl_dropout_mask_fill") == 2 and dry.count("serl_bc_loss") == 1
+    assert dry.count("serl_tanh_fwd") == 2 and dry.count("serl_tanh_bwd") == 2 and dry.count("serl_adam_polyak") == 1
+    assert dry.count("serl_layernorm_tanh_fwd") == 3 and dry.count("serl_layernorm_tanh_bwd") == 1      # heads forward; only the proprio LN backward
+    gemm = "serl_gemm_f32" if precision == "fp32" else "serl_gemm_tf32x3"
+    assert dry.count(gemm) == (2 + 1 + 4) + (2 + 2 + 1 + 1 + 1 + 1 + 1)        # forward: 2 image heads, proprio, 4 policy; backward: head dW x2, head dX x2, dW2, dh1, dW1, d proprio, dW proprio
+    tree = agent.state.params
+    assert tree["modules_actor"]["network"]["Dense_0"]["kernel"].shape == (256 * 2 + 64, 256) and "LayerNorm_0" not in tree["modules_actor"]["network"]
+    a = agent.sample_actions({k: v[0] for k, v in batch["observations"].items()}, argmax=True)
+    assert a.shape == (4,)
+    a = agent.sample_actions(batch["observations"], seed=np.array([0, 3], np.uint32))
+    assert a.shape == (6, 4)
+    agent.state.replace(params=tree)
