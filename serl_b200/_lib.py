@@ -285,9 +285,9 @@ class _Side:
     """A side stream with fork / join against the CURRENT stream (works eagerly and under CUDA-graph capture, where the
     event dependencies become fork / join edges of the captured graph).  Entering it makes it the current stream."""
 
-    def __init__(self, device):
+    def __init__(self, device, priority: int = 0):
         import torch
-        self.s = torch.cuda.Stream(device)
+        self.s = torch.cuda.Stream(device, priority=priority)
         self._ctx = None
 
     def fork(self):                 # side stream waits for everything enqueued on the current stream so far
@@ -322,8 +322,10 @@ class _NoSide:
     def __exit__(self, *a): return False
 
 
-def new_side_stream(device, enabled=True):
-    return _Side(device) if enabled and device.type == "cuda" else _NoSide()
+def new_side_stream(device, enabled=True, priority: int = 0):
+    """priority < 0: a high-priority stream (its kernels' CTAs are placed before those of default-priority streams whenever an SM
+    frees up; captured into CUDA-graph kernel nodes)."""
+    return _Side(device, priority) if enabled and device.type == "cuda" else _NoSide()
 
 
 def pin(t):

@@ -46,6 +46,9 @@ namespace serl {
 int balanced_grid(int items, int sms) {
   static int full = -1;
   if (full < 0) { const char* e = getenv("SERL_FULL_GRID"); full = (e && atoi(e) != 0) ? 1 : 0; }
+  static int limit = -1;                                          // SERL_TRUNK_SM_LIMIT=n: at most n CTAs (experiments: SM share of the trunk)
+  if (limit < 0) { const char* e = getenv("SERL_TRUNK_SM_LIMIT"); limit = e ? atoi(e) : 0; }
+  if (limit > 0 && limit < sms) sms = limit;
   if (items <= sms || full) return items < sms ? items : sms;
   const int waves = (items + sms - 1) / sms;
   return (items + waves - 1) / waves;
