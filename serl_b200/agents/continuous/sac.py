@@ -31,6 +31,7 @@ ALL_NETS = frozenset({"actor", "critic", "temperature"})
 
 
 _HEADS_PDL = os.environ.get("SERL_HEADS_PDL", "0") not in ("", "0")
+_SPLIT_ALLREDUCE = os.environ.get("SERL_SPLIT_ALLREDUCE", "1") not in ("", "0")
 
 
 def _dist():
@@ -351,6 +352,15 @@ class SACAgent:
         heads_pdl = _HEADS_PDL and torch.device(self.device).type == "cuda"
         if heads_pdl:
             L.call("serl_set_pdl", 1)
+        # data-parallel critic step on the fused heads: the critic-MLP gradients (+ the info scalars right behind them in the flat
+        # buffer) are complete while the encoder backward still runs - their all-reduce goes out on the weight-gradient side stream
+        # and overlaps it; the encoder segment follows at the end (two collectives, the first one hidden)
+        early = None
+        fused = getattr(eng, "fused", None)
+        if dp and fused is not None and nets == frozenset({"critic"}) and _SPLIT_ALLREDUCE:
+            c0 = st.leaf["modules_critic/network/Dense_0/kernel"].offset
+            early = (c0, st.info_off + 4)
+            fused.early_allreduce = lambda: self._allreduce(*early)
         with self._section("heads"):
             if "critic" in nets:
                 eng.critic_loss_and_grads(self._keys, grad_scale=gscale, explicit=expl)
@@ -363,7 +373,11 @@ class SACAgent:
         if dp and nets:
             # [group 0 | critic infos] and/or [actor, temperature infos | groups 1, 2 | aux]: one contiguous range either way
             with self._section("allreduce"):
-                self._allreduce(0 if "critic" in nets else st.info_off + 4, st.n if at else st.info_off + 4)
+                if early is not None:
+                    fused.early_allreduce = None
+                    self._allreduce(0, early[0])
+                else:
+                    self._allreduce(0 if "critic" in nets else st.info_off + 4, st.n if at else st.info_off + 4)
         with self._section("adam_polyak"):
             eng.optimizer_step([int("critic" in nets), int("actor" in nets), int("temperature" in nets)], polyak="critic" in nets)
         self.state.step += 1

@@ -46,6 +46,7 @@ class FusedCritic:
         self.ws_enc = ops.Workspace(nprob * self.S * B * 256 * 4, dev)
         self.error = torch.zeros(1, dtype=torch.int32, device=dev)
         self._rng_prefetched = False
+        self.early_allreduce = None           # data parallel: callable that all-reduces [critic MLP gradients | infos] (set per step by the agent)
 
     # ------------------------------------------------------------------------------------------------------------
     def _fill_rng(self, keys):
@@ -197,6 +198,8 @@ class FusedCritic:
                 (L.SMALL_GRAD_LN, dy1.data_ptr(), 256, cm.xhat1.data_ptr(), 256, P(G, f"{c}/LayerNorm_0/scale"), P(G, f"{c}/LayerNorm_0/bias"), E, B, 256),
                 (L.SMALL_GRAD_HEAD, cm.h2.data_ptr(), 256, eng.dq.data_ptr(), 1, P(G, "modules_critic/Dense_0/kernel"), P(G, "modules_critic/Dense_0/bias"), 1, R, 256),
             ])
+            if self.early_allreduce is not None:                     # every critic-MLP / value-head gradient is enqueued on this stream
+                self.early_allreduce()
         # d enc = sum_e dz1[e] @ W1[e][:F]^T  (the input is broadcast over the ensemble; only the encoder columns are needed)
         # (the E partial products stay in the workspace; the encoder heads' LayerNorm backward sums them while it reads them)
         ops.tgemm(eng.ws, [ops.tgemm_problem(dz1.data_ptr(), P(Pm, f"{c}/Dense_0/kernel"), sAm=256, sAk=1, sBk=1, sBn=256, Z=E, sAz=B * 256, sBz=FA * 256)],
@@ -221,14 +224,17 @@ class FusedCritic:
         jobs.append((L.SMALL_GRAD_COLSUM, eng.d_enc_zp.data_ptr(), 64, None, 0, P(G, f"{ENC}/Dense_0/bias"), None, 1, B, 64))
         jobs.append((L.SMALL_GRAD_LN, eng.d_enc_yp.data_ptr(), 64, eng.enc_xhat_p.data_ptr(), 64, P(G, f"{ENC}/LayerNorm_0/scale"), P(G, f"{ENC}/LayerNorm_0/bias"), 1, B, 64))
         ops.ln_tanh_bwd_multi(lnb)
-        side.fork()
-        with side:
-            ops.tgemm(wss, wg, 4096, 256, B, splits=1, error=err)
+        # encoder weight gradients on side stream 1: stream 0 may be busy with the early all-reduce of the critic bucket
+        side1, wss1 = eng.side[1], eng.ws_side[1]
+        side1.fork()
+        with side1:
+            ops.tgemm(wss1, wg, 4096, 256, B, splits=1, error=err)
             ops.small_grads(jobs)
-            ops.dense_bwd_weight(wss, eng.state_o.data_ptr(), cfg.state_in, eng.d_enc_zp.data_ptr(), 64, P(G, f"{ENC}/Dense_0/kernel"), B, cfg.state_in, 64)
+            ops.dense_bwd_weight(wss1, eng.state_o.data_ptr(), cfg.state_in, eng.d_enc_zp.data_ptr(), 64, P(G, f"{ENC}/Dense_0/kernel"), B, cfg.state_in, 64)
         ops.tgemm(eng.ws, dsle, B, 4096, 256, splits=1, error=err)
         ops.sle_bwd_multi(eng.ws, [(eng.feats[cam][slice(0, B)].data_ptr(), self.d_sle[cam].data_ptr(), 4096,
                                     P(G, f"{ENC}/encoder_{cam}/SpatialLearnedEmbeddings_0/kernel")) for cam in cfg.cams], B, 16, 512)
+        side1.join()
         side.join()
         eng.launches += 6 + 2 * ncam
 

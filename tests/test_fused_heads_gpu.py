@@ -83,3 +83,36 @@ def test_fused_critic_step_matches_oracle_and_unfused_chain(cams, B, monkeypatch
                     got = st.view(st.grad, leaf.path).cpu().numpy()
                     assert np.abs(got - ref).max() <= 2e-2 * max(np.abs(ref).max(), 1e-8), leaf.path
     agent.check_status()
+
+
+def test_learner_iteration_on_the_fp16_build_mixes_fused_critic_and_per_op_actor_step():
+    """examples/async_drq_sim/async_drq_sim.py:266-292 on the 16-bit build: `update_critics` (fused head kernels) then
+    `update_high_utd(utd_ratio=1)` (critic step on the fused kernels, actor / temperature step on the per-op chain, shared buffers),
+    eager then graph-replayed, against the oracle: every info scalar within 1e-2, the key chain bit-exact."""
+    from oracle import drq as O
+    from oracle.replay import unpack
+    cams, B = ("front", "wrist"), 12
+    agent, rb = _setup(cams)
+    ocfg = oracle_cfg_from_agent(agent)
+    it = rb.get_iterator(sample_args={"batch_size": B, "pack_obs_and_next_obs": True})
+    close = lambda got, ref: abs(float(got) - ref) <= 1e-2 * max(abs(ref), 1e-2)
+    for rep in range(3):
+        ostate = oracle_state_from_agent(agent)
+        batch = next(it)
+        host = unpack(to_numpy_tree({k: v for k, v in batch.to_dict().items() if k != "_indices"}))
+        agent, info = agent.update_critics(batch)
+        oc = O.update_critics(ostate, ocfg, host)
+        assert close(info["critic"]["critic_loss"], oc["critic"]["critic_loss"]), (rep, float(info["critic"]["critic_loss"]), oc["critic"]["critic_loss"])
+        np.testing.assert_array_equal(agent.state.rng, ostate.rng)
+        ostate = oracle_state_from_agent(agent)
+        batch = next(it)
+        host = unpack(to_numpy_tree({k: v for k, v in batch.to_dict().items() if k != "_indices"}))
+        agent, info = agent.update_high_utd(batch, utd_ratio=1)
+        oi = O.update_high_utd(ostate, ocfg, host, 1)
+        for k in ("critic_loss", "predicted_qs", "target_qs"):
+            assert close(info["critic"][k], oi["critic"][k]), (rep, k, float(info["critic"][k]), oi["critic"][k])
+        for k in ("actor_loss", "temperature", "entropy"):
+            assert close(info["actor"][k], oi["actor"][k]), (rep, k, float(info["actor"][k]), oi["actor"][k])
+        assert close(info["temperature"]["temperature_loss"], oi["temperature"]["temperature_loss"])
+        np.testing.assert_array_equal(agent.state.rng, ostate.rng)
+    agent.check_status()
