@@ -31,7 +31,7 @@ ALL_NETS = frozenset({"actor", "critic", "temperature"})
 
 
 _HEADS_PDL = os.environ.get("SERL_HEADS_PDL", "0") not in ("", "0")
-_SPLIT_ALLREDUCE = os.environ.get("SERL_SPLIT_ALLREDUCE", "1") not in ("", "0")
+_SPLIT_ALLREDUCE = os.environ.get("SERL_SPLIT_ALLREDUCE", "0") not in ("", "0")
 
 
 def _dist():
@@ -352,9 +352,11 @@ class SACAgent:
         heads_pdl = _HEADS_PDL and torch.device(self.device).type == "cuda"
         if heads_pdl:
             L.call("serl_set_pdl", 1)
-        # data-parallel critic step on the fused heads: the critic-MLP gradients (+ the info scalars right behind them in the flat
-        # buffer) are complete while the encoder backward still runs - their all-reduce goes out on the weight-gradient side stream
-        # and overlaps it; the encoder segment follows at the end (two collectives, the first one hidden)
+        # SERL_SPLIT_ALLREDUCE=1 (experimental, off: ONE collective per step by default): the critic-MLP gradients (+ the info scalars
+        # right behind them in the flat buffer) are complete while the encoder backward still runs - their all-reduce goes out on the
+        # weight-gradient side stream and overlaps it, the encoder segment follows at the end.  Measured on 2 GPUs (trunk-bound per
+        # rank, the heads chain is hidden by the step pipeline): 1186 vs 1200 steps/s, i.e. the extra collective costs more than it
+        # hides there; not measured at 8 GPUs, where the heads chain + all-reduce is what bounds the step.
         early = None
         fused = getattr(eng, "fused", None)
         if dp and fused is not None and nets == frozenset({"critic"}) and _SPLIT_ALLREDUCE:
