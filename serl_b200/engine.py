@@ -451,6 +451,8 @@ class Engine:
 
     def actor_temp_loss_and_grads(self, keys, grad_scale=1.0, explicit=None, do_actor=True, do_temperature=True):
         """sac.py:193-234 + gradients w.r.t. group-1 / group-2 parameters (and the actor-tx twin of the proprio encoder)."""
+        if self.fused is not None and os.environ.get("SERL_FUSED_ACTOR", "1") != "0":
+            return self.fused.actor_temp_loss_and_grads(keys, grad_scale=grad_scale, explicit=explicit, do_actor=do_actor, do_temperature=do_temperature)
         cfg, B, E, A, st = self.cfg, self.B, self.cfg.ensemble, self.cfg.action_dim, self.store
         obs_rows, next_rows = slice(0, B), slice(B, 2 * B)
         lam = self.P(st.params, "modules_temperature/lagrange")

@@ -238,6 +238,125 @@ class FusedCritic:
         side.join()
         eng.launches += 6 + 2 * ncam
 
+    # ------------------------------------------------------------------------------------------------------------
+    def actor_temp_loss_and_grads(self, keys, grad_scale=1.0, explicit=None, do_actor=True, do_temperature=True):
+        """sac.py:193-234 on the fused kernels: the forward passes of the actor loss (policy on s with dropout, saved; critic on
+        (s, pi(s)) with constant parameters) and of the temperature loss (policy on s' with a fresh dropout mask / sample) share
+        one SLE launch, one k-split GEMM launch and one finish launch for their encoder passes and one launch per policy layer;
+        the gradient w.r.t. the ACTION columns comes back through the same TF32 GEMMs.  The loss kernels and the policy backward
+        (engine.policy_backward: policy MLP, heads and the proprio encoder's actor-tx twin) are the per-op ones."""
+        eng = self.eng
+        cfg, B, E, A, st = eng.cfg, eng.B, eng.cfg.ensemble, eng.cfg.action_dim, eng.store
+        F, FA, ncam, S = eng.F, eng.FA, self.ncam, self.S
+        Pm, P, err = st.params, eng.P, self.error
+        obs_rows, next_rows = slice(0, B), slice(B, 2 * B)
+        lam = P(Pm, "modules_temperature/lagrange")
+        if not hasattr(self, "Xp_t"):
+            e = lambda *sh: torch.empty(*sh, dtype=f32, device=eng.dev)
+            self.Xp_t, self.eps_t, self.logp_t, self.h1_t, self.act_t = e(B, F), e(B, A), e(B), e(B, 256), e(B, A)
+            self.masks_t = {c: torch.empty(B, 4096, dtype=torch.uint8, device=eng.dev) for c in cfg.cams}
+            self.sle_c2 = {c: e(B, 4096) for c in cfg.cams}
+        # ---- randomness ----
+        jobs = []
+        if do_actor:
+            jobs.append((eng.eps, eng.masks_u8, L.KEY_ACTOR_SAMPLE, L.KEY_ACTOR_DROPOUT, None if explicit is None else explicit["actor"]))
+        if do_temperature:
+            jobs.append((self.eps_t, self.masks_t, L.KEY_TEMP_NEXT, L.KEY_TEMP_NEXT, None if explicit is None else explicit["temperature"]))
+        for eps, masks, k_eps, k_drop, ex in jobs:
+            if ex is None:
+                ops.normal_fill(ops.key_ptr(keys, k_eps), eps, B * A)
+                for j, cam in enumerate(cfg.cams):
+                    ops.dropout_mask_fill(ops.key_ptr(keys, k_drop), j, 0.9, masks[cam], B * 4096)
+                eng.launches += 1 + ncam
+            else:
+                eps.copy_(ex["eps"])
+                for cam in cfg.cams:
+                    masks[cam].copy_(ex["dropout"][cam])
+        # ---- encoder passes: policy(s) with dropout [actor], critic input enc(s) [actor], policy(s') with dropout [temperature] ----
+        passes = []
+        if do_actor:
+            passes += [(obs_rows, eng.state_o, eng.Xp, F, eng.masks_u8, self.sle_p, "pa"), (obs_rows, eng.state_o, eng.Xc, FA, None, self.sle_c2, None)]
+        if do_temperature:
+            passes += [(next_rows, eng.state_n, self.Xp_t, F, self.masks_t, self.sle_t, None)]
+        sle, gemm, fin = [], [], []
+        for pi, (rows, state, X, ldx, masks, sles, save) in enumerate(passes):
+            for j, cam in enumerate(cfg.cams):
+                p = f"{ENC}/encoder_{cam}"
+                i = pi * ncam + j
+                sle.append((eng.feats[cam][rows].data_ptr(), P(Pm, f"{p}/SpatialLearnedEmbeddings_0/kernel"),
+                            None if masks is None else masks[cam].data_ptr(), sles[cam].data_ptr(), 4096))
+                gemm.append(ops.tgemm_problem(sles[cam].data_ptr(), P(Pm, f"{p}/Dense_0/kernel"), sAm=4096, sAk=1, sBk=256, sBn=1))
+                fin.append(dict(partials=self.ws_enc.buf.data_ptr() + 4 * i * S * B * 256, S=S, bias=P(Pm, f"{p}/Dense_0/bias"),
+                                ln_scale=P(Pm, f"{p}/LayerNorm_0/scale"), ln_bias=P(Pm, f"{p}/LayerNorm_0/bias"), out=ops.at(X, 256 * j), ld_out=ldx, D=256))
+        for rows, state, X, ldx, masks, sles, save in passes:
+            # the policy's stop_gradient leaves the proprio Dense / LayerNorm differentiable (encoding.py:48-70): keep its statistics
+            fin.append(dict(x=state.data_ptr(), ld_x=cfg.state_in, w=P(Pm, f"{ENC}/Dense_0/kernel"), K=cfg.state_in, bias=P(Pm, f"{ENC}/Dense_0/bias"),
+                            ln_scale=P(Pm, f"{ENC}/LayerNorm_0/scale"), ln_bias=P(Pm, f"{ENC}/LayerNorm_0/bias"), out=ops.at(X, 256 * ncam), ld_out=ldx, D=64,
+                            xhat=eng.enc_xhat_pa.data_ptr() if save == "pa" else None, rstd=eng.enc_rstd_pa.data_ptr() if save == "pa" else None))
+        ops.sle_fwd_multi(sle, 0.9, B, 16, 512)
+        ops.tgemm(self.ws_enc, gemm, B, 256, 4096, epilogue=L.TGEMM_PARTIAL, splits=S, error=err)
+        ops.enc_finish(fin, B)
+        # ---- policy MLP(s): layer 1, then layer 2 + heads + tanh-Gaussian sample ----
+        n, pa = "modules_actor/network", eng.p_acts
+        l1, l2 = [], []
+        if do_actor:
+            l1.append(ops.tgemm_problem(eng.Xp.data_ptr(), P(Pm, f"{n}/Dense_0/kernel"), sAm=F, sAk=1, sBk=256, sBn=1, C_=pa.h1.data_ptr(), ldc=256,
+                                        bias=P(Pm, f"{n}/Dense_0/bias"), ln_scale=P(Pm, f"{n}/LayerNorm_0/scale"), ln_bias=P(Pm, f"{n}/LayerNorm_0/bias"),
+                                        xhat=pa.xhat1.data_ptr(), rstd=pa.rstd1.data_ptr()))
+            l2.append(ops.tgemm_problem(pa.h1.data_ptr(), P(Pm, f"{n}/Dense_1/kernel"), sAm=256, sAk=1, sBk=256, sBn=1, C_=pa.h2.data_ptr(), ldc=256,
+                                        bias=P(Pm, f"{n}/Dense_1/bias"), ln_scale=P(Pm, f"{n}/LayerNorm_1/scale"), ln_bias=P(Pm, f"{n}/LayerNorm_1/bias"),
+                                        xhat=pa.xhat2.data_ptr(), rstd=pa.rstd2.data_ptr(),
+                                        head_w=P(Pm, "modules_actor/Dense_0/kernel"), head_b=P(Pm, "modules_actor/Dense_0/bias"), head_out=eng.mu.data_ptr(),
+                                        head_w2=P(Pm, "modules_actor/Dense_1/kernel"), head_b2=P(Pm, "modules_actor/Dense_1/bias"), head_out2=eng.ls.data_ptr(),
+                                        noise=eng.eps.data_ptr(), act=ops.at(eng.Xc, F), ld_act=FA, logp=eng.logp.data_ptr(), u_out=eng.u.data_ptr(),
+                                        std_out=eng.std.data_ptr()))
+        if do_temperature:
+            l1.append(ops.tgemm_problem(self.Xp_t.data_ptr(), P(Pm, f"{n}/Dense_0/kernel"), sAm=F, sAk=1, sBk=256, sBn=1, C_=self.h1_t.data_ptr(), ldc=256,
+                                        bias=P(Pm, f"{n}/Dense_0/bias"), ln_scale=P(Pm, f"{n}/LayerNorm_0/scale"), ln_bias=P(Pm, f"{n}/LayerNorm_0/bias")))
+            l2.append(ops.tgemm_problem(self.h1_t.data_ptr(), P(Pm, f"{n}/Dense_1/kernel"), sAm=256, sAk=1, sBk=256, sBn=1,
+                                        bias=P(Pm, f"{n}/Dense_1/bias"), ln_scale=P(Pm, f"{n}/LayerNorm_1/scale"), ln_bias=P(Pm, f"{n}/LayerNorm_1/bias"),
+                                        head_w=P(Pm, "modules_actor/Dense_0/kernel"), head_b=P(Pm, "modules_actor/Dense_0/bias"), head_out=self.act_t.data_ptr(),
+                                        head_w2=P(Pm, "modules_actor/Dense_1/kernel"), head_b2=P(Pm, "modules_actor/Dense_1/bias"),
+                                        noise=self.eps_t.data_ptr(), act=self.act_t.data_ptr(), ld_act=A, logp=self.logp_t.data_ptr()))
+        ops.tgemm(None, l1, B, 256, F, epilogue=L.TGEMM_LN_TANH, error=err)
+        ops.tgemm(None, l2, B, 256, 256, epilogue=L.TGEMM_LN_TANH_POLICY, head_n=A, std_min=cfg.std_min, std_max=cfg.std_max, error=err)
+        eng.launches += 5
+        if do_actor:
+            # ---- q = mean_e Q_e(s, pi(s)) with constant critic parameters; dQ/da through the same GEMMs ----
+            c, cm = "modules_critic/network", eng.c_main
+            R = E * B
+            eng.pol_state = eng.state_o
+            ops.tgemm(None, [ops.tgemm_problem(eng.Xc.data_ptr(), P(Pm, f"{c}/Dense_0/kernel"), sAm=FA, sAk=1, sBk=256, sBn=1, Z=E, sAz=0, sBz=FA * 256,
+                                               C_=cm.h1.data_ptr(), sCz=B * 256, ldc=256, bias=P(Pm, f"{c}/Dense_0/bias"), sBiasZ=256,
+                                               ln_scale=P(Pm, f"{c}/LayerNorm_0/scale"), ln_bias=P(Pm, f"{c}/LayerNorm_0/bias"), sLnZ=256,
+                                               xhat=cm.xhat1.data_ptr(), rstd=cm.rstd1.data_ptr(), sXhatZ=B * 256, sRstdZ=B)],
+                      B, 256, FA, epilogue=L.TGEMM_LN_TANH, error=err)
+            ops.tgemm(None, [ops.tgemm_problem(cm.h1.data_ptr(), P(Pm, f"{c}/Dense_1/kernel"), sAm=256, sAk=1, sBk=256, sBn=1, Z=E, sAz=B * 256, sBz=256 * 256,
+                                               C_=cm.h2.data_ptr(), sCz=B * 256, ldc=256, bias=P(Pm, f"{c}/Dense_1/bias"), sBiasZ=256,
+                                               ln_scale=P(Pm, f"{c}/LayerNorm_1/scale"), ln_bias=P(Pm, f"{c}/LayerNorm_1/bias"), sLnZ=256,
+                                               xhat=cm.xhat2.data_ptr(), rstd=cm.rstd2.data_ptr(), sXhatZ=B * 256, sRstdZ=B,
+                                               head_w=P(Pm, "modules_critic/Dense_0/kernel"), head_b=P(Pm, "modules_critic/Dense_0/bias"),
+                                               head_out=eng.q.data_ptr(), sHeadOutZ=B, ld_head=1)],
+                      B, 256, 256, epilogue=L.TGEMM_LN_TANH_HEAD, head_n=1, error=err)
+            ops.fill(eng.dq.data_ptr(), -grad_scale / (E * B), E * B)
+            ops.ln_tanh_bwd_multi([dict(dq=eng.dq.data_ptr(), head_w=P(Pm, "modules_critic/Dense_0/kernel"), head_w_stride=0, t=cm.h2.data_ptr(), ld_t=256,
+                                        xhat=cm.xhat2.data_ptr(), rstd=cm.rstd2.data_ptr(), scale=P(Pm, f"{c}/LayerNorm_1/scale"), rows_per_group=B,
+                                        group_stride=256, dz=eng.dz.data_ptr(), R=R, D=256)])
+            ops.tgemm(eng.ws, [ops.tgemm_problem(eng.dz.data_ptr(), P(Pm, f"{c}/Dense_1/kernel"), sAm=256, sAk=1, sBk=1, sBn=256, Z=E, sAz=B * 256, sBz=256 * 256,
+                                                 C_=eng.dh.data_ptr(), sCz=B * 256, ldc=256)], B, 256, 256, splits=1, error=err)
+            ops.ln_tanh_bwd_multi([dict(dt=eng.dh.data_ptr(), ld_dt=256, t=cm.h1.data_ptr(), ld_t=256, xhat=cm.xhat1.data_ptr(), rstd=cm.rstd1.data_ptr(),
+                                        scale=P(Pm, f"{c}/LayerNorm_0/scale"), rows_per_group=B, group_stride=256, dz=eng.dz0.data_ptr(), R=R, D=256)])
+            # dQ/da = sum_e dz1[e] @ W1[e][F:, :]^T: the action rows of the first layer only
+            ops.tgemm(eng.ws, [ops.tgemm_problem(eng.dz0.data_ptr(), P(Pm, f"{c}/Dense_0/kernel") + 4 * F * 256, sAm=256, sAk=1, sBk=1, sBn=256, Z=E,
+                                                 sAz=B * 256, sBz=FA * 256, C_=ops.at(eng.dX, F), sCz=0, ldc=FA)], B, A, 256, reduce_z=True, error=err)
+            ops.actor_loss(eng.q, eng.logp, lam, ops.at(eng.dX, F), FA, ops.at(eng.Xc, F), FA, eng.std, eng.ls, eng.eps, cfg.std_min, cfg.std_max, grad_scale,
+                           eng.dmu, eng.dls, ops.at(eng.info, 4), E, B, A)
+            eng.policy_backward(eng.Xp)
+            eng.launches += 9
+        if do_temperature:
+            ops.temperature_loss(self.logp_t, lam, cfg.target_entropy, grad_scale, P(st.grad, "modules_temperature/lagrange"), ops.at(eng.info, 8), B)
+            eng.launches += 1
+
     def check_error(self):
         if int(self.error.item()):
             raise L.SerlError("tgemm_tf32_kernel: pipeline barrier timeout (flagged by the kernel)")

@@ -258,3 +258,24 @@ def test_bc_agent_call_sequence(dry, precision):
     a = agent.sample_actions(batch["observations"], seed=np.array([0, 3], np.uint32))
     assert a.shape == (6, 4)
     agent.state.replace(params=tree)
+
+
+def test_fused_actor_temperature_call_sequence(dry, monkeypatch):
+    """Host logic of the fused actor / temperature step (heads_fused.py): encoder passes of both losses in one SLE / GEMM / finish
+    launch each, one launch per policy layer for both policy passes, critic forward + dQ/da on the TF32 GEMMs."""
+    monkeypatch.setenv("SERL_FUSED_HEADS", "force")
+    from serl_b200.utils.launcher import make_drq_agent
+    cams = ("front", "wrist")
+    rb = _ring(cams, 64, 128)
+    trs = random_transitions(np.random.default_rng(0), 40, cams, 128)
+    for tr in trs:
+        rb.insert(tr)
+    agent = make_drq_agent(1, trs[0]["observations"], trs[0]["actions"], image_keys=cams, encoder_type="resnet-pretrained", device="cpu", precision="fp16")
+    del dry[:]
+    agent, info = agent.update_high_utd(rb.sample(4, pack_obs_and_next_obs=True), utd_ratio=1)
+    assert set(info) >= {"critic", "actor", "temperature"}
+    assert dry.count("serl_sle_fwd_multi") == 2 and dry.count("serl_enc_finish") == 2                  # critic step + actor / temperature step
+    assert dry.count("serl_actor_loss") == 1 and dry.count("serl_temperature_loss") == 1 and dry.count("serl_critic_loss") == 1
+    assert dry.count("serl_tgemm_tf32") == 11 + (1 + 2 + 2 + 2)                                        # + encoder GEMM, 2 policy layers, 2 critic layers, dh1, dQ/da
+    assert dry.count("serl_layernorm_tanh_fwd") == 0 and dry.count("serl_sle_fwd") == 0
+    assert dry.count("serl_adam_polyak") == 2 and agent.state.step == 2

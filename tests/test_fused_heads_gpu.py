@@ -116,3 +116,41 @@ def test_learner_iteration_on_the_fp16_build_mixes_fused_critic_and_per_op_actor
         assert close(info["temperature"]["temperature_loss"], oi["temperature"]["temperature_loss"])
         np.testing.assert_array_equal(agent.state.rng, ostate.rng)
     agent.check_status()
+
+
+def test_fused_actor_temperature_step_matches_per_op_chain(monkeypatch):
+    """update(networks_to_update={actor, temperature}) on the fused forward kernels vs SERL_FUSED_ACTOR=0 (per-op chain) from the same
+    state, batch and keys: actions, log-probs, Q, every actor / temperature gradient leaf and the proprio encoder's actor-tx twin."""
+    cams, B = ("front", "wrist"), 24
+    agent, rb = _setup(cams)
+    ref_agent, _ = _setup(cams)
+    it = rb.get_iterator(sample_args={"batch_size": B, "pack_obs_and_next_obs": True})
+    nets = frozenset({"actor", "temperature"})
+    for step in range(2):
+        for a, b in ((ref_agent._store.params, agent._store.params), (ref_agent._store.target, agent._store.target), (ref_agent._store.m, agent._store.m),
+                     (ref_agent._store.v, agent._store.v), (ref_agent._store.counts, agent._store.counts), (ref_agent.state._rng, agent.state._rng)):
+            a.copy_(b)
+        bd = {k: v for k, v in next(it).to_dict().items() if k != "_indices"}
+        agent, info = agent.update(bd, networks_to_update=nets)
+        monkeypatch.setenv("SERL_FUSED_ACTOR", "0")
+        ref_agent, rinfo = ref_agent.update(bd, networks_to_update=nets)
+        monkeypatch.delenv("SERL_FUSED_ACTOR")
+        eng, reng = agent._engines[B], ref_agent._engines[B]
+        F = eng.F
+        assert rel_err(eng.Xc[:, F:].cpu().numpy(), reng.Xc[:, F:].cpu().numpy().astype(np.float64)) < 5e-3          # pi(s)
+        # (the per-op chain reuses one log-prob buffer: after the call it holds the temperature pass's, the fused path keeps both)
+        assert rel_err(eng.fused.logp_t.cpu().numpy(), reng.logp.cpu().numpy().astype(np.float64)) < 5e-3
+        assert rel_err(eng.q.cpu().numpy(), reng.q.cpu().numpy().astype(np.float64)) < 5e-3
+        for k in ("actor_loss", "temperature", "entropy"):
+            assert abs(float(info["actor"][k]) - float(rinfo["actor"][k])) <= 5e-3 * max(abs(float(rinfo["actor"][k])), 1e-2), k
+        assert abs(float(info["temperature"]["temperature_loss"]) - float(rinfo["temperature"]["temperature_loss"])) <= 5e-3 * max(abs(float(rinfo["temperature"]["temperature_loss"])), 1e-3)
+        st, rst = agent._store, ref_agent._store
+        for leaf in st.spec:
+            if leaf.group == 0:
+                continue
+            got, ref = st.view(st.grad, leaf.path).cpu().numpy(), rst.view(rst.grad, leaf.path).cpu().numpy().astype(np.float64)
+            assert np.abs(got - ref).max() <= 1e-2 * max(np.abs(ref).max(), 1e-12), leaf.path
+        for path in ("modules_actor/encoder/Dense_0/kernel", "modules_actor/encoder/LayerNorm_0/scale"):
+            got, ref = st.aux_view(st.grad, path).cpu().numpy(), rst.aux_view(rst.grad, path).cpu().numpy().astype(np.float64)
+            assert np.abs(ref).max() > 0 and np.abs(got - ref).max() <= 1e-2 * np.abs(ref).max(), path
+    agent.check_status()
