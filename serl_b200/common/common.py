@@ -90,6 +90,7 @@ class TrainState:
         if "rng" in kw:
             key = np.ascontiguousarray(np.asarray(kw.pop("rng")), dtype=np.uint32).reshape(2)
             self._rng.copy_(torch.from_numpy(key.view(np.int32)).view(torch.uint32))
+            st.version += 1               # the step pipeline's look-ahead key chain (and any prefetched batch) is stale: agents re-check the version
         if "step" in kw:
             self.step = int(kw.pop("step"))
         if "opt_states" in kw:
