@@ -28,6 +28,7 @@ int serl_stem_v2_active(void);                /* 1: the fused stem uses the TMA-
 int serl_version(void);                       /* ABI version, bumped on signature changes */
 unsigned long long serl_launch_count(void);   /* kernels this library has enqueued in this process (graph capture included) */
 int serl_device_sm_count(int device);         /* host query used to size persistent grids */
+int serl_balanced_grid(int items, int sms);   /* CTAs of a persistent one-CTA-per-SM kernel over `items` work items: the smallest grid with as few waves as min(items, sms) CTAs */
 
 /* ---- replay ring in HBM ---------------------------------------------------------------------
  * Storage layout of data/replay_buffer.py:41-66 + data/memory_efficient_replay_buffer.py:13-51:

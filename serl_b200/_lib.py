@@ -183,7 +183,7 @@ _PROTOS = {
     "serl_temperature_loss": [vp, vp, f32, f32, vp, vp, C.c_int, vp],
     "serl_adam_polyak": [C.POINTER(AdamDesc), vp],
 }
-EXPORTS = sorted(list(_PROTOS) + ["serl_last_error", "serl_version", "serl_device_sm_count", "serl_launch_count", "serl_stem_v2_active"])
+EXPORTS = sorted(list(_PROTOS) + ["serl_last_error", "serl_version", "serl_device_sm_count", "serl_launch_count", "serl_stem_v2_active", "serl_balanced_grid"])
 
 _lib = None
 
