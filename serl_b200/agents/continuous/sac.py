@@ -426,6 +426,7 @@ class SACAgent:
     def update_high_utd(self, batch, *, utd_ratio: int, pmap_axis: Optional[str] = None, _augment: bool = False):
         """sac.py:544-596: utd_ratio critic updates on consecutive minibatches, then one actor+temperature update
         on the full batch."""
+        self._pipe, self._keys = None, self._keys_pair[0]          # consumes the key chain: a prefetched next batch is stale
         B = batch.batch_size if isinstance(batch, BatchHandle) else int(np.asarray(_leaf(batch, "rewards")).shape[0])
         assert B % utd_ratio == 0, f"Batch size {B} must be divisible by UTD ratio {utd_ratio}"
         full = self._engine(B)
