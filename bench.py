@@ -125,7 +125,7 @@ def run_reference(args):
     line = {"metric": "drq_critic_grad_steps_per_sec", "value": v, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {k: v_ for k, v_ in workload_config(args).items() if k != "step_pipeline"},     # (a GPU-arm scheduling note)
+            "config": workload_config(args),
             "cpu_baseline": {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample,
                              "extrapolated_x": args.batch / args.ref_rows},
             "e2e": {"value": v, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
