@@ -1,5 +1,7 @@
 #!/bin/bash
 # One GPU-box round trip: parity tests, smoke, short bench, ncu launch list (+ DRAM bytes).  Everything lands in gpurun_out/.
+# (Written before the round-2 kernels became the default: SERL_STEM_V2 / SERL_RES_CONV / SERL_RES_S2 / SERL_CAM_STREAMS are now ON unless set to 0,
+# so the "switched on" sections below repeat the default path; scripts/gpu_final.sh is the round-end script.)
 set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,memory.total,clocks.max.sm --format=csv > gpurun_out/gpu.txt 2>&1
